@@ -1,0 +1,168 @@
+/*
+ * sbwt_b200.h -- C ABI of the B200-native plain-matrix SBWT k-mer query path.
+ *
+ * This is the drop-in boundary for ONE path of algbio/SBWT (paths relative to
+ * the reference root): the plain-matrix index's k-mer membership queries,
+ *   SubsetMatrixRank::rank            include/sbwt/SubsetMatrixRank.hh:31-37
+ *   SBWT::update_sbwt_interval        include/sbwt/SBWT.hh:423-437
+ *   SBWT::search                      include/sbwt/SBWT.hh:390-415
+ *   SBWT::streaming_search            include/sbwt/SBWT.hh:545-581
+ *   SBWT::load (plain-matrix file)    include/sbwt/SBWT.hh:501-516, SubsetMatrixRank.hh:102-125
+ *   get_char_idx / DNA_to_char_idx    include/sbwt/SBWT.hh:49-57, globals.hh:38-47
+ * The reference has no FFI; the C++ mirror of its template surface
+ * (sbwt_b200/csrc/SBWT.hh) and the `sbwt search` command line
+ * (sbwt_b200/csrc/cli_search.cpp) are thin callers of exactly these entry
+ * points. INTEGRATION.md shows the binding a maintainer of the reference adds.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success and nonzero on failure, with the message available from
+ * sbwt_gpu_last_error() (thread-local); no C++ exception crosses the boundary;
+ * there is NO CPU fallback -- without a CUDA device every compute entry point
+ * fails.  Results are bit-exact with the reference: one int64 per k-mer, the
+ * colex rank of its column, or -1.
+ */
+#ifndef SBWT_B200_H
+#define SBWT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBWT_B200_ABI_VERSION 1
+
+/* Which reference entry point a batch call mirrors. */
+#define SBWT_GPU_MODE_SEARCH 0    /* SBWT::search on every k-mer start (sbwt_search.cpp:67-91)      */
+#define SBWT_GPU_MODE_STREAMING 1 /* SBWT::streaming_search per read   (sbwt_search.cpp:45-65)      */
+
+/* How read bytes are interpreted (the "packer", reference row H). */
+#define SBWT_GPU_CASE_UPPER 0 /* a-z folded to A-Z first: what the index sees through `sbwt search`,
+                                 where seq_io::Reader upper-cases every base (SeqIO.hh:294-297,330-333) */
+#define SBWT_GPU_CASE_EXACT 1 /* only the bytes 'A','C','G','T' are valid: SBWT::search() called
+                                 directly on a caller's buffer (SBWT.hh:427, globals.hh:38-47)         */
+
+typedef struct sbwt_gpu_index sbwt_gpu_index;     /* one device-resident index (index, device)         */
+typedef struct sbwt_gpu_session sbwt_gpu_session; /* scratch + streams for batches against one index   */
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char *sbwt_gpu_last_error(void);
+/* Number of CUDA devices, or 0 when there is no usable device / driver. */
+int sbwt_gpu_device_count(void);
+int sbwt_gpu_abi_version(void);
+
+/* ---- index ------------------------------------------------------------- */
+
+/* Replaces SBWT(A,C,G,T,streaming_support,k,n_kmers,precalc_k) + the four rank_support_v5
+ * constructors (SBWT.hh:336-353, rank_support_v5.hpp:65-109): copies the four n_nodes-bit
+ * vectors (LSB-first 64-bit words, ceil(n_nodes/64) words each) to `device` and re-lays them
+ * there as interleaved count+payload sectors. suffix_group_starts may be NULL (index built with
+ * --no-streaming-support). precalc_lr holds 4^precalc_k pairs (l,r) as in
+ * SBWT::kmer_prefix_precalc (may be NULL iff precalc_k == 0). The caller keeps its arrays. */
+int sbwt_gpu_index_create(const uint64_t *const bits[4], const uint64_t *suffix_group_starts,
+                          int64_t n_nodes, int64_t n_kmers, int64_t k, const int64_t C[4],
+                          const int64_t *precalc_lr, int64_t precalc_k, int device,
+                          sbwt_gpu_index **out);
+/* Replaces the variant-string read of sbwt_search.cpp:194-199 + plain_matrix_sbwt_t::load:
+ * parses a serialized plain-matrix .sbwt file bit-for-bit and creates the device index. */
+int sbwt_gpu_index_load(const char *path, int device, sbwt_gpu_index **out);
+void sbwt_gpu_index_destroy(sbwt_gpu_index *idx);
+
+/* Accessors mirroring SBWT.hh:111-157,253. */
+int64_t sbwt_gpu_index_k(const sbwt_gpu_index *idx);
+int64_t sbwt_gpu_index_n_nodes(const sbwt_gpu_index *idx);   /* number_of_subsets() */
+int64_t sbwt_gpu_index_n_kmers(const sbwt_gpu_index *idx);   /* number_of_kmers()   */
+int64_t sbwt_gpu_index_precalc_k(const sbwt_gpu_index *idx); /* get_precalc_k()     */
+int sbwt_gpu_index_has_streaming_support(const sbwt_gpu_index *idx);
+int sbwt_gpu_index_device(const sbwt_gpu_index *idx);
+void sbwt_gpu_index_C(const sbwt_gpu_index *idx, int64_t C[4]); /* get_C_array() */
+/* Bytes of device memory held by the re-laid index (sectors + tables + suffix-group bits). */
+int64_t sbwt_gpu_index_device_bytes(const sbwt_gpu_index *idx);
+/* 1 if every non-suffix-group-start column has an empty subset (true for every index the
+ * reference builds; lets the streaming step use one sector instead of a walk-back). */
+int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index *idx);
+
+/* SubsetMatrixRank::rank(pos, c) for n host-side queries (positions in [0, n_nodes], chars
+ * as bytes; any byte outside ACGT gives 0). Small-batch diagnostic / parity entry point. */
+int sbwt_gpu_rank(sbwt_gpu_index *idx, const int64_t *pos, const char *chars, int64_t n, int64_t *out);
+
+/* ---- batches ----------------------------------------------------------- */
+
+/* A session owns the device scratch (packed reads, plan, staging) for batches of at most
+ * max_bases read bytes and max_reads reads per device-side launch; host-side calls of any size
+ * are chunked to fit. One session per host thread; sessions on one index are independent. */
+int sbwt_gpu_session_create(sbwt_gpu_index *idx, int64_t max_bases, int64_t max_reads,
+                            sbwt_gpu_session **out);
+void sbwt_gpu_session_destroy(sbwt_gpu_session *s);
+
+/* Number of results a batch produces: sum over reads of max(0, len - k + 1). Host arrays. */
+int64_t sbwt_gpu_count_outputs(const int64_t *read_offsets, int64_t n_reads, int64_t k);
+
+/* Host-buffer batch (the call `sbwt search` makes): reads are concatenated in `ascii`, read i
+ * is ascii[read_offsets[i] .. read_offsets[i+1]) (read_offsets[0] need not be 0). Writes
+ * sbwt_gpu_count_outputs() int64 values to `out`, read after read -- the concatenation of the
+ * vectors SBWT::streaming_search / the search() loop return. Copies H2D, packs, walks and copies
+ * D2H through pinned staging buffers in a double-buffered pipeline. MODE_STREAMING on an index
+ * without streaming support fails like the reference ("streaming search support not built"). */
+int sbwt_gpu_query_host(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,
+                        int64_t n_reads, int mode, int case_mode, int64_t *out);
+
+/* Device-buffer batch: d_ascii / d_read_offsets / d_out are device pointers on the index's
+ * device, read_offsets[0] == 0, n_bases == read_offsets[n_reads] <= max_bases, n_reads <=
+ * max_reads; d_out holds n_out == count_outputs values. Enqueues pack -> plan -> walk on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream) and returns without synchronising. */
+int sbwt_gpu_query_device(sbwt_gpu_session *s, const char *d_ascii, const int64_t *d_read_offsets,
+                          int64_t n_reads, int64_t n_bases, int mode, int case_mode,
+                          int64_t *d_out, int64_t n_out, void *cuda_stream);
+
+/* The two names of the reference API, as thin wrappers of sbwt_gpu_query_host with CASE_UPPER. */
+int sbwt_gpu_search_batch(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,
+                          int64_t n_reads, int64_t *out);
+int sbwt_gpu_streaming_batch(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,
+                             int64_t n_reads, int64_t *out);
+
+/* Page-locked host memory for the buffers handed to sbwt_gpu_query_host: pinned buffers are
+ * DMA'd directly, pageable ones are staged through the session's own pinned buffers. */
+int sbwt_gpu_host_alloc(size_t bytes, void **out);
+void sbwt_gpu_host_free(void *p);
+
+/* The packer alone (device buffers): 2-bit codes, 32 bases per u64 word, and one invalid bit
+ * per base, 32 per u32 word; both arrays need n_bases/32 + 4 words. Asynchronous. */
+int sbwt_gpu_pack_device(const char *d_ascii, int64_t n_bases, int case_mode, uint64_t *d_codes,
+                         uint32_t *d_invalid, void *cuda_stream);
+
+/* ---- measurement ------------------------------------------------------- */
+
+typedef struct sbwt_gpu_stats {
+    int64_t lookups;      /* results produced                                                       */
+    int64_t hits;         /* results >= 0                                                           */
+    int64_t rank_ops;     /* rank evaluations with the reference's accounting: 2 per interval step  */
+    int64_t index_sectors; /* distinct 32-byte index sectors the walk had to read (incl. table rows) */
+    int64_t kernel_launches; /* kernels of this library launched by the counted call               */
+} sbwt_gpu_stats;
+
+/* Same work as sbwt_gpu_query_device but with counting kernels; synchronises and fills `st`.
+ * For the roofline's algorithmic bytes; never inside a timed region. */
+int sbwt_gpu_query_device_counted(sbwt_gpu_session *s, const char *d_ascii, const int64_t *d_read_offsets,
+                                  int64_t n_reads, int64_t n_bases, int mode, int case_mode,
+                                  int64_t *d_out, int64_t n_out, void *cuda_stream, sbwt_gpu_stats *st);
+/* Per-kernel timing of device-buffer batches: when enabled, sbwt_gpu_query_device records CUDA
+ * events on the launching stream before the packer, before the walk kernel and after it;
+ * last_timing waits for the last batch and returns the two intervals in milliseconds. */
+int sbwt_gpu_session_set_timing(sbwt_gpu_session *s, int enable);
+int sbwt_gpu_session_last_timing(sbwt_gpu_session *s, double *prep_ms, double *walk_ms);
+/* Kernels launched by this library on the calling thread since the last reset. */
+int64_t sbwt_gpu_launch_count(int reset);
+
+/* Random 32-byte (or 64-byte) sector gather micro-benchmark: `n_loads` independent loads of
+ * `bytes_per_load` (32 or 64) at uniformly random aligned offsets inside a device buffer of
+ * buffer_bytes, repeated `iters` times; returns the best time in milliseconds. Gives the
+ * random-sector ceilings (DRAM-resident and L2-resident buffers) the roofline is quoted against. */
+int sbwt_gpu_sector_probe(int device, int64_t buffer_bytes, int64_t n_loads, int bytes_per_load,
+                          int iters, double *best_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

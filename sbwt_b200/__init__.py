@@ -1,0 +1,253 @@
+"""sbwt_b200 -- B200-native (sm_100a) plain-matrix SBWT k-mer query path.
+
+This module is only the ctypes view of the C ABI declared in include/sbwt_b200.h
+(built from sbwt_b200/csrc into sbwt_b200/libsbwt_b200.so). The product is the
+shared library; Python is test / bench plumbing. There is no CPU fallback: if the
+library is missing, or there is no CUDA device, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsbwt_b200.so")
+
+MODE_SEARCH = 0
+MODE_STREAMING = 1
+CASE_UPPER = 0
+CASE_EXACT = 1
+
+EXPORTS = [
+    "sbwt_gpu_last_error", "sbwt_gpu_device_count", "sbwt_gpu_abi_version",
+    "sbwt_gpu_index_create", "sbwt_gpu_index_load", "sbwt_gpu_index_destroy",
+    "sbwt_gpu_index_k", "sbwt_gpu_index_n_nodes", "sbwt_gpu_index_n_kmers", "sbwt_gpu_index_precalc_k",
+    "sbwt_gpu_index_has_streaming_support", "sbwt_gpu_index_device", "sbwt_gpu_index_C",
+    "sbwt_gpu_index_device_bytes", "sbwt_gpu_index_edges_only_at_group_starts", "sbwt_gpu_rank",
+    "sbwt_gpu_session_create", "sbwt_gpu_session_destroy", "sbwt_gpu_count_outputs",
+    "sbwt_gpu_query_host", "sbwt_gpu_query_device", "sbwt_gpu_search_batch", "sbwt_gpu_streaming_batch",
+    "sbwt_gpu_host_alloc", "sbwt_gpu_host_free", "sbwt_gpu_pack_device",
+    "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
+    "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [("lookups", C.c_int64), ("hits", C.c_int64), ("rank_ops", C.c_int64),
+                ("index_sectors", C.c_int64), ("kernel_launches", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library. Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "or `make -C sbwt_b200/csrc`. The SBWT GPU query path has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+        L.sbwt_gpu_last_error.restype = C.c_char_p
+        L.sbwt_gpu_index_create.argtypes = [C.POINTER(vp), vp, i64, i64, i64, vp, vp, i64, i32, C.POINTER(vp)]
+        L.sbwt_gpu_index_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+        L.sbwt_gpu_index_destroy.argtypes = [vp]
+        L.sbwt_gpu_index_destroy.restype = None
+        for name in ("k", "n_nodes", "n_kmers", "precalc_k", "device_bytes"):
+            f = getattr(L, "sbwt_gpu_index_" + name)
+            f.argtypes, f.restype = [vp], i64
+        for name in ("has_streaming_support", "device", "edges_only_at_group_starts"):
+            f = getattr(L, "sbwt_gpu_index_" + name)
+            f.argtypes, f.restype = [vp], i32
+        L.sbwt_gpu_index_C.argtypes = [vp, vp]
+        L.sbwt_gpu_index_C.restype = None
+        L.sbwt_gpu_rank.argtypes = [vp, vp, vp, i64, vp]
+        L.sbwt_gpu_session_create.argtypes = [vp, i64, i64, C.POINTER(vp)]
+        L.sbwt_gpu_session_destroy.argtypes = [vp]
+        L.sbwt_gpu_session_destroy.restype = None
+        L.sbwt_gpu_count_outputs.argtypes = [vp, i64, i64]
+        L.sbwt_gpu_count_outputs.restype = i64
+        L.sbwt_gpu_query_host.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+        L.sbwt_gpu_query_device.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp, i64, vp]
+        L.sbwt_gpu_query_device_counted.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp, i64, vp, C.POINTER(Stats)]
+        L.sbwt_gpu_search_batch.argtypes = [vp, vp, vp, i64, vp]
+        L.sbwt_gpu_streaming_batch.argtypes = [vp, vp, vp, i64, vp]
+        L.sbwt_gpu_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        L.sbwt_gpu_host_free.argtypes = [vp]
+        L.sbwt_gpu_host_free.restype = None
+        L.sbwt_gpu_pack_device.argtypes = [vp, i64, i32, vp, vp, vp]
+        L.sbwt_gpu_session_set_timing.argtypes = [vp, i32]
+        L.sbwt_gpu_session_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.sbwt_gpu_launch_count.argtypes = [i32]
+        L.sbwt_gpu_launch_count.restype = i64
+        L.sbwt_gpu_sector_probe.argtypes = [i32, i64, i64, i32, i32, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+class SbwtGpuError(RuntimeError):
+    pass
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise SbwtGpuError(lib().sbwt_gpu_last_error().decode())
+
+
+def device_count() -> int:
+    return lib().sbwt_gpu_device_count()
+
+
+def launch_count(reset: bool = False) -> int:
+    return lib().sbwt_gpu_launch_count(int(reset))
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """A numpy array in page-locked host memory (sbwt_gpu_host_alloc); freed with the array."""
+    dtype = np.dtype(dtype)
+    p = C.c_void_p()
+    _check(lib().sbwt_gpu_host_alloc(max(1, n * dtype.itemsize), C.byref(p)))
+    buf = (C.c_char * max(1, n * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().sbwt_gpu_host_free(self.ptr)
+            except Exception:
+                pass
+
+    _OWNERS[arr.ctypes.data] = _Owner(p)
+    return arr
+
+
+_OWNERS: dict = {}
+
+
+def release_pinned(arr: np.ndarray) -> None:
+    _OWNERS.pop(arr.ctypes.data, None)
+
+
+class Index:
+    """A plain-matrix SBWT index resident on one GPU (sbwt_gpu_index)."""
+
+    def __init__(self, path: str | None = None, device: int = 0, *, arrays: dict | None = None):
+        self._h = C.c_void_p()
+        if path is not None:
+            _check(lib().sbwt_gpu_index_load(os.fsencode(path), device, C.byref(self._h)))
+        else:
+            a = arrays
+            bits = [np.ascontiguousarray(b, dtype=np.uint64) for b in a["bits"]]
+            ptrs = (C.c_void_p * 4)(*[b.ctypes.data for b in bits])
+            sgs = a.get("sgs")
+            sgs = None if sgs is None else np.ascontiguousarray(sgs, dtype=np.uint64)
+            Carr = np.ascontiguousarray(a["C"], dtype=np.int64)
+            pre = a.get("precalc")
+            pre = None if pre is None or a.get("precalc_k", 0) == 0 else np.ascontiguousarray(pre, dtype=np.int64)
+            _check(lib().sbwt_gpu_index_create(ptrs, None if sgs is None else sgs.ctypes.data, a["n_nodes"], a["n_kmers"], a["k"],
+                                               Carr.ctypes.data, None if pre is None else pre.ctypes.data, a.get("precalc_k", 0),
+                                               device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sbwt_gpu_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    k = property(lambda s: lib().sbwt_gpu_index_k(s._h))
+    n_nodes = property(lambda s: lib().sbwt_gpu_index_n_nodes(s._h))
+    n_kmers = property(lambda s: lib().sbwt_gpu_index_n_kmers(s._h))
+    precalc_k = property(lambda s: lib().sbwt_gpu_index_precalc_k(s._h))
+    has_streaming_support = property(lambda s: bool(lib().sbwt_gpu_index_has_streaming_support(s._h)))
+    device = property(lambda s: lib().sbwt_gpu_index_device(s._h))
+    device_bytes = property(lambda s: lib().sbwt_gpu_index_device_bytes(s._h))
+    edges_only_at_group_starts = property(lambda s: bool(lib().sbwt_gpu_index_edges_only_at_group_starts(s._h)))
+
+    @property
+    def C_array(self):
+        out = np.zeros(4, dtype=np.int64)
+        lib().sbwt_gpu_index_C(self._h, out.ctypes.data)
+        return out.tolist()
+
+    def rank(self, pos, chars: bytes) -> np.ndarray:
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        assert len(chars) == pos.size
+        out = np.empty(pos.size, dtype=np.int64)
+        _check(lib().sbwt_gpu_rank(self._h, pos.ctypes.data, chars, pos.size, out.ctypes.data))
+        return out
+
+
+class Session:
+    """Scratch + streams for batches against one index (sbwt_gpu_session)."""
+
+    def __init__(self, index: Index, max_bases: int, max_reads: int):
+        self.index = index
+        self._h = C.c_void_p()
+        _check(lib().sbwt_gpu_session_create(index._h, max_bases, max_reads, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sbwt_gpu_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def count_outputs(self, offsets: np.ndarray) -> int:
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        return lib().sbwt_gpu_count_outputs(offsets.ctypes.data, offsets.size - 1, self.index.k)
+
+    def query_host(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER,
+                   out: np.ndarray | None = None) -> np.ndarray:
+        """sbwt_gpu_query_host: host buffers in, int64 results out (H2D + pack + walk + D2H)."""
+        assert ascii_.dtype == np.uint8 and ascii_.flags.c_contiguous
+        assert offsets.dtype == np.int64 and offsets.flags.c_contiguous
+        n_out = self.count_outputs(offsets)
+        if out is None:
+            out = np.empty(n_out, dtype=np.int64)
+        assert out.dtype == np.int64 and out.size >= n_out
+        _check(lib().sbwt_gpu_query_host(self._h, ascii_.ctypes.data, offsets.ctypes.data, offsets.size - 1, mode, case_mode,
+                                         out.ctypes.data))
+        return out[:n_out]
+
+    def query_device(self, d_ascii: int, d_offsets: int, n_reads: int, n_bases: int, mode: int, d_out: int, n_out: int,
+                     stream: int = 0, case_mode: int = CASE_UPPER) -> None:
+        """sbwt_gpu_query_device: raw device pointers, asynchronous on `stream`."""
+        _check(lib().sbwt_gpu_query_device(self._h, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, n_out, stream))
+
+    def set_timing(self, enable: bool = True) -> None:
+        _check(lib().sbwt_gpu_session_set_timing(self._h, int(enable)))
+
+    def last_timing(self) -> tuple[float, float]:
+        """(prep_ms, walk_ms) of the last device-buffer batch: packer+plan, and the walk kernel."""
+        a, b = C.c_double(), C.c_double()
+        _check(lib().sbwt_gpu_session_last_timing(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def query_device_counted(self, d_ascii: int, d_offsets: int, n_reads: int, n_bases: int, mode: int, d_out: int, n_out: int,
+                             stream: int = 0, case_mode: int = CASE_UPPER) -> Stats:
+        st = Stats()
+        _check(lib().sbwt_gpu_query_device_counted(self._h, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, n_out,
+                                                   stream, C.byref(st)))
+        return st
+
+
+def sector_probe(device: int, buffer_bytes: int, n_loads: int, bytes_per_load: int = 32, iters: int = 3) -> float:
+    """Random aligned-sector gather rate: returns loads per second."""
+    ms = C.c_double()
+    _check(lib().sbwt_gpu_sector_probe(device, buffer_bytes, n_loads, bytes_per_load, iters, C.byref(ms)))
+    return n_loads / (ms.value * 1e-3)

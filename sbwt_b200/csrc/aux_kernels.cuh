@@ -1,0 +1,278 @@
+// aux_kernels.cuh -- everything on the device except the walk itself:
+//   K1  pack_kernel       ASCII -> 2-bit codes + invalid mask   (replaces get_char_idx / DNA_to_char_idx,
+//                         SBWT.hh:49-57, globals.hh:38-47, and SeqIO's per-byte upper-casing, SeqIO.hh:44-45)
+//   plan_* kernels        per-read result counts, exclusive scans, work items
+//   K0  index build       block popcounts -> scan -> sectors     (replaces rank_support_v5's constructor,
+//                         rank_support_v5.hpp:65-109)
+//   rank_kernel           SubsetMatrixRank::rank for the diagnostic entry point
+//   probe_kernel          random-sector gather micro-benchmark
+#pragma once
+
+#include "device_index.cuh"
+
+namespace sbwt_b200 {
+
+// ------------------------------------------------------------------ K1: packer
+
+// 4 ASCII bytes in a word -> 4 two-bit codes in the low byte and 4 invalid flags in the low nibble.
+// code = ((ch >> 1) ^ (ch >> 2)) & 3 maps A,C,G,T -> 0,1,2,3 (and a,c,g,t likewise).
+__device__ __forceinline__ void pack4(uint32_t x, uint32_t fold, uint32_t& codes, uint32_t& inval) {
+    const uint32_t u = x & fold; // fold = 0xDFDFDFDF folds a-z onto A-Z; 0xFFFFFFFF keeps the byte exact
+    const uint32_t c = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+    // the character each code stands for: A=0x41, C=0x43, G=0x47, T=0x54
+    const uint32_t lo = c & 0x01010101u, hi = (c >> 1) & 0x01010101u;
+    const uint32_t expect = 0x41414141u + lo * 2u + hi * 6u + (lo & hi) * 11u;
+    const uint32_t ok = __vcmpeq4(u, expect); // 0xFF per valid byte
+    inval = (((~ok) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
+    codes = (c * 0x01041040u) >> 24;
+}
+
+// One thread packs 32 bases: two 16-byte loads, one u64 + one u32 store. n_words covers the
+// padding words as well (they are written as "all invalid").
+template <bool VEC>
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ ascii, int64_t n_bases, uint32_t fold,
+                                                   uint64_t* __restrict__ codes, uint32_t* __restrict__ invalid,
+                                                   int64_t n_words) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_words) return;
+    const int64_t g = t << 5;
+    uint64_t cw = 0;
+    uint32_t iw = 0;
+    if (VEC && g + 32 <= n_bases) {
+        const uint4* src = reinterpret_cast<const uint4*>(ascii + g);
+        uint4 q[2];
+        q[0] = __ldcs(src);
+        q[1] = __ldcs(src + 1);
+        const uint32_t* x = reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t c, v;
+            pack4(x[i], fold, c, v);
+            cw |= (uint64_t)c << (8 * i);
+            iw |= v << (4 * i);
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 8; i++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int64_t pos = g + 4 * i + b;
+                const uint32_t ch = pos < n_bases ? ascii[pos] : 0u; // beyond the end: invalid
+                x |= ch << (8 * b);
+            }
+            uint32_t c, v;
+            pack4(x, fold, c, v);
+            cw |= (uint64_t)c << (8 * i);
+            iw |= v << (4 * i);
+        }
+    }
+    codes[t] = cw;
+    invalid[t] = iw;
+}
+
+// ------------------------------------------------------------------ scans
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t* total) {
+    __shared__ int64_t warp_sums[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < kScanThreads / 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= o) w += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int64_t base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[kScanThreads / 32 - 1];
+    __syncthreads();
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int64_t* __restrict__ data, int64_t n,
+                                                                   int64_t* __restrict__ partials) {
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++)
+        if (base + i < n) s += data[base + i];
+    int64_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the partials in place; grand total to *total_out
+__global__ void __launch_bounds__(kScanThreads) scan_partials_kernel(int64_t* __restrict__ partials, int64_t n,
+                                                                     int64_t* __restrict__ total_out) {
+    int64_t carry = 0;
+    for (int64_t base = 0; base < n; base += kScanThreads) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = i < n ? partials[i] : 0;
+        int64_t total;
+        const int64_t ex = block_exclusive_scan(v, &total);
+        if (i < n) partials[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(int64_t* __restrict__ data, int64_t n,
+                                                                  const int64_t* __restrict__ partials) {
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t v[kScanItems];
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        v[i] = base + i < n ? data[base + i] : 0;
+        s += v[i];
+    }
+    int64_t total;
+    int64_t run = block_exclusive_scan(s, &total) + partials[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        if (base + i < n) data[base + i] = run;
+        run += v[i];
+    }
+}
+
+// ------------------------------------------------------------------ plan
+
+// per read: number of results and number of work items (windows of at most `window` k-mers)
+__global__ void __launch_bounds__(256) plan_count_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k,
+                                                         int window, int64_t* __restrict__ n_out,
+                                                         int64_t* __restrict__ n_win) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int64_t len = offsets[r + 1] - offsets[r];
+    const int64_t nk = len >= k ? len - k + 1 : 0;
+    n_out[r] = nk;
+    n_win[r] = (nk + window - 1) / window;
+}
+
+// per read: emit its work items. out_off / win_off are the exclusive scans of the counts.
+__global__ void __launch_bounds__(256) plan_emit_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k,
+                                                        int window, const int64_t* __restrict__ out_off,
+                                                        const int64_t* __restrict__ win_off, int64_t out_base,
+                                                        int64_t* __restrict__ item_base, int64_t* __restrict__ item_out,
+                                                        int32_t* __restrict__ item_cnt) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int64_t start = offsets[r] - offsets[0];
+    const int64_t len = offsets[r + 1] - offsets[r];
+    const int64_t nk = len >= k ? len - k + 1 : 0;
+    int64_t it = win_off[r];
+    for (int64_t done = 0; done < nk; done += window, it++) {
+        item_base[it] = start + done;
+        item_out[it] = out_base + out_off[r] + done;
+        item_cnt[it] = (int32_t)(nk - done < window ? nk - done : window);
+    }
+}
+
+// ------------------------------------------------------------------ K0: index build
+
+// raw[c] = bit vector c as u32 words, zero padded to n_blocks * 7 words
+__global__ void __launch_bounds__(256) k0_block_popcount_kernel(const uint32_t* __restrict__ raw, int64_t words_per_vec,
+                                                                int64_t n_blocks, int64_t* __restrict__ counts) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4 * n_blocks) return;
+    const int64_t c = t / n_blocks, b = t - c * n_blocks;
+    const uint32_t* w = raw + c * words_per_vec + b * kPayloadWords;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kPayloadWords; i++) s += __popc(w[i]);
+    counts[t] = s;
+}
+
+// prefix[c][b] = ones of vector c before block b (exclusive scan of counts, per vector)
+__global__ void __launch_bounds__(256) k0_emit_kernel(const uint32_t* __restrict__ raw, int64_t words_per_vec,
+                                                      int64_t n_blocks, const int64_t* __restrict__ prefix,
+                                                      int64_t C0, int64_t C1, int64_t C2, int64_t C3, int wide,
+                                                      int sb_shift, int64_t n_sb, Sector* __restrict__ sectors,
+                                                      int64_t* __restrict__ sbbase) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4 * n_blocks) return;
+    const int64_t b = t >> 2;
+    const int c = (int)(t & 3);
+    const int64_t Cc = c == 0 ? C0 : (c == 1 ? C1 : (c == 2 ? C2 : C3));
+    const int64_t pre = prefix[(int64_t)c * n_blocks + b];
+    const uint32_t* w = raw + (int64_t)c * words_per_vec + b * kPayloadWords;
+    Sector s;
+    if (wide) {
+        const int64_t sb = b >> sb_shift;
+        const int64_t pre_sb = prefix[(int64_t)c * n_blocks + (sb << sb_shift)];
+        s.w[0] = (uint32_t)(pre - pre_sb);
+        if ((b & ((1ll << sb_shift) - 1)) == 0) sbbase[(int64_t)c * n_sb + sb] = Cc + pre_sb;
+    } else {
+        s.w[0] = (uint32_t)(Cc + pre);
+    }
+#pragma unroll
+    for (int i = 0; i < kPayloadWords; i++) s.w[i + 1] = w[i];
+    sectors[t] = s;
+}
+
+// flag |= 1 if some column that is not a suffix-group start has a non-empty subset
+__global__ void __launch_bounds__(256) k0_check_edges_kernel(const uint32_t* __restrict__ raw, int64_t words_per_vec,
+                                                             const uint32_t* __restrict__ sgs, int64_t n_words,
+                                                             int* __restrict__ flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_words) return;
+    const uint32_t any = raw[t] | raw[words_per_vec + t] | raw[2 * words_per_vec + t] | raw[3 * words_per_vec + t];
+    if (any & ~sgs[t]) atomicOr(flag, 1);
+}
+
+// ------------------------------------------------------------------ rank entry point
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) rank_kernel(const DeviceIndexView ix, const int64_t* __restrict__ pos,
+                                                   const char* __restrict__ chars, int64_t n, int64_t C0, int64_t C1,
+                                                   int64_t C2, int64_t C3, int64_t* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const char ch = chars[t];
+    const int c = ch == 'A' ? 0 : (ch == 'C' ? 1 : (ch == 'G' ? 2 : (ch == 'T' ? 3 : -1)));
+    if (c < 0) { out[t] = 0; return; } // SubsetMatrixRank.hh:36
+    const BlockPos bp = split_pos<WIDE>(pos[t]);
+    const Sector s = ld_sector(sector_addr<WIDE>(ix, bp.blk, c));
+    const int64_t Cc = c == 0 ? C0 : (c == 1 ? C1 : (c == 2 ? C2 : C3));
+    out[t] = lf_value<WIDE>(ix, s, bp.blk, bp.off, c) - Cc;
+}
+
+// ------------------------------------------------------------------ random-sector probe
+
+// Each thread issues `per_thread` independent random aligned loads of BYTES (32 or 64) and xors them.
+template <int BYTES>
+__global__ void __launch_bounds__(256) probe_kernel(const Sector* __restrict__ buf, uint64_t n_units, int per_thread,
+                                                    uint32_t seed, uint32_t* __restrict__ sink) {
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + seed;
+    uint32_t acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < per_thread; i++) {
+        x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull; x ^= x >> 33;
+        const uint64_t u = (uint64_t)(((unsigned __int128)x * n_units) >> 64);
+        const Sector* p = buf + u * (BYTES / 32);
+        Sector s = ld_sector(p);
+        acc ^= s.w[0] ^ s.w[7];
+        if (BYTES == 64) {
+            Sector s2 = ld_sector(p + 1);
+            acc ^= s2.w[0] ^ s2.w[7];
+        }
+    }
+    if (acc == 0x12345678u) sink[0] = acc; // keep the loads alive
+}
+
+} // namespace sbwt_b200

@@ -1,0 +1,115 @@
+// device_index.cuh -- the device-resident layout of the four SBWT bit vectors and the rank primitive.
+//
+// Replaces sdsl::bit_vector + rank_support_v5<1,1> under SubsetMatrixRank
+// (reference: include/sbwt/SubsetMatrixRank.hh:19-37,
+//  sdsl-lite/include/sdsl/rank_support_v5.hpp:65-134). The reference keeps, per
+// character, a bit array and a separate 2048-bit-superblock directory, so one
+// rank touches two arrays. Here one 32-byte SECTOR holds everything one rank
+// needs:
+//
+//   sector(block b, char c) = { u32 count ; 7 x u32 payload }      32 bytes, 32-byte aligned
+//     payload = bits [224 b, 224 b + 224) of vector c, LSB-first
+//     count   = C[c] + rank_c(224 b)            (narrow: n_nodes < 2^32)
+//             = rank_c(224 b) - rank_c(224 * first block of b's superblock)   (wide),
+//               with sbbase[c][superblock] = C[c] + rank_c(superblock start) as int64
+//   sectors are interleaved [b][c]: address = base + 32 * (4 b + c)
+//
+// so  C[c] + rank_c(pos) = count + popcount(payload bits below pos % 224)  -- the LF-mapping
+// value the interval walk needs (SBWT.hh:430-431) from exactly one sector, fetched with one
+// 256-bit load (LDG.E.256 on sm_100a). n_blocks = n_nodes / 224 + 1, so pos == n_nodes is
+// addressable (reference: rank(size()) touches the padding word, memory_management.hpp:351-368).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sbwt_b200 {
+
+constexpr int kBlockCols = 224;       // columns per sector
+constexpr int kPayloadWords = 7;      // u32 payload words per sector
+constexpr int kDefaultSbShift = 23;   // 2^23 blocks (1.88e9 columns) per superblock in wide mode
+
+struct __align__(32) Sector {
+    uint32_t w[8]; // w[0] = count, w[1..7] = payload
+};
+
+struct DeviceIndexView {
+    const Sector* sectors;     // [n_blocks][4]
+    const int64_t* sbbase;     // [4][n_sb], wide mode only
+    const int64_t* precalc;    // 4^p pairs (l, r), 32-byte aligned; nullptr if p == 0
+    const uint32_t* sgs;       // suffix_group_starts as u32 words (padded), nullptr if absent
+    int64_t n_nodes;
+    int64_t n_blocks;
+    int64_t n_sb;
+    int k;
+    int p;
+    int sb_shift;
+    int wide;                  // 1 if n_nodes >= 2^32 (or forced for tests)
+    int edges_at_starts;       // structural invariant (i) of SURVEY.md section 8(a) note 7 holds
+};
+
+// 256-bit read-only load of one sector, not allocated in L1 (random access, no reuse there).
+__device__ __forceinline__ Sector ld_sector(const Sector* p) {
+    Sector s;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]), "=r"(s.w[4]), "=r"(s.w[5]),
+                   "=r"(s.w[6]), "=r"(s.w[7])
+                 : "l"(p));
+    return s;
+}
+
+// count + number of payload bits below in-block offset o (0 <= o < 224).
+__device__ __forceinline__ uint32_t sector_rank(const Sector& s, uint32_t o) {
+    const uint32_t full = o >> 5, rem = o & 31u;
+    uint32_t r = s.w[0];
+#pragma unroll
+    for (int i = 0; i < kPayloadWords; i++) {
+        const uint32_t m = ((uint32_t)i < full) ? 0xFFFFFFFFu : (((uint32_t)i == full) ? ((1u << rem) - 1u) : 0u);
+        r += __popc(s.w[i + 1] & m);
+    }
+    return r;
+}
+
+// payload bit at in-block offset o.
+__device__ __forceinline__ uint32_t sector_bit(const Sector& s, uint32_t o) {
+    const uint32_t wi = o >> 5;
+    uint32_t w = s.w[1];
+#pragma unroll
+    for (int i = 1; i < kPayloadWords; i++) w = (wi == (uint32_t)i) ? s.w[i + 1] : w;
+    return (w >> (o & 31u)) & 1u;
+}
+
+struct BlockPos {
+    int64_t blk;
+    uint32_t off;
+};
+
+template <bool WIDE>
+__device__ __forceinline__ BlockPos split_pos(int64_t pos) {
+    BlockPos bp;
+    if (WIDE) {
+        bp.blk = (int64_t)((uint64_t)pos / (uint64_t)kBlockCols);
+        bp.off = (uint32_t)((uint64_t)pos - (uint64_t)bp.blk * (uint64_t)kBlockCols);
+    } else {
+        const uint32_t p32 = (uint32_t)pos;
+        const uint32_t b = p32 / (uint32_t)kBlockCols;
+        bp.blk = b;
+        bp.off = p32 - b * (uint32_t)kBlockCols;
+    }
+    return bp;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ const Sector* sector_addr(const DeviceIndexView& ix, int64_t blk, int c) {
+    return ix.sectors + ((blk << 2) + c);
+}
+
+// C[c] + rank_c(pos) given the already loaded sector of pos's block.
+template <bool WIDE>
+__device__ __forceinline__ int64_t lf_value(const DeviceIndexView& ix, const Sector& s, int64_t blk, uint32_t off, int c) {
+    int64_t v = (int64_t)sector_rank(s, off);
+    if (WIDE) v += __ldg(ix.sbbase + (int64_t)c * ix.n_sb + (blk >> ix.sb_shift));
+    return v;
+}
+
+} // namespace sbwt_b200

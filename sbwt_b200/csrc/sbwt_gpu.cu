@@ -1,0 +1,642 @@
+// sbwt_gpu.cu -- the extern "C" layer of include/sbwt_b200.h: index creation, sessions,
+// kernel launches and the host<->device pipeline. No torch types, no CPU fallback.
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sbwt_b200.h"
+#include "aux_kernels.cuh"
+#include "device_index.cuh"
+#include "sbwt_file.hpp"
+#include "walk_kernel.cuh"
+
+using namespace sbwt_b200;
+
+// ------------------------------------------------------------------ errors
+
+static thread_local std::string g_last_error;
+static thread_local int64_t g_launches = 0;
+
+static int set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return 1;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) return set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define LAUNCHED() (g_launches++)
+
+static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------ objects
+
+struct sbwt_gpu_index {
+    int device = 0;
+    int64_t n_nodes = 0, n_kmers = 0, k = 0, precalc_k = 0;
+    int64_t C[4] = {0, 0, 0, 0};
+    bool has_sgs = false;
+    int sm_count = 0;
+    int64_t device_bytes = 0;
+    DeviceIndexView view{};
+    void* d_sectors = nullptr;
+    void* d_sbbase = nullptr;
+    void* d_precalc = nullptr;
+    void* d_sgs = nullptr;
+};
+
+struct Scratch {
+    int64_t max_bases = 0, max_reads = 0, max_items = 0;
+    uint64_t* codes = nullptr;
+    uint32_t* invalid = nullptr;
+    int64_t* n_out = nullptr;   // per read; becomes the exclusive scan
+    int64_t* n_win = nullptr;   // per read; becomes the exclusive scan
+    int64_t* partials = nullptr;
+    int64_t* totals = nullptr;  // [0] = total results, [1] = total items
+    int64_t* item_base = nullptr;
+    int64_t* item_out = nullptr;
+    int32_t* item_cnt = nullptr;
+    unsigned long long* stats = nullptr;
+};
+
+struct HostSlot {
+    Scratch sc;
+    char* d_ascii = nullptr;
+    int64_t* d_offsets = nullptr;
+    int64_t* d_out = nullptr;
+    char* h_ascii = nullptr;      // pinned staging, used only for pageable caller buffers
+    int64_t* h_offsets = nullptr;
+    int64_t* h_out = nullptr;
+    int64_t* h_totals = nullptr;  // pinned copy of sc.totals
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    // what to do when the slot's work has finished
+    int64_t out_count = 0;
+    int64_t* out_dst = nullptr;
+    bool out_staged = false;
+};
+
+struct sbwt_gpu_session {
+    sbwt_gpu_index* idx = nullptr;
+    int64_t max_bases = 0, max_reads = 0;
+    int window = 256;
+    Scratch sc;          // for device-buffer batches
+    bool timing = false; // record events around the walk kernel of device-buffer batches
+    cudaEvent_t ev_start = nullptr, ev_walk0 = nullptr, ev_walk1 = nullptr;
+    bool host_ready = false;
+    HostSlot slots[2];
+};
+
+// ------------------------------------------------------------------ small helpers
+
+static int dmalloc(void** p, size_t bytes, int64_t* account = nullptr) {
+    CU(cudaMalloc(p, bytes ? bytes : 16));
+    if (account) *account += (int64_t)bytes;
+    return 0;
+}
+
+static int exclusive_scan_inplace(int64_t* d_data, int64_t n, int64_t* d_partials, int64_t* d_total, cudaStream_t st) {
+    if (n == 0) {
+        CU(cudaMemsetAsync(d_total, 0, 8, st));
+        return 0;
+    }
+    const unsigned nb = grid_for(n, kScanTile);
+    scan_reduce_kernel<<<nb, kScanThreads, 0, st>>>(d_data, n, d_partials); LAUNCHED();
+    scan_partials_kernel<<<1, kScanThreads, 0, st>>>(d_partials, nb, d_total); LAUNCHED();
+    scan_apply_kernel<<<nb, kScanThreads, 0, st>>>(d_data, n, d_partials); LAUNCHED();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int64_t scan_partials_needed(int64_t n) { return (n + kScanTile - 1) / kScanTile + 1; }
+
+// ------------------------------------------------------------------ API: misc
+
+extern "C" const char* sbwt_gpu_last_error(void) { return g_last_error.c_str(); }
+extern "C" int sbwt_gpu_abi_version(void) { return SBWT_B200_ABI_VERSION; }
+extern "C" int sbwt_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int64_t sbwt_gpu_launch_count(int reset) {
+    int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+extern "C" int64_t sbwt_gpu_count_outputs(const int64_t* off, int64_t n_reads, int64_t k) {
+    int64_t t = 0;
+    for (int64_t i = 0; i < n_reads; i++) {
+        const int64_t len = off[i + 1] - off[i];
+        if (len >= k) t += len - k + 1;
+    }
+    return t;
+}
+
+// ------------------------------------------------------------------ API: index
+
+static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs, int64_t n_nodes, int64_t n_kmers,
+                             int64_t k, const int64_t C[4], const int64_t* precalc, int64_t p, int device,
+                             sbwt_gpu_index** out) {
+    *out = nullptr;
+    if (sbwt_gpu_device_count() <= 0) return set_error("no CUDA device available: the SBWT GPU query path has no CPU fallback");
+    if (device < 0 || device >= sbwt_gpu_device_count()) return set_error("invalid device %d", device);
+    if (n_nodes < 1 || k < 1) return set_error("invalid index: n_nodes=%lld k=%lld", (long long)n_nodes, (long long)k);
+    if (k > 64) return set_error("k = %lld is not supported by this build (k <= 64)", (long long)k);
+    if (p < 0 || p > k || p > 14) return set_error("precalc length %lld is not supported (0 <= p <= min(k,14))", (long long)p);
+    if (p > 0 && !precalc) return set_error("precalc table missing");
+    DeviceGuard guard(device);
+    sbwt_gpu_index* ix = new sbwt_gpu_index();
+    auto fail = [&](int rc) { sbwt_gpu_index_destroy(ix); return rc; };
+    ix->device = device;
+    ix->n_nodes = n_nodes; ix->n_kmers = n_kmers; ix->k = k; ix->precalc_k = p;
+    for (int c = 0; c < 4; c++) ix->C[c] = C[c];
+    ix->has_sgs = sgs != nullptr;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(set_error("cudaGetDeviceProperties failed"));
+    ix->sm_count = prop.multiProcessorCount;
+
+    const char* force_wide = getenv("SBWT_B200_FORCE_WIDE"); // tests: exercise the > 2^32-column layout on small indexes
+    const int wide = (n_nodes >= (1ll << 32) - 256 || (force_wide && atoi(force_wide) > 0)) ? 1 : 0;
+    const int sb_shift = (force_wide && atoi(force_wide) > 0) ? atoi(force_wide) : kDefaultSbShift;
+    const int64_t n_blocks = n_nodes / kBlockCols + 1;
+    const int64_t n_sb = wide ? ((n_blocks - 1) >> sb_shift) + 1 : 1;
+    const int64_t words_per_vec = n_blocks * kPayloadWords; // u32 words, zero padded
+    const int64_t host_words64 = (n_nodes + 63) / 64;
+
+    uint32_t* d_raw = nullptr;
+    int64_t* d_counts = nullptr;
+    int64_t* d_partials = nullptr;
+    int64_t* d_total = nullptr;
+    int* d_flag = nullptr;
+    auto cleanup_tmp = [&]() { cudaFree(d_raw); cudaFree(d_counts); cudaFree(d_partials); cudaFree(d_total); cudaFree(d_flag); };
+#define CUI(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            cleanup_tmp();                                                                            \
+            return fail(set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__))); \
+        }                                                                                             \
+    } while (0)
+    CUI(cudaMalloc(&d_raw, (size_t)(4 * words_per_vec + 8) * 4));
+    CUI(cudaMemset(d_raw, 0, (size_t)(4 * words_per_vec + 8) * 4));
+    for (int c = 0; c < 4; c++)
+        CUI(cudaMemcpy(d_raw + c * words_per_vec, bits[c], (size_t)host_words64 * 8, cudaMemcpyHostToDevice));
+    // (bits at positions >= n_nodes in the last word are zero in every sdsl-written file; memory_management.hpp:360-367)
+    CUI(cudaMalloc(&d_counts, (size_t)(4 * n_blocks) * 8));
+    CUI(cudaMalloc(&d_partials, (size_t)scan_partials_needed(n_blocks) * 8));
+    CUI(cudaMalloc(&d_total, 8 * 4));
+    CUI(cudaMalloc(&d_flag, 4));
+    CUI(cudaMemset(d_flag, 0, 4));
+    k0_block_popcount_kernel<<<grid_for(4 * n_blocks, 256), 256>>>(d_raw, words_per_vec, n_blocks, d_counts); LAUNCHED();
+    for (int c = 0; c < 4; c++)
+        if (exclusive_scan_inplace(d_counts + c * n_blocks, n_blocks, d_partials, d_total + c, 0)) { cleanup_tmp(); return fail(1); }
+    int64_t totals[4];
+    CUI(cudaMemcpy(totals, d_total, 32, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < 3; c++)
+        if (C[c + 1] - C[c] != totals[c]) {
+            cleanup_tmp();
+            return fail(set_error("Error: Corrupt index file (C array does not match the bit vectors: C[%d+1]-C[%d]=%lld, ones=%lld)",
+                                  c, c, (long long)(C[c + 1] - C[c]), (long long)totals[c]));
+        }
+    if (C[3] + totals[3] > n_nodes || C[0] < 0) { cleanup_tmp(); return fail(set_error("Error: Corrupt index file (C array out of range)")); }
+
+    if (dmalloc(&ix->d_sectors, (size_t)(4 * n_blocks) * sizeof(Sector), &ix->device_bytes)) { cleanup_tmp(); return fail(1); }
+    if (wide && dmalloc(&ix->d_sbbase, (size_t)(4 * n_sb) * 8, &ix->device_bytes)) { cleanup_tmp(); return fail(1); }
+    k0_emit_kernel<<<grid_for(4 * n_blocks, 256), 256>>>(d_raw, words_per_vec, n_blocks, d_counts, C[0], C[1], C[2], C[3], wide,
+                                                         sb_shift, n_sb, (Sector*)ix->d_sectors, (int64_t*)ix->d_sbbase); LAUNCHED();
+    CUI(cudaGetLastError());
+
+    int edges_at_starts = 0;
+    if (sgs) {
+        const int64_t sgs_words = words_per_vec + 8;
+        if (dmalloc(&ix->d_sgs, (size_t)sgs_words * 4, &ix->device_bytes)) { cleanup_tmp(); return fail(1); }
+        CUI(cudaMemset(ix->d_sgs, 0, (size_t)sgs_words * 4));
+        CUI(cudaMemcpy(ix->d_sgs, sgs, (size_t)host_words64 * 8, cudaMemcpyHostToDevice));
+        k0_check_edges_kernel<<<grid_for(words_per_vec, 256), 256>>>(d_raw, words_per_vec, (const uint32_t*)ix->d_sgs, words_per_vec, d_flag); LAUNCHED();
+        int flag = 0;
+        CUI(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
+        edges_at_starts = flag ? 0 : 1;
+    }
+    if (p > 0) {
+        const size_t bytes = (size_t)16 << (2 * p);
+        if (dmalloc(&ix->d_precalc, bytes + 32, &ix->device_bytes)) { cleanup_tmp(); return fail(1); }
+        CUI(cudaMemset((char*)ix->d_precalc + bytes, 0xFF, 32));
+        CUI(cudaMemcpy(ix->d_precalc, precalc, bytes, cudaMemcpyHostToDevice));
+    }
+    CUI(cudaDeviceSynchronize());
+    cleanup_tmp();
+#undef CUI
+    DeviceIndexView& v = ix->view;
+    v.sectors = (const Sector*)ix->d_sectors;
+    v.sbbase = (const int64_t*)ix->d_sbbase;
+    v.precalc = (const int64_t*)ix->d_precalc;
+    v.sgs = (const uint32_t*)ix->d_sgs;
+    v.n_nodes = n_nodes; v.n_blocks = n_blocks; v.n_sb = n_sb;
+    v.k = (int)k; v.p = (int)p; v.sb_shift = sb_shift; v.wide = wide; v.edges_at_starts = edges_at_starts;
+    *out = ix;
+    return 0;
+}
+
+extern "C" int sbwt_gpu_index_create(const uint64_t* const bits[4], const uint64_t* sgs, int64_t n_nodes, int64_t n_kmers,
+                                     int64_t k, const int64_t C[4], const int64_t* precalc, int64_t p, int device,
+                                     sbwt_gpu_index** out) {
+    if (!out || !bits || !C) return set_error("null argument");
+    return index_create_impl(bits, sgs, n_nodes, n_kmers, k, C, precalc, p, device, out);
+}
+
+extern "C" int sbwt_gpu_index_load(const char* path, int device, sbwt_gpu_index** out) {
+    if (!out || !path) return set_error("null argument");
+    *out = nullptr;
+    try {
+        PlainMatrixFile F = load_plain_matrix_file(path);
+        const uint64_t* bits[4] = {F.bits[0].data(), F.bits[1].data(), F.bits[2].data(), F.bits[3].data()};
+        return index_create_impl(bits, F.suffix_group_starts.empty() ? nullptr : F.suffix_group_starts.data(), F.n_nodes,
+                                 F.n_kmers, F.k, F.C, F.precalc.empty() ? nullptr : F.precalc.data(), F.precalc_k, device, out);
+    } catch (const std::exception& e) {
+        return set_error("%s", e.what());
+    }
+}
+
+extern "C" void sbwt_gpu_index_destroy(sbwt_gpu_index* ix) {
+    if (!ix) return;
+    DeviceGuard guard(ix->device);
+    cudaFree(ix->d_sectors); cudaFree(ix->d_sbbase); cudaFree(ix->d_precalc); cudaFree(ix->d_sgs);
+    delete ix;
+}
+
+extern "C" int64_t sbwt_gpu_index_k(const sbwt_gpu_index* ix) { return ix->k; }
+extern "C" int64_t sbwt_gpu_index_n_nodes(const sbwt_gpu_index* ix) { return ix->n_nodes; }
+extern "C" int64_t sbwt_gpu_index_n_kmers(const sbwt_gpu_index* ix) { return ix->n_kmers; }
+extern "C" int64_t sbwt_gpu_index_precalc_k(const sbwt_gpu_index* ix) { return ix->precalc_k; }
+extern "C" int sbwt_gpu_index_has_streaming_support(const sbwt_gpu_index* ix) { return ix->has_sgs ? 1 : 0; }
+extern "C" int sbwt_gpu_index_device(const sbwt_gpu_index* ix) { return ix->device; }
+extern "C" void sbwt_gpu_index_C(const sbwt_gpu_index* ix, int64_t C[4]) { for (int c = 0; c < 4; c++) C[c] = ix->C[c]; }
+extern "C" int64_t sbwt_gpu_index_device_bytes(const sbwt_gpu_index* ix) { return ix->device_bytes; }
+extern "C" int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index* ix) { return ix->view.edges_at_starts; }
+
+extern "C" int sbwt_gpu_rank(sbwt_gpu_index* ix, const int64_t* pos, const char* chars, int64_t n, int64_t* out) {
+    if (!ix) return set_error("null index");
+    if (n <= 0) return 0;
+    for (int64_t i = 0; i < n; i++)
+        if (pos[i] < 0 || pos[i] > ix->n_nodes) return set_error("rank position %lld out of range [0, %lld]", (long long)pos[i], (long long)ix->n_nodes);
+    DeviceGuard guard(ix->device);
+    int64_t *d_pos = nullptr, *d_out = nullptr;
+    char* d_ch = nullptr;
+    CU(cudaMalloc(&d_pos, n * 8)); CU(cudaMalloc(&d_out, n * 8)); CU(cudaMalloc(&d_ch, n));
+    CU(cudaMemcpy(d_pos, pos, n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_ch, chars, n, cudaMemcpyHostToDevice));
+    if (ix->view.wide) rank_kernel<true><<<grid_for(n, 256), 256>>>(ix->view, d_pos, d_ch, n, ix->C[0], ix->C[1], ix->C[2], ix->C[3], d_out);
+    else rank_kernel<false><<<grid_for(n, 256), 256>>>(ix->view, d_pos, d_ch, n, ix->C[0], ix->C[1], ix->C[2], ix->C[3], d_out);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d_out, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_pos); cudaFree(d_out); cudaFree(d_ch);
+    return 0;
+}
+
+// ------------------------------------------------------------------ sessions
+
+static void scratch_free(Scratch& sc) {
+    cudaFree(sc.codes); cudaFree(sc.invalid); cudaFree(sc.n_out); cudaFree(sc.n_win); cudaFree(sc.partials);
+    cudaFree(sc.totals); cudaFree(sc.item_base); cudaFree(sc.item_out); cudaFree(sc.item_cnt); cudaFree(sc.stats);
+    sc = Scratch();
+}
+
+static int scratch_alloc(Scratch& sc, int64_t max_bases, int64_t max_reads, int window) {
+    sc.max_bases = max_bases; sc.max_reads = max_reads;
+    sc.max_items = max_reads + max_bases / window + 1;
+    const int64_t words = max_bases / 32 + 8;
+    CU(cudaMalloc(&sc.codes, words * 8));
+    CU(cudaMalloc(&sc.invalid, words * 4));
+    CU(cudaMalloc(&sc.n_out, (max_reads + 1) * 8));
+    CU(cudaMalloc(&sc.n_win, (max_reads + 1) * 8));
+    CU(cudaMalloc(&sc.partials, scan_partials_needed(max_reads + 1) * 8));
+    CU(cudaMalloc(&sc.totals, 4 * 8));
+    CU(cudaMalloc(&sc.item_base, sc.max_items * 8));
+    CU(cudaMalloc(&sc.item_out, sc.max_items * 8));
+    CU(cudaMalloc(&sc.item_cnt, sc.max_items * 4));
+    CU(cudaMalloc(&sc.stats, 8 * 8));
+    return 0;
+}
+
+extern "C" int sbwt_gpu_session_create(sbwt_gpu_index* ix, int64_t max_bases, int64_t max_reads, sbwt_gpu_session** out) {
+    if (!ix || !out) return set_error("null argument");
+    *out = nullptr;
+    if (max_bases < 1 || max_reads < 1) return set_error("session capacity must be positive");
+    DeviceGuard guard(ix->device);
+    sbwt_gpu_session* s = new sbwt_gpu_session();
+    s->idx = ix; s->max_bases = max_bases; s->max_reads = max_reads;
+    if (const char* w = getenv("SBWT_B200_WINDOW")) s->window = std::max(1, atoi(w));
+    if (scratch_alloc(s->sc, max_bases, max_reads, s->window)) { sbwt_gpu_session_destroy(s); return 1; }
+    *out = s;
+    return 0;
+}
+
+extern "C" int sbwt_gpu_session_set_timing(sbwt_gpu_session* s, int enable) {
+    if (!s) return set_error("null session");
+    DeviceGuard guard(s->idx->device);
+    if (enable && !s->ev_start) {
+        CU(cudaEventCreate(&s->ev_start)); CU(cudaEventCreate(&s->ev_walk0)); CU(cudaEventCreate(&s->ev_walk1));
+    }
+    s->timing = enable != 0;
+    return 0;
+}
+
+extern "C" int sbwt_gpu_session_last_timing(sbwt_gpu_session* s, double* prep_ms, double* walk_ms) {
+    if (!s || !s->ev_start) return set_error("timing was not enabled on this session");
+    DeviceGuard guard(s->idx->device);
+    CU(cudaEventSynchronize(s->ev_walk1));
+    float a = 0, b = 0;
+    CU(cudaEventElapsedTime(&a, s->ev_start, s->ev_walk0));
+    CU(cudaEventElapsedTime(&b, s->ev_walk0, s->ev_walk1));
+    if (prep_ms) *prep_ms = a;
+    if (walk_ms) *walk_ms = b;
+    return 0;
+}
+
+extern "C" void sbwt_gpu_session_destroy(sbwt_gpu_session* s) {
+    if (!s) return;
+    DeviceGuard guard(s->idx->device);
+    scratch_free(s->sc);
+    if (s->ev_start) { cudaEventDestroy(s->ev_start); cudaEventDestroy(s->ev_walk0); cudaEventDestroy(s->ev_walk1); }
+    for (HostSlot& h : s->slots) {
+        scratch_free(h.sc);
+        cudaFree(h.d_ascii); cudaFree(h.d_offsets); cudaFree(h.d_out);
+        cudaFreeHost(h.h_ascii); cudaFreeHost(h.h_offsets); cudaFreeHost(h.h_out); cudaFreeHost(h.h_totals);
+        if (h.stream) cudaStreamDestroy(h.stream);
+        if (h.done) cudaEventDestroy(h.done);
+    }
+    delete s;
+}
+
+// ------------------------------------------------------------------ launches
+
+static int launch_pack(const char* d_ascii, int64_t n_bases, int case_mode, uint64_t* codes, uint32_t* invalid, cudaStream_t st) {
+    const int64_t n_words = n_bases / 32 + 4;
+    const uint32_t fold = case_mode == SBWT_GPU_CASE_EXACT ? 0xFFFFFFFFu : 0xDFDFDFDFu;
+    const bool vec = ((uintptr_t)d_ascii & 15) == 0;
+    if (vec) pack_kernel<true><<<grid_for(n_words, 256), 256, 0, st>>>((const uint8_t*)d_ascii, n_bases, fold, codes, invalid, n_words);
+    else pack_kernel<false><<<grid_for(n_words, 256), 256, 0, st>>>((const uint8_t*)d_ascii, n_bases, fold, codes, invalid, n_words);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int NW, bool STREAMING, bool WIDE>
+static void launch_walk_t(const WalkParams& P, bool count, unsigned grid, cudaStream_t st) {
+    if (count) walk_kernel<NW, STREAMING, WIDE, true><<<grid, 256, 0, st>>>(P);
+    else walk_kernel<NW, STREAMING, WIDE, false><<<grid, 256, 0, st>>>(P);
+}
+
+static int launch_walk(const sbwt_gpu_index* ix, const WalkParams& P, bool streaming, bool count, cudaStream_t st) {
+    int blocks_per_sm = 4;
+    if (const char* e = getenv("SBWT_B200_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, atoi(e));
+    const unsigned grid = (unsigned)(ix->sm_count * blocks_per_sm);
+    const int nw = ix->k <= 32 ? 1 : 2;
+    const bool wide = ix->view.wide;
+#define WALK(NW_, S_, W_) launch_walk_t<NW_, S_, W_>(P, count, grid, st)
+    if (nw == 1) {
+        if (streaming) { if (wide) WALK(1, true, true); else WALK(1, true, false); }
+        else { if (wide) WALK(1, false, true); else WALK(1, false, false); }
+    } else {
+        if (streaming) { if (wide) WALK(2, true, true); else WALK(2, true, false); }
+        else { if (wide) WALK(2, false, true); else WALK(2, false, false); }
+    }
+#undef WALK
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// pack -> plan -> walk for one device-resident batch, all on `st`
+static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_ascii, const int64_t* d_offsets, int64_t n_reads,
+                            int64_t n_bases, int mode, int case_mode, int64_t* d_out, bool count, cudaStream_t st) {
+    sbwt_gpu_index* ix = s->idx;
+    if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
+    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
+    if (mode == SBWT_GPU_MODE_STREAMING && !ix->has_sgs) return set_error("Error: streaming search support not built"); // SBWT.hh:546-547
+    if (n_reads < 0 || n_bases < 0) return set_error("negative batch size");
+    if (n_bases > sc.max_bases || n_reads > sc.max_reads)
+        return set_error("batch of %lld reads / %lld bases exceeds the session capacity (%lld / %lld)", (long long)n_reads,
+                         (long long)n_bases, (long long)sc.max_reads, (long long)sc.max_bases);
+    if (n_reads == 0) return 0;
+    if (s->timing && &sc == &s->sc) CU(cudaEventRecord(s->ev_start, st));
+    if (launch_pack(d_ascii, n_bases, case_mode, sc.codes, sc.invalid, st)) return 1;
+    plan_count_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, s->window, sc.n_out, sc.n_win); LAUNCHED();
+    if (exclusive_scan_inplace(sc.n_out, n_reads, sc.partials, sc.totals + 0, st)) return 1;
+    if (exclusive_scan_inplace(sc.n_win, n_reads, sc.partials, sc.totals + 1, st)) return 1;
+    plan_emit_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, s->window, sc.n_out, sc.n_win, 0,
+                                                            sc.item_base, sc.item_out, sc.item_cnt); LAUNCHED();
+    CU(cudaGetLastError());
+    WalkParams P;
+    P.ix = ix->view;
+    P.codes = sc.codes; P.invalid = sc.invalid;
+    P.item_base = sc.item_base; P.item_out = sc.item_out; P.item_cnt = sc.item_cnt;
+    P.n_items = sc.totals + 1;
+    P.out = d_out;
+    P.stats = sc.stats;
+    if (count) CU(cudaMemsetAsync(sc.stats, 0, 64, st));
+    const bool timed = s->timing && &sc == &s->sc;
+    if (timed) CU(cudaEventRecord(s->ev_walk0, st));
+    if (launch_walk(ix, P, mode == SBWT_GPU_MODE_STREAMING, count, st)) return 1;
+    if (timed) CU(cudaEventRecord(s->ev_walk1, st));
+    return 0;
+}
+
+extern "C" int sbwt_gpu_pack_device(const char* d_ascii, int64_t n_bases, int case_mode, uint64_t* d_codes, uint32_t* d_invalid, void* stream) {
+    if (n_bases < 0) return set_error("negative size");
+    return launch_pack(d_ascii, n_bases, case_mode, d_codes, d_invalid, (cudaStream_t)stream);
+}
+
+extern "C" int sbwt_gpu_query_device(sbwt_gpu_session* s, const char* d_ascii, const int64_t* d_offsets, int64_t n_reads,
+                                     int64_t n_bases, int mode, int case_mode, int64_t* d_out, int64_t n_out, void* stream) {
+    if (!s) return set_error("null session");
+    (void)n_out;
+    DeviceGuard guard(s->idx->device);
+    return run_device_batch(s, s->sc, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, false, (cudaStream_t)stream);
+}
+
+extern "C" int sbwt_gpu_query_device_counted(sbwt_gpu_session* s, const char* d_ascii, const int64_t* d_offsets, int64_t n_reads,
+                                             int64_t n_bases, int mode, int case_mode, int64_t* d_out, int64_t n_out, void* stream,
+                                             sbwt_gpu_stats* stats) {
+    if (!s || !stats) return set_error("null argument");
+    (void)n_out;
+    DeviceGuard guard(s->idx->device);
+    const int64_t before = g_launches;
+    if (run_device_batch(s, s->sc, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, true, (cudaStream_t)stream)) return 1;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (n_reads > 0) CU(cudaMemcpy(h, s->sc.stats, 32, cudaMemcpyDeviceToHost));
+    stats->lookups = (int64_t)h[0]; stats->hits = (int64_t)h[1]; stats->rank_ops = (int64_t)h[2]; stats->index_sectors = (int64_t)h[3];
+    stats->kernel_launches = g_launches - before;
+    return 0;
+}
+
+// ------------------------------------------------------------------ host pipeline
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int host_slots_init(sbwt_gpu_session* s) {
+    if (s->host_ready) return 0;
+    for (HostSlot& h : s->slots) {
+        if (scratch_alloc(h.sc, s->max_bases, s->max_reads, s->window)) return 1;
+        CU(cudaMalloc(&h.d_ascii, s->max_bases + 64));
+        CU(cudaMalloc(&h.d_offsets, (s->max_reads + 1) * 8));
+        CU(cudaMalloc(&h.d_out, std::max<int64_t>(s->max_bases, 1) * 8));
+        CU(cudaMallocHost(&h.h_totals, 4 * 8));
+        CU(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+    }
+    s->host_ready = true;
+    return 0;
+}
+
+static int slot_finish(HostSlot& h) {
+    if (!h.busy) return 0;
+    CU(cudaEventSynchronize(h.done));
+    if (h.out_staged && h.out_count) memcpy(h.out_dst, h.h_out, (size_t)h.out_count * 8);
+    h.busy = false;
+    return 0;
+}
+
+extern "C" int sbwt_gpu_query_host(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                                   int case_mode, int64_t* out) {
+    if (!s) return set_error("null session");
+    if (n_reads < 0) return set_error("negative batch size");
+    if (n_reads == 0) return 0;
+    if (!ascii || !off || !out) return set_error("null buffer");
+    sbwt_gpu_index* ix = s->idx;
+    if (mode == SBWT_GPU_MODE_STREAMING && !ix->has_sgs) return set_error("Error: streaming search support not built");
+    DeviceGuard guard(ix->device);
+    if (host_slots_init(s)) return 1;
+    const bool pin_in = is_pinned(ascii), pin_off = is_pinned(off), pin_out = is_pinned(out);
+    const int64_t k = ix->k;
+    int64_t r0 = 0, out_pos = 0;
+    int turn = 0;
+    while (r0 < n_reads) {
+        // largest chunk [r0, r1) that fits the session capacity
+        int64_t r1 = r0, bases = 0;
+        while (r1 < n_reads && r1 - r0 < s->max_reads) {
+            const int64_t len = off[r1 + 1] - off[r1];
+            if (len < 0) return set_error("read offsets must be non-decreasing");
+            if (len > s->max_bases) return set_error("read %lld (%lld bases) is longer than the session capacity (%lld bases)", (long long)r1, (long long)len, (long long)s->max_bases);
+            if (bases + len > s->max_bases) break;
+            bases += len;
+            r1++;
+        }
+        const int64_t nr = r1 - r0;
+        const int64_t n_out = sbwt_gpu_count_outputs(off + r0, nr, k);
+        HostSlot& h = s->slots[turn & 1];
+        turn++;
+        if (slot_finish(h)) return 1;
+        const char* src = ascii + off[r0];
+        if (!pin_in) {
+            if (!h.h_ascii) CU(cudaMallocHost(&h.h_ascii, s->max_bases + 64));
+            memcpy(h.h_ascii, src, (size_t)bases);
+            src = h.h_ascii;
+        }
+        const int64_t* osrc = off + r0;
+        if (!pin_off) {
+            if (!h.h_offsets) CU(cudaMallocHost(&h.h_offsets, (s->max_reads + 1) * 8));
+            memcpy(h.h_offsets, osrc, (size_t)(nr + 1) * 8);
+            osrc = h.h_offsets;
+        }
+        CU(cudaMemcpyAsync(h.d_ascii, src, (size_t)bases, cudaMemcpyHostToDevice, h.stream));
+        CU(cudaMemcpyAsync(h.d_offsets, osrc, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, h.stream));
+        if (run_device_batch(s, h.sc, h.d_ascii, h.d_offsets, nr, bases, mode, case_mode, h.d_out, false, h.stream)) return 1;
+        int64_t* dst = out + out_pos;
+        h.out_dst = dst; h.out_count = n_out; h.out_staged = !pin_out;
+        if (!pin_out) {
+            if (!h.h_out) CU(cudaMallocHost(&h.h_out, std::max<int64_t>(s->max_bases, 1) * 8));
+            dst = h.h_out;
+        }
+        if (n_out) CU(cudaMemcpyAsync(dst, h.d_out, (size_t)n_out * 8, cudaMemcpyDeviceToHost, h.stream));
+        CU(cudaEventRecord(h.done, h.stream));
+        h.busy = true;
+        out_pos += n_out;
+        r0 = r1;
+    }
+    for (HostSlot& h : s->slots)
+        if (slot_finish(h)) return 1;
+    return 0;
+}
+
+extern "C" int sbwt_gpu_search_batch(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int64_t* out) {
+    return sbwt_gpu_query_host(s, ascii, off, n_reads, SBWT_GPU_MODE_SEARCH, SBWT_GPU_CASE_UPPER, out);
+}
+extern "C" int sbwt_gpu_streaming_batch(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int64_t* out) {
+    return sbwt_gpu_query_host(s, ascii, off, n_reads, SBWT_GPU_MODE_STREAMING, SBWT_GPU_CASE_UPPER, out);
+}
+
+extern "C" int sbwt_gpu_host_alloc(size_t bytes, void** out) {
+    if (!out) return set_error("null argument");
+    CU(cudaMallocHost(out, bytes ? bytes : 16));
+    return 0;
+}
+extern "C" void sbwt_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ probe
+
+extern "C" int sbwt_gpu_sector_probe(int device, int64_t buffer_bytes, int64_t n_loads, int bytes_per_load, int iters, double* best_ms) {
+    if (bytes_per_load != 32 && bytes_per_load != 64) return set_error("bytes_per_load must be 32 or 64");
+    if (sbwt_gpu_device_count() <= 0) return set_error("no CUDA device available");
+    DeviceGuard guard(device);
+    void* buf = nullptr;
+    uint32_t* sink = nullptr;
+    CU(cudaMalloc(&buf, (size_t)buffer_bytes));
+    CU(cudaMemset(buf, 1, (size_t)buffer_bytes));
+    CU(cudaMalloc(&sink, 4));
+    const uint64_t n_units = (uint64_t)buffer_bytes / (uint64_t)bytes_per_load;
+    const int per_thread = 32;
+    const int64_t threads = (n_loads + per_thread - 1) / per_thread;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 1e30;
+    for (int it = 0; it < iters + 1; it++) {
+        CU(cudaEventRecord(e0));
+        if (bytes_per_load == 32) probe_kernel<32><<<grid_for(threads, 256), 256>>>((const Sector*)buf, n_units, per_thread, 1234u + it, sink);
+        else probe_kernel<64><<<grid_for(threads, 256), 256>>>((const Sector*)buf, n_units, per_thread, 1234u + it, sink);
+        LAUNCHED();
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (it > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    *best_ms = best;
+    return 0;
+}

@@ -16,7 +16,7 @@
 //
 // tests/test_builder.py byte-compares its output with files written by the
 // reference's own constructors (KMC-based `sbwt build` and the in-memory
-// constructor through oracle/_ref/sbwt_ref).
+// constructor compiled from the reference tree).
 //
 // usage: build_plain_matrix -i in.fna[,in2.fna...] -o out.sbwt -k K [-p P]
 //            [--no-streaming-support] [--add-reverse-complements] [-t threads]

@@ -1,0 +1,272 @@
+"""Parity of the CUDA path with the reference, through the C ABI, on a real GPU.
+
+Expected values come from (a) the committed outputs of the reference's own classes
+(tests/golden, MANIFEST.json) and (b) the C oracle on the same seeded inputs; at
+BASELINE.json's full sizes, from size-independent properties (streaming == per-k-mer search,
+hit counts of planted reads)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import sbwt_b200 as S
+from conftest import c1_expected, c1_reads, golden, parse_expected, read_fasta_reads
+from sbwt_b200.testing import build_index, read_sbwt, strip_streaming_support, synth
+
+pytestmark = pytest.mark.gpu
+MAN = json.load(open(golden("MANIFEST.json")))
+
+
+def run_both(index_path, reads, modes=(S.MODE_STREAMING, S.MODE_SEARCH), case_mode=S.CASE_UPPER, **kw):
+    a, off = synth.ragged_to_batch(reads)
+    idx = S.Index(index_path)
+    ses = S.Session(idx, max(1, a.size), max(1, len(reads)))
+    res = {m: ses.query_host(a, off, m, case_mode).copy() for m in modes}
+    ses.close()
+    idx.close()
+    return res
+
+
+@pytest.mark.parametrize("name", ["cli_k6", "small_k31", "small_k63_rc", "small_k8_p0"])
+def test_golden_fixtures(name, tmp_path):
+    if name == "cli_k6":
+        expected = open(golden(name, "known_answer.txt"), "rb").read() + open(golden(name, "edge.expected.txt"), "rb").read()
+        reads = read_fasta_reads(golden(name, "queries.fna")) + read_fasta_reads(golden(name, "edge.fna"))
+    else:
+        expected = open(golden(name, "expected.txt"), "rb").read()
+        reads = read_fasta_reads(golden(name, "reads.fna"))
+    vals, counts = parse_expected(expected)
+    res = run_both(golden(name, "index.sbwt"), reads)
+    np.testing.assert_array_equal(res[S.MODE_STREAMING], vals)
+    np.testing.assert_array_equal(res[S.MODE_SEARCH], vals)
+    assert oracle.format_lines(res[S.MODE_STREAMING], counts) == expected
+    # the --no-streaming-support flavour: per-k-mer path only, streaming must refuse like the reference
+    ns = str(tmp_path / "ns.sbwt")
+    strip_streaming_support(golden(name, "index.sbwt"), ns)
+    np.testing.assert_array_equal(run_both(ns, reads, modes=(S.MODE_SEARCH,))[S.MODE_SEARCH], vals)
+    with pytest.raises(S.SbwtGpuError, match="streaming search support not built"):
+        run_both(ns, reads, modes=(S.MODE_STREAMING,))
+
+
+def test_config1_coli3():
+    """BASELINE config 1 (reference output md5 bbb3a7a4...)."""
+    expected = c1_expected()
+    vals, counts = parse_expected(expected)
+    res = run_both(golden("c1", "index.sbwt"), c1_reads())
+    np.testing.assert_array_equal(res[S.MODE_STREAMING], vals)
+    np.testing.assert_array_equal(res[S.MODE_SEARCH], vals)
+    assert oracle.format_lines(res[S.MODE_STREAMING], counts) == expected
+
+
+def test_index_accessors_and_rank():
+    idx = S.Index(golden("c1", "index.sbwt"))
+    orc = oracle.OracleIndex(golden("c1", "index.sbwt"))
+    assert (idx.n_nodes, idx.n_kmers, idx.k, idx.precalc_k) == (10401756, 10335847, 30, 8)
+    assert idx.C_array == [1, 2567588, 5206718, 7835964] == orc.C_array
+    assert idx.has_streaming_support and idx.edges_only_at_group_starts
+    n = idx.n_nodes
+    rng = np.random.default_rng(3)
+    pos = np.concatenate([rng.integers(0, n + 1, 5000), [0, 1, 223, 224, 225, 447, 448, n - 1, n]]).astype(np.int64)
+    chars = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=pos.size))
+    got = idx.rank(pos, chars)
+    want = np.array([orc.rank(int(p), chr(c)) for p, c in zip(pos, chars)])
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(S.SbwtGpuError, match="out of range"):
+        idx.rank(np.array([n + 1]), b"A")
+
+
+@pytest.mark.parametrize("env", [{"SBWT_B200_FORCE_WIDE": "3"}, {"SBWT_B200_WINDOW": "7"}, {"SBWT_B200_WINDOW": "1", "SBWT_B200_FORCE_WIDE": "1"}])
+def test_wide_layout_and_window_splitting(env, monkeypatch):
+    """The > 2^32-column layout (superblock bases) and the splitting of reads into windows, forced on small data."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    for name in ("small_k31", "small_k63_rc"):
+        vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+        res = run_both(golden(name, "index.sbwt"), read_fasta_reads(golden(name, "reads.fna")))
+        np.testing.assert_array_equal(res[S.MODE_STREAMING], vals)
+        np.testing.assert_array_equal(res[S.MODE_SEARCH], vals)
+
+
+def test_chunked_host_pipeline_and_empty_inputs():
+    """Host batches larger than the session capacity are chunked; ragged / empty batches."""
+    name = "small_k31"
+    vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+    reads = read_fasta_reads(golden(name, "reads.fna"))
+    a, off = synth.ragged_to_batch(reads)
+    idx = S.Index(golden(name, "index.sbwt"))
+    ses = S.Session(idx, max_bases=max(len(r) for r in reads) + 100, max_reads=7)
+    for pinned in (False, True):
+        if pinned:
+            pa, po = S.pinned_empty(a.size, np.uint8), S.pinned_empty(off.size, np.int64)
+            pa[:], po[:] = a, off
+            out = S.pinned_empty(vals.size, np.int64)
+            got = ses.query_host(pa, po, S.MODE_STREAMING, out=out)
+        else:
+            got = ses.query_host(a, off, S.MODE_STREAMING)
+        np.testing.assert_array_equal(got, vals)
+    # offsets that do not start at zero (a slice of a larger batch)
+    cut = 100
+    sub = ses.query_host(a, off[cut:].copy(), S.MODE_SEARCH)
+    np.testing.assert_array_equal(sub, vals[ses.count_outputs(off[:cut + 1]):])
+    # no reads, and reads that are all shorter than k
+    assert ses.query_host(a, np.zeros(1, np.int64), S.MODE_STREAMING).size == 0
+    short = [b"ACGT", b"", b"A" * 30]
+    sa, so = synth.ragged_to_batch(short)
+    assert ses.query_host(sa, so, S.MODE_STREAMING).size == 0
+    with pytest.raises(S.SbwtGpuError, match="longer than the session capacity"):
+        la, lo = synth.ragged_to_batch([b"A" * (ses.index.k + 5000 + max(len(r) for r in reads))])
+        ses.query_host(la, lo, S.MODE_SEARCH)
+
+
+def test_case_exact_mode_matches_search_api():
+    """CASE_EXACT = SBWT::search() on the caller's raw bytes: lower case is a miss (SBWT.hh:427)."""
+    name = "small_k31"
+    raw = []
+    cur = None
+    for line in open(golden(name, "reads.fna"), "rb").read().split(b"\n"):
+        if line.startswith(b">"):
+            if cur is not None:
+                raw.append(cur)
+            cur = b""
+        elif cur is not None:
+            cur += line
+    raw.append(cur)
+    a, off = synth.ragged_to_batch(raw)
+    orc = oracle.OracleIndex(golden(name, "index.sbwt"))
+    want = orc.query_batch(a, off, streaming=False)
+    got = run_both(golden(name, "index.sbwt"), raw, modes=(S.MODE_SEARCH,), case_mode=S.CASE_EXACT)[S.MODE_SEARCH]
+    np.testing.assert_array_equal(got, want)
+    assert (want != parse_expected(open(golden(name, "expected.txt"), "rb").read())[0]).any()  # the fixture has lower case
+
+
+def test_index_create_from_arrays_and_violated_invariant(tmp_path):
+    """sbwt_gpu_index_create (the SBWT(A,C,G,T,...) constructor path) and the literal walk-back:
+    clearing suffix-group marks makes columns with edges non-starts, so the one-sector shortcut
+    must be abandoned; the reference semantics (oracle) is the judge."""
+    name = "small_k31"
+    d = read_sbwt(golden(name, "index.sbwt"))
+    n = d["n_nodes"]
+    sgs = d["sgs"][1].copy()
+    rng = np.random.default_rng(5)
+    for col in rng.integers(1, n, 4000):
+        sgs[col >> 6] &= ~np.uint64(1 << (int(col) & 63))
+    arrays = dict(bits=[w for _, w in d["bits"]], sgs=sgs, C=d["C"], precalc=d["precalc"].reshape(-1), precalc_k=d["precalc_k"],
+                  n_nodes=n, n_kmers=d["n_kmers"], k=d["k"])
+    # write the modified index so the oracle can load it (same layout, rank supports unchanged)
+    raw = np.fromfile(golden(name, "index.sbwt"), dtype=np.uint8)
+    tail = 8 + 32 + 8 + d["precalc"].size * 8 + 32
+    start = raw.size - tail - sgs.size * 8
+    mod = raw.copy()
+    mod[start:start + sgs.size * 8] = sgs.view(np.uint8)
+    p = str(tmp_path / "mod.sbwt")
+    mod.tofile(p)
+    reads = read_fasta_reads(golden(name, "reads.fna"))
+    a, off = synth.ragged_to_batch(reads)
+    want = oracle.OracleIndex(p).query_batch(a, off, streaming=True)
+    idx = S.Index(arrays=arrays)
+    assert not idx.edges_only_at_group_starts
+    ses = S.Session(idx, a.size, len(reads))
+    np.testing.assert_array_equal(ses.query_host(a, off, S.MODE_STREAMING), want)
+    idx2 = S.Index(p)
+    assert not idx2.edges_only_at_group_starts
+    # an inconsistent C array is rejected
+    bad = dict(arrays)
+    bad["C"] = d["C"] + np.array([0, 1, 0, 0])
+    with pytest.raises(S.SbwtGpuError, match="C array does not match"):
+        S.Index(arrays=bad)
+
+
+def test_device_buffers_and_counters():
+    """sbwt_gpu_query_device on torch-owned device memory, plus the rank-op / sector accounting."""
+    import torch
+    name = "small_k31"
+    vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+    reads = read_fasta_reads(golden(name, "reads.fna"))
+    a, off = synth.ragged_to_batch(reads)
+    idx = S.Index(golden(name, "index.sbwt"))
+    ses = S.Session(idx, a.size, len(reads))
+    da, do = torch.from_numpy(a).cuda(), torch.from_numpy(off).cuda()
+    out = torch.full((vals.size,), -7, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+        out.fill_(-7)
+        ses.query_device(da.data_ptr(), do.data_ptr(), len(reads), a.size, mode, out.data_ptr(), vals.size, st)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.cpu().numpy(), vals)
+        stats = ses.query_device_counted(da.data_ptr(), do.data_ptr(), len(reads), a.size, mode, out.data_ptr(), vals.size, st)
+        assert stats.lookups == vals.size and stats.hits == int((vals >= 0).sum())
+        assert stats.rank_ops > 0 and stats.rank_ops % 2 == 0 and 0 < stats.index_sectors <= stats.rank_ops + stats.lookups
+        np.testing.assert_array_equal(out.cpu().numpy(), vals)
+    # per-k-mer search does at least as many rank ops as streaming
+    s1 = ses.query_device_counted(da.data_ptr(), do.data_ptr(), len(reads), a.size, S.MODE_SEARCH, out.data_ptr(), vals.size, st)
+    s2 = ses.query_device_counted(da.data_ptr(), do.data_ptr(), len(reads), a.size, S.MODE_STREAMING, out.data_ptr(), vals.size, st)
+    assert s1.rank_ops >= s2.rank_ops
+
+
+def test_random_differential_vs_oracle(tmp_path):
+    """Fresh seeded cases (several k, p, +-RC): GPU == C oracle on hits, misses, Ns, ragged lengths."""
+    for seed, (k, p, rc) in enumerate([(31, 8, False), (21, 5, True), (32, 8, False), (33, 6, True), (64, 8, False), (12, 12, True), (5, 2, False)]):
+        ref = synth.random_contigs(3, 6000, seed=100 + seed)
+        fa = str(tmp_path / f"r{seed}.fna")
+        synth.write_fasta(fa, [ref[i] for i in range(3)])
+        ix = str(tmp_path / f"i{seed}.sbwt")
+        build_index(fa, ix, k=k, precalc=p, add_rc=rc)
+        rng = np.random.default_rng(200 + seed)
+        reads = []
+        for i in range(700):
+            L = int(rng.integers(1, 5 * k))
+            if i % 3 == 0:
+                s = synth.LUT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+            else:
+                L = min(L, 6000)
+                o = int(rng.integers(0, 6000 - L + 1))
+                s = ref[int(rng.integers(0, 3)), o:o + L].copy()
+                if i % 5 == 0 and L:
+                    s[int(rng.integers(0, L))] = ord("N")
+                if i % 7 == 0 and L:
+                    s[int(rng.integers(0, L))] = synth.LUT[int(rng.integers(0, 4))]
+            reads.append(bytes(s))
+        a, off = synth.ragged_to_batch(reads)
+        orc = oracle.OracleIndex(ix)
+        want = orc.query_batch(a, off, streaming=True)
+        np.testing.assert_array_equal(orc.query_batch(a, off, streaming=False), want)
+        res = run_both(ix, reads)
+        np.testing.assert_array_equal(res[S.MODE_STREAMING], want, err_msg=f"k={k} p={p}")
+        np.testing.assert_array_equal(res[S.MODE_SEARCH], want, err_msg=f"k={k} p={p}")
+
+
+def test_k_above_64_is_refused(tmp_path):
+    d = read_sbwt(golden("small_k63_rc", "index.sbwt"))
+    arrays = dict(bits=[w for _, w in d["bits"]], sgs=d["sgs"][1], C=d["C"], precalc=d["precalc"].reshape(-1), precalc_k=8,
+                  n_nodes=d["n_nodes"], n_kmers=d["n_kmers"], k=65)
+    with pytest.raises(S.SbwtGpuError, match="not supported"):
+        S.Index(arrays=arrays)
+
+
+def test_scale_properties_config2_like(tmp_path):
+    """At a BASELINE-like shape (random reference, 150-bp reads, 50 % planted): streaming == per-k-mer
+    search on the GPU, planted reads hit on all 120 k-mers, random reads miss, and a sample agrees with the oracle."""
+    ref = synth.random_contigs(20, 200_000, seed=42)
+    raw = str(tmp_path / "ref.txt")
+    with open(raw, "wb") as f:
+        for i in range(ref.shape[0]):
+            f.write(ref[i].tobytes() + b"\n")
+    ix = str(tmp_path / "c2.sbwt")
+    info = build_index(raw, ix, k=31, precalc=8, raw=True)
+    assert info["n_kmers"] == 20 * (200_000 - 30)
+    reads = synth.sample_reads(ref, 200_000, 150, 0.5, seed=43)
+    a, off = synth.matrix_to_batch(reads)
+    idx = S.Index(ix)
+    ses = S.Session(idx, a.size, reads.shape[0])
+    s = ses.query_host(a, off, S.MODE_STREAMING)
+    q = ses.query_host(a, off, S.MODE_SEARCH)
+    np.testing.assert_array_equal(s, q)
+    per_read = (s.reshape(-1, 120) >= 0).sum(axis=1)
+    assert set(np.unique(per_read)) <= {0, 120}
+    assert 0.49 < (per_read == 120).mean() < 0.51
+    assert s[s >= 0].min() >= 1 and s.max() < idx.n_nodes
+    orc = oracle.OracleIndex(ix)
+    m = 3000
+    np.testing.assert_array_equal(orc.query_batch(a[:m * 150], off[:m + 1], streaming=True), s[:m * 120])
