@@ -59,7 +59,8 @@ int sbwt_gpu_abi_version(void);
  * vectors (LSB-first 64-bit words, ceil(n_nodes/64) words each) to `device` and re-lays them
  * there as interleaved count+payload sectors. suffix_group_starts may be NULL (index built with
  * --no-streaming-support). precalc_lr holds 4^precalc_k pairs (l,r) as in
- * SBWT::kmer_prefix_precalc (may be NULL iff precalc_k == 0). The caller keeps its arrays. */
+ * SBWT::kmer_prefix_precalc; with precalc_k > 0 and precalc_lr == NULL the table is computed on
+ * the device (SBWT::do_kmer_prefix_precalc, SBWT.hh:617-645). The caller keeps its arrays. */
 int sbwt_gpu_index_create(const uint64_t *const bits[4], const uint64_t *suffix_group_starts,
                           int64_t n_nodes, int64_t n_kmers, int64_t k, const int64_t C[4],
                           const int64_t *precalc_lr, int64_t precalc_k, int device,
@@ -82,6 +83,9 @@ int64_t sbwt_gpu_index_device_bytes(const sbwt_gpu_index *idx);
 /* 1 if every non-suffix-group-start column has an empty subset (true for every index the
  * reference builds; lets the streaming step use one sector instead of a walk-back). */
 int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index *idx);
+
+/* get_precalc(): copies the 4^p (l,r) pairs of the device's table to out_lr (2*4^p values). */
+int sbwt_gpu_index_get_precalc(const sbwt_gpu_index *idx, int64_t *out_lr);
 
 /* SubsetMatrixRank::rank(pos, c) for n host-side queries (positions in [0, n_nodes], chars
  * as bytes; any byte outside ACGT gives 0). Small-batch diagnostic / parity entry point. */

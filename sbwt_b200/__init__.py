@@ -30,7 +30,7 @@ EXPORTS = [
     "sbwt_gpu_query_host", "sbwt_gpu_query_device", "sbwt_gpu_search_batch", "sbwt_gpu_streaming_batch",
     "sbwt_gpu_host_alloc", "sbwt_gpu_host_free", "sbwt_gpu_pack_device",
     "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
-    "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing",
+    "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
 ]
 
 
@@ -65,6 +65,7 @@ def lib():
         L.sbwt_gpu_index_C.argtypes = [vp, vp]
         L.sbwt_gpu_index_C.restype = None
         L.sbwt_gpu_rank.argtypes = [vp, vp, vp, i64, vp]
+        L.sbwt_gpu_index_get_precalc.argtypes = [vp, vp]
         L.sbwt_gpu_session_create.argtypes = [vp, i64, i64, C.POINTER(vp)]
         L.sbwt_gpu_session_destroy.argtypes = [vp]
         L.sbwt_gpu_session_destroy.restype = None
@@ -149,7 +150,7 @@ class Index:
             sgs = None if sgs is None else np.ascontiguousarray(sgs, dtype=np.uint64)
             Carr = np.ascontiguousarray(a["C"], dtype=np.int64)
             pre = a.get("precalc")
-            pre = None if pre is None or a.get("precalc_k", 0) == 0 else np.ascontiguousarray(pre, dtype=np.int64)
+            pre = None if pre is None or a.get("precalc_k", 0) == 0 else np.ascontiguousarray(pre, dtype=np.int64)  # None: computed on device
             _check(lib().sbwt_gpu_index_create(ptrs, None if sgs is None else sgs.ctypes.data, a["n_nodes"], a["n_kmers"], a["k"],
                                                Carr.ctypes.data, None if pre is None else pre.ctypes.data, a.get("precalc_k", 0),
                                                device, C.byref(self._h)))
@@ -179,6 +180,11 @@ class Index:
         out = np.zeros(4, dtype=np.int64)
         lib().sbwt_gpu_index_C(self._h, out.ctypes.data)
         return out.tolist()
+
+    def precalc(self) -> np.ndarray:
+        out = np.empty((4 ** self.precalc_k if self.precalc_k else 0, 2), dtype=np.int64)
+        _check(lib().sbwt_gpu_index_get_precalc(self._h, out.ctypes.data))
+        return out
 
     def rank(self, pos, chars: bytes) -> np.ndarray:
         pos = np.ascontiguousarray(pos, dtype=np.int64)

@@ -235,6 +235,30 @@ __global__ void __launch_bounds__(256) k0_check_edges_kernel(const uint32_t* __r
     if (any & ~sgs[t]) atomicOr(flag, 1);
 }
 
+// ------------------------------------------------------------------ p-mer interval table
+
+// SBWT::do_kmer_prefix_precalc (SBWT.hh:617-645) on the device: one thread per p-mer walks the
+// interval {0, n-1} over its p characters (character j = digit j of the table index).
+template <bool WIDE>
+__global__ void __launch_bounds__(256) precalc_kernel(const DeviceIndexView ix, int p, int64_t* __restrict__ table) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (1ull << (2 * p))) return;
+    int64_t l = 0, r = ix.n_nodes - 1;
+    for (int j = 0; j < p; j++) {
+        const int c = (int)((idx >> (2 * j)) & 3);
+        const BlockPos b0 = split_pos<WIDE>(l), b1 = split_pos<WIDE>(r + 1);
+        const Sector s0 = ld_sector(sector_addr<WIDE>(ix, b0.blk, c));
+        const Sector s1 = ld_sector(sector_addr<WIDE>(ix, b1.blk, c));
+        const int64_t nl = lf_value<WIDE>(ix, s0, b0.blk, b0.off, c);
+        const int64_t nr = lf_value<WIDE>(ix, s1, b1.blk, b1.off, c) - 1;
+        if (nl > nr) { l = r = -1; break; }
+        l = nl;
+        r = nr;
+    }
+    table[2 * idx] = l;
+    table[2 * idx + 1] = r;
+}
+
 // ------------------------------------------------------------------ rank entry point
 
 template <bool WIDE>

@@ -171,7 +171,6 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     if (n_nodes < 1 || k < 1) return set_error("invalid index: n_nodes=%lld k=%lld", (long long)n_nodes, (long long)k);
     if (k > 64) return set_error("k = %lld is not supported by this build (k <= 64)", (long long)k);
     if (p < 0 || p > k || p > 14) return set_error("precalc length %lld is not supported (0 <= p <= min(k,14))", (long long)p);
-    if (p > 0 && !precalc) return set_error("precalc table missing");
     DeviceGuard guard(device);
     sbwt_gpu_index* ix = new sbwt_gpu_index();
     auto fail = [&](int rc) { sbwt_gpu_index_destroy(ix); return rc; };
@@ -245,22 +244,30 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
         CUI(cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
         edges_at_starts = flag ? 0 : 1;
     }
+    DeviceIndexView& v = ix->view;
+    v.sectors = (const Sector*)ix->d_sectors;
+    v.sbbase = (const int64_t*)ix->d_sbbase;
+    v.sgs = (const uint32_t*)ix->d_sgs;
+    v.n_nodes = n_nodes; v.n_blocks = n_blocks; v.n_sb = n_sb;
+    v.k = (int)k; v.p = (int)p; v.sb_shift = sb_shift; v.wide = wide; v.edges_at_starts = edges_at_starts;
     if (p > 0) {
         const size_t bytes = (size_t)16 << (2 * p);
         if (dmalloc(&ix->d_precalc, bytes + 32, &ix->device_bytes)) { cleanup_tmp(); return fail(1); }
         CUI(cudaMemset((char*)ix->d_precalc + bytes, 0xFF, 32));
-        CUI(cudaMemcpy(ix->d_precalc, precalc, bytes, cudaMemcpyHostToDevice));
+        if (precalc) {
+            CUI(cudaMemcpy(ix->d_precalc, precalc, bytes, cudaMemcpyHostToDevice));
+        } else { // SBWT::do_kmer_prefix_precalc on the device
+            const int64_t np = 1ll << (2 * p);
+            if (wide) precalc_kernel<true><<<grid_for(np, 256), 256>>>(v, (int)p, (int64_t*)ix->d_precalc);
+            else precalc_kernel<false><<<grid_for(np, 256), 256>>>(v, (int)p, (int64_t*)ix->d_precalc);
+            LAUNCHED();
+            CUI(cudaGetLastError());
+        }
     }
+    v.precalc = (const int64_t*)ix->d_precalc;
     CUI(cudaDeviceSynchronize());
     cleanup_tmp();
 #undef CUI
-    DeviceIndexView& v = ix->view;
-    v.sectors = (const Sector*)ix->d_sectors;
-    v.sbbase = (const int64_t*)ix->d_sbbase;
-    v.precalc = (const int64_t*)ix->d_precalc;
-    v.sgs = (const uint32_t*)ix->d_sgs;
-    v.n_nodes = n_nodes; v.n_blocks = n_blocks; v.n_sb = n_sb;
-    v.k = (int)k; v.p = (int)p; v.sb_shift = sb_shift; v.wide = wide; v.edges_at_starts = edges_at_starts;
     *out = ix;
     return 0;
 }
@@ -301,6 +308,14 @@ extern "C" int sbwt_gpu_index_device(const sbwt_gpu_index* ix) { return ix->devi
 extern "C" void sbwt_gpu_index_C(const sbwt_gpu_index* ix, int64_t C[4]) { for (int c = 0; c < 4; c++) C[c] = ix->C[c]; }
 extern "C" int64_t sbwt_gpu_index_device_bytes(const sbwt_gpu_index* ix) { return ix->device_bytes; }
 extern "C" int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index* ix) { return ix->view.edges_at_starts; }
+
+extern "C" int sbwt_gpu_index_get_precalc(const sbwt_gpu_index* ix, int64_t* out_lr) {
+    if (!ix || !out_lr) return set_error("null argument");
+    if (ix->precalc_k == 0) return 0;
+    DeviceGuard guard(ix->device);
+    CU(cudaMemcpy(out_lr, ix->d_precalc, (size_t)16 << (2 * ix->precalc_k), cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 extern "C" int sbwt_gpu_rank(sbwt_gpu_index* ix, const int64_t* pos, const char* chars, int64_t n, int64_t* out) {
     if (!ix) return set_error("null index");

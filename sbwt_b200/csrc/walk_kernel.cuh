@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
 
     const int k = ix.k, p = ix.p;
     const uint64_t pmask = p ? ((1ull << (2 * p)) - 1ull) : 0ull;
+    const Sector* const pre_base = reinterpret_cast<const Sector*>(ix.precalc);
 
     Window<NW> win;
     int64_t l = 0, r = 0;     // current interval; in STREAM mode l is the previous column
@@ -137,14 +138,6 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
     int j = 0;                // characters of the current k-mer already consumed
     int mode = M_NEED;
     unsigned long long st_lookups = 0, st_hits = 0, st_ranks = 0, st_sectors = 0;
-
-    // one result for the current k-mer; advances to the next k-mer of the item
-    auto emit = [&](int64_t ans) {
-        P.out[outp++] = ans;
-        if (COUNT) { st_lookups++; st_hits += ans >= 0; }
-        if (--remaining == 0) mode = M_NEED;
-        else win.shift(P.codes, P.invalid);
-    };
 
     while (true) {
         // ---- refill finished lanes from the warp's range
@@ -166,114 +159,96 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
         }
         if (__all_sync(FULL, mode == M_DONE)) break;
 
-        // ---- address phase: what does this lane need from memory?
-        int kind = K_NONE, c = 0;
-        BlockPos b0 = {0, 0}, b1 = {0, 0};
-        const Sector* a0 = ix.sectors;
-        uint32_t pre_hi = 0;
+        // ---- classify: every live lane becomes one of  PRE (table row), STEP (one interval step)
+        //      or INVALID (a k-mer covering a non-ACGT byte: answer -1 without touching memory)
+        const bool from_stream = STREAMING && mode == M_STREAM;
+        bool invalid = false, pre = false, step = false;
         if (mode == M_START) {
-            if (win.any_invalid(k)) {
-                mode = M_START;
-                emit(-1); // a k-mer covering a non-ACGT byte (SBWT.hh:399,428)
-            } else if (p > 0) {
-                const uint64_t pidx = win.b[0] & pmask; // first character = least significant digit (SBWT.hh:396-401)
-                a0 = reinterpret_cast<const Sector*>(ix.precalc) + (pidx >> 1);
-                pre_hi = (uint32_t)(pidx & 1);
-                kind = K_PRE;
-            } else {
-                l = 0;
-                r = ix.n_nodes - 1;
-                j = 0;
-                mode = M_WALK;
+            invalid = win.any_invalid(k);             // SBWT.hh:399,428
+            if (!invalid) {
+                if (p > 0) pre = true;
+                else { l = 0; r = ix.n_nodes - 1; j = 0; step = true; }
             }
-        }
-        if (mode == M_WALK && kind == K_NONE) {
-            c = win.code_at(j);
-            b0 = split_pos<WIDE>(l);
-            b1 = split_pos<WIDE>(r + 1);
-            a0 = sector_addr<WIDE>(ix, b0.blk, c);
-            kind = K_WALK;
-        } else if (STREAMING && mode == M_STREAM) {
-            if (win.invalid_at(k - 1)) {
-                mode = M_START;
-                emit(-1); // SBWT.hh:568
-            } else {
-                c = win.code_at(k - 1);
-                b0 = split_pos<WIDE>(l);
-                a0 = sector_addr<WIDE>(ix, b0.blk, c);
-                kind = K_STREAM;
-            }
+        } else if (mode == M_WALK) {
+            step = true;
+        } else if (from_stream) {
+            invalid = win.invalid_at(k - 1) != 0;     // SBWT.hh:568
+            if (!invalid) { r = l; j = k - 1; step = true; } // one step on [col, col] with the new character
         }
 
-        // ---- load phase
+        // ---- addresses + loads: the same instructions for every kind of lane
+        const int c = win.code_at(j);
+        const BlockPos b0 = split_pos<WIDE>(l), b1 = split_pos<WIDE>(r + 1);
+        const uint64_t pidx = win.b[0] & pmask; // first character = least significant digit (SBWT.hh:396-401)
+        const Sector* a0 = pre ? pre_base + (pidx >> 1) : sector_addr<WIDE>(ix, b0.blk, c);
+        const bool two = step && (b1.blk != b0.blk);
         Sector s0, s1;
-        const bool two = (kind == K_WALK) && (b1.blk != b0.blk);
-        if (kind != K_NONE) s0 = ld_sector(a0);
+        if (pre || step) s0 = ld_sector(a0);
         if (two) s1 = ld_sector(sector_addr<WIDE>(ix, b1.blk, c));
 
-        // ---- consume phase
-        if (kind == K_PRE) {
-            const uint32_t e0 = pre_hi ? s0.w[4] : s0.w[0], e1 = pre_hi ? s0.w[5] : s0.w[1];
-            const uint32_t e2 = pre_hi ? s0.w[6] : s0.w[2], e3 = pre_hi ? s0.w[7] : s0.w[3];
-            l = (int64_t)(((uint64_t)e1 << 32) | e0);
-            r = (int64_t)(((uint64_t)e3 << 32) | e2);
+        // ---- consume
+        int64_t nl, nr;
+        {
+            uint32_t vl = sector_rank(s0, b0.off);
+            uint32_t vr = sector_rank(two ? s1 : s0, b1.off);
+            nl = (int64_t)vl;
+            nr = (int64_t)vr;
+            if (WIDE && step) {
+                nl += __ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b0.blk >> ix.sb_shift));
+                nr += __ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b1.blk >> ix.sb_shift));
+            }
+            nr -= 1;
+        }
+        if (pre) {
+            const bool hi = (pidx & 1) != 0;
+            const uint32_t e0 = hi ? s0.w[4] : s0.w[0], e1 = hi ? s0.w[5] : s0.w[1];
+            const uint32_t e2 = hi ? s0.w[6] : s0.w[2], e3 = hi ? s0.w[7] : s0.w[3];
+            nl = (int64_t)(((uint64_t)e1 << 32) | e0);
+            nr = (int64_t)(((uint64_t)e3 << 32) | e2);
+        }
+        bool miss = pre ? (nl < 0) : (nl > nr); // absent p-mer (SBWT.hh:424) / empty interval (SBWT.hh:433)
+        if (COUNT) {
+            if (step) { st_ranks += 2; st_sectors += two ? 2 : 1; }
+            if (pre) st_sectors++;
+        }
+        if (STREAMING && from_stream && step && (miss || !ix.edges_at_starts)) {
+            // literal form (SBWT.hh:562-563): the step must start from the suffix-group start of col.
+            // With edges only at group starts a set bit proves col is the start, so only a clear bit
+            // (or an index that violates the invariant) gets here.
+            int64_t s = l;
+            while (true) {
+                const uint32_t w = __ldg(ix.sgs + (s >> 5)) & (0xFFFFFFFFu >> (31 - (int)(s & 31)));
+                if (w) { s = (s & ~31ll) + (31 - __clz(w)); break; }
+                s = (s & ~31ll) - 1;
+            }
             if (COUNT) st_sectors++;
-            if (l < 0) {
-                mode = M_START;
-                emit(-1); // p-mer absent (SBWT.hh:424)
-            } else if (p == k) {
-                mode = STREAMING ? M_STREAM : M_START;
-                emit(l);
-            } else {
-                j = p;
-                mode = M_WALK;
+            if (s != l) {
+                const BlockPos bs = split_pos<WIDE>(s);
+                const Sector ss = ld_sector(sector_addr<WIDE>(ix, bs.blk, c));
+                if (COUNT) st_sectors += bs.blk != b0.blk;
+                miss = sector_bit(ss, bs.off) == 0;
+                nl = lf_value<WIDE>(ix, ss, bs.blk, bs.off, c);
+                nr = nl;
             }
-        } else if (kind == K_WALK) {
-            const int64_t nl = lf_value<WIDE>(ix, s0, b0.blk, b0.off, c);
-            const int64_t nr = lf_value<WIDE>(ix, two ? s1 : s0, b1.blk, b1.off, c) - 1;
-            if (COUNT) { st_ranks += 2; st_sectors += two ? 2 : 1; }
-            if (nl > nr) {
-                mode = M_START;
-                emit(-1); // SBWT.hh:433
-            } else {
-                l = nl;
-                r = nr;
-                if (++j == k) {
-                    // a k-mer interval is a singleton (SBWT.hh:410-413 aborts otherwise)
-                    mode = STREAMING ? M_STREAM : M_START;
-                    emit(nl);
-                }
-            }
-        } else if (STREAMING && kind == K_STREAM) {
-            uint32_t bit = sector_bit(s0, b0.off);
-            int64_t ans;
-            if (COUNT) { st_ranks += 2; st_sectors++; }
-            if (bit && ix.edges_at_starts) {
-                ans = lf_value<WIDE>(ix, s0, b0.blk, b0.off, c);
-            } else {
-                // literal form: walk back to the suffix-group start (SBWT.hh:562-563)
-                int64_t s = l;
-                while (true) {
-                    const uint32_t w = __ldg(ix.sgs + (s >> 5)) & (0xFFFFFFFFu >> (31 - (int)(s & 31)));
-                    if (w) { s = (s & ~31ll) + (31 - __clz(w)); break; }
-                    s = (s & ~31ll) - 1;
-                }
-                if (COUNT) st_sectors++;
-                if (s != l) {
-                    const BlockPos bs = split_pos<WIDE>(s);
-                    if (bs.blk != b0.blk) {
-                        s0 = ld_sector(sector_addr<WIDE>(ix, bs.blk, c));
-                        if (COUNT) st_sectors++;
-                    }
-                    bit = sector_bit(s0, bs.off);
-                    ans = bit ? lf_value<WIDE>(ix, s0, bs.blk, bs.off, c) : -1;
-                } else {
-                    ans = bit ? lf_value<WIDE>(ix, s0, b0.blk, b0.off, c) : -1;
-                }
-            }
-            l = ans;
-            mode = ans >= 0 ? M_STREAM : M_START;
-            emit(ans);
+        }
+        const int nj = pre ? p : j + 1;
+        const bool done = (pre || step) && !miss && nj == k; // a k-mer interval is a singleton (SBWT.hh:410-413)
+        if (pre || step) {
+            l = nl;
+            r = nr;
+            j = nj;
+            mode = M_WALK;
+        }
+
+        // ---- emit: one result, advance to the next k-mer of the item
+        if (invalid || ((pre || step) && (miss || done))) {
+            const int64_t ans = done ? nl : -1;
+            __stcs(P.out + outp, ans);
+            outp++;
+            if (COUNT) { st_lookups++; st_hits += ans >= 0; }
+            mode = (STREAMING && done) ? M_STREAM : M_START;
+            if (--remaining == 0) mode = M_NEED;
+            else win.shift(P.codes, P.invalid);
         }
     }
 
