@@ -70,6 +70,39 @@ __device__ __forceinline__ uint32_t sector_rank(const Sector& s, uint32_t o) {
     return r;
 }
 
+// The same quantity with the work moved off the integer-ALU pipe (the walk is ALU-bound, ncu
+// r01): the popcounts of payload words 0..5 are packed into bytes and turned into exclusive
+// prefix sums with two multiplies (IMAD runs on the otherwise idle FMA pipe); one PRMT then
+// picks the prefix of the word that holds the position, and only that word is masked.
+//   X = [0, s1, s2, s3]   Y = [s4, s5, s6, *]   with s_f = ones in payload words [0, f)
+struct SectorPrefix {
+    uint32_t X, Y;
+};
+
+__device__ __forceinline__ SectorPrefix sector_prefix(const Sector& s) {
+    const uint32_t pc0 = __popc(s.w[1]), pc1 = __popc(s.w[2]), pc2 = __popc(s.w[3]), pc3 = __popc(s.w[4]);
+    const uint32_t pc4 = __popc(s.w[5]), pc5 = __popc(s.w[6]);
+    const uint32_t P = pc0 + pc1 * 0x100u + pc2 * 0x10000u + pc3 * 0x1000000u;
+    const uint32_t Q = P * 0x01010101u; // byte j = pc0 + ... + pcj  (<= 128, no carries)
+    SectorPrefix r;
+    r.X = Q << 8;
+    r.Y = (Q >> 24) * 0x010101u + pc4 * 0x010100u + pc5 * 0x010000u; // [s4, s4+pc4, s4+pc4+pc5]
+    return r;
+}
+
+__device__ __forceinline__ uint32_t sector_word(const Sector& s, uint32_t f) { // payload word f (0..6)
+    const bool b0 = f & 1u, b1 = f & 2u, b2 = f & 4u;
+    const uint32_t t0 = b0 ? s.w[2] : s.w[1], t1 = b0 ? s.w[4] : s.w[3], t2 = b0 ? s.w[6] : s.w[5];
+    const uint32_t u0 = b1 ? t1 : t0, u1 = b1 ? s.w[7] : t2;
+    return b2 ? u1 : u0;
+}
+
+__device__ __forceinline__ uint32_t sector_rank_fast(const Sector& s, const SectorPrefix& pf, uint32_t o) {
+    const uint32_t f = o >> 5, rem = o & 31u;
+    const uint32_t w = sector_word(s, f);
+    return s.w[0] + __byte_perm(pf.X, pf.Y, f) + __popc(w & ((1u << rem) - 1u));
+}
+
 // payload bit at in-block offset o.
 __device__ __forceinline__ uint32_t sector_bit(const Sector& s, uint32_t o) {
     const uint32_t wi = o >> 5;

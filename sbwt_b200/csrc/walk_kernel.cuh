@@ -6,22 +6,29 @@
 //
 // Work item = up to `window` consecutive k-mers of one read (a whole read when it is short).
 // One LANE owns one item at a time and is a small state machine; every trip of the warp loop
-// each lane performs at most one memory round trip of whatever kind it needs next:
+// each lane performs at most one memory round trip, and every kind of round trip runs through
+// the SAME instructions (the first profile of this kernel was integer-ALU bound with 14 of 32
+// lanes active per instruction, profiles/r01_walk_v1_summary.txt):
 //
-//   START   first p characters -> row of the precalc table (kmer_prefix_precalc, SBWT.hh:404)
-//   WALK    one interval step  [l,r] -> [C[c]+rank_c(l), C[c]+rank_c(r+1)-1]  (two sectors,
-//           one when l and r+1 fall into the same 224-column block)
-//   STREAM  previous k-mer was found at column `col`: one sector holding bit_c(col) and
-//           C[c]+rank_c(col). In a reference-built index only suffix-group starts carry edges
-//           (SURVEY.md section 8(a) note 7), so bit_c(col)==1 already proves col is the group
-//           start and the answer is C[c]+rank_c(col); otherwise the literal walk-back over
-//           suffix_group_starts (SBWT.hh:562-563) runs on a slow path.
+//   PRE    first p characters -> row of the precalc table (kmer_prefix_precalc, SBWT.hh:404);
+//          the row is fetched with the same 256-bit load as a sector
+//   STEP   one interval step  [l,r] -> [C[c]+rank_c(l), C[c]+rank_c(r+1)-1]  (two sectors, one
+//          when l and r+1 fall into the same 224-column block). A streaming step (previous k-mer
+//          found at column col, SBWT.hh:561-575) is the same step on [col, col] with the new
+//          character: in a reference-built index only suffix-group starts carry edges
+//          (SURVEY.md section 8(a) note 7), so a set bit_c(col) already proves col is the group
+//          start; a clear bit (or an index violating the invariant) takes the literal
+//          walk-back over suffix_group_starts on a slow path.
 //
-// so lanes that sit in a long from-scratch walk, lanes that stream along a matching read and
-// lanes that just fetched a new read all keep one or two independent sector loads in flight --
-// the pointer chase is hidden by the ~2000 resident lanes per SM, not by ILP inside a lane.
-// Finished lanes refill from the warp's own contiguous item range (ballot/popc, no atomics).
+// Everything that happens once per k-mer rather than once per step -- storing the result,
+// sliding the read window, validity checks, choosing the next table row -- lives in one
+// divergent ADVANCE block, so lanes in long from-scratch walks, lanes streaming along a matching
+// read and lanes that just fetched a read share the step code at full width. The pointer chase
+// is hidden by the ~1000-2000 resident lanes per SM, each with one or two sector loads in
+// flight. Finished lanes refill from the warp's own contiguous item range (ballot/popc).
 #pragma once
+
+#include <type_traits>
 
 #include "device_index.cuh"
 
@@ -39,8 +46,7 @@ struct WalkParams {
     unsigned long long* stats; // [lookups, hits, rank_ops, sectors] (COUNT only)
 };
 
-enum : int { M_NEED = 0, M_START = 1, M_WALK = 2, M_STREAM = 3, M_DONE = 4 };
-enum : int { K_NONE = 0, K_PRE = 1, K_WALK = 2, K_STREAM = 3 };
+enum : int { M_NEED = 0, M_PRE = 1, M_STEP = 2, M_DONE = 3 };
 
 // Sliding window over the packed read: base t of the window (t = 0 is the first character of
 // the current k-mer) sits at bits [2(t%32), 2(t%32)+2) of b[t/32]; v holds the invalid flags.
@@ -116,6 +122,7 @@ struct Window {
 
 template <int NW, bool STREAMING, bool WIDE, bool COUNT>
 __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
+    typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t; // columns fit 32 bits in narrow mode
     const DeviceIndexView& ix = P.ix;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -128,16 +135,49 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
     const int64_t end = (int64_t)(((__int128)n_items * (gw + 1)) / nw);
 
     const int k = ix.k, p = ix.p;
-    const uint64_t pmask = p ? ((1ull << (2 * p)) - 1ull) : 0ull;
+    const uint32_t pmask = p ? (uint32_t)((1ull << (2 * p)) - 1ull) : 0u;
     const Sector* const pre_base = reinterpret_cast<const Sector*>(ix.precalc);
+    const Sector* const sec_base = ix.sectors;
 
     Window<NW> win;
-    int64_t l = 0, r = 0;     // current interval; in STREAM mode l is the previous column
+    pos_t l = 0, r = 0;       // STEP: current interval.  PRE: l = table row pair index, r = parity
     int64_t outp = 0;         // next result slot
     int remaining = 0;        // k-mers left in the item, current one included
     int j = 0;                // characters of the current k-mer already consumed
     int mode = M_NEED;
+    bool fs = false;          // this STEP is a streaming step (previous k-mer was found at column l)
     unsigned long long st_lookups = 0, st_hits = 0, st_ranks = 0, st_sectors = 0;
+
+    // Runs when a lane moves on to a new k-mer (window already positioned on it): answers k-mers
+    // that cover a non-ACGT byte on the spot (SBWT.hh:399,428,568) and leaves the lane in PRE or
+    // STEP mode for the first k-mer that needs memory, or in NEED mode when the item is exhausted.
+    auto setup = [&](bool stream) {
+        while (true) {
+            if (remaining == 0) { mode = M_NEED; return; }
+            if (STREAMING && stream) {
+                if (!win.invalid_at(k - 1)) { r = l; j = k - 1; fs = true; mode = M_STEP; return; }
+            } else if (!win.any_invalid(k)) {
+                fs = false;
+                if (p > 0) {
+                    const uint32_t pidx = (uint32_t)win.b[0] & pmask; // first character = least significant digit (SBWT.hh:396-401)
+                    l = (pos_t)(pidx >> 1);
+                    r = (pos_t)(pidx & 1u);
+                    mode = M_PRE;
+                } else {
+                    l = 0;
+                    r = (pos_t)(ix.n_nodes - 1);
+                    j = 0;
+                    mode = M_STEP;
+                }
+                return;
+            }
+            __stcs(P.out + outp, (int64_t)-1);
+            outp++;
+            if (COUNT) st_lookups++;
+            stream = false;
+            if (--remaining) win.shift(P.codes, P.invalid);
+        }
+    };
 
     while (true) {
         // ---- refill finished lanes from the warp's range
@@ -151,104 +191,86 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
                     outp = P.item_out[mine];
                     remaining = P.item_cnt[mine];
                     win.init(P.codes, P.invalid, g);
-                    mode = M_START;
+                    setup(false);
                 } else {
                     mode = M_DONE;
                 }
             }
-        }
-        if (__all_sync(FULL, mode == M_DONE)) break;
-
-        // ---- classify: every live lane becomes one of  PRE (table row), STEP (one interval step)
-        //      or INVALID (a k-mer covering a non-ACGT byte: answer -1 without touching memory)
-        const bool from_stream = STREAMING && mode == M_STREAM;
-        bool invalid = false, pre = false, step = false;
-        if (mode == M_START) {
-            invalid = win.any_invalid(k);             // SBWT.hh:399,428
-            if (!invalid) {
-                if (p > 0) pre = true;
-                else { l = 0; r = ix.n_nodes - 1; j = 0; step = true; }
-            }
-        } else if (mode == M_WALK) {
-            step = true;
-        } else if (from_stream) {
-            invalid = win.invalid_at(k - 1) != 0;     // SBWT.hh:568
-            if (!invalid) { r = l; j = k - 1; step = true; } // one step on [col, col] with the new character
+            if (__all_sync(FULL, mode == M_DONE)) break;
         }
 
-        // ---- addresses + loads: the same instructions for every kind of lane
+        // ---- STEP / PRE: the same instructions for every live lane
+        const bool pre = mode == M_PRE, step = mode == M_STEP;
         const int c = win.code_at(j);
-        const BlockPos b0 = split_pos<WIDE>(l), b1 = split_pos<WIDE>(r + 1);
-        const uint64_t pidx = win.b[0] & pmask; // first character = least significant digit (SBWT.hh:396-401)
-        const Sector* a0 = pre ? pre_base + (pidx >> 1) : sector_addr<WIDE>(ix, b0.blk, c);
+        const BlockPos b0 = split_pos<WIDE>((int64_t)l), b1 = split_pos<WIDE>((int64_t)r + 1);
+        const Sector* a0 = pre ? pre_base + l : sec_base + ((b0.blk << 2) + c);
         const bool two = step && (b1.blk != b0.blk);
         Sector s0, s1;
         if (pre || step) s0 = ld_sector(a0);
-        if (two) s1 = ld_sector(sector_addr<WIDE>(ix, b1.blk, c));
+        if (two) s1 = ld_sector(sec_base + ((b1.blk << 2) + c));
+        else s1 = s0;
 
-        // ---- consume
-        int64_t nl, nr;
-        {
-            uint32_t vl = sector_rank(s0, b0.off);
-            uint32_t vr = sector_rank(two ? s1 : s0, b1.off);
-            nl = (int64_t)vl;
-            nr = (int64_t)vr;
-            if (WIDE && step) {
-                nl += __ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b0.blk >> ix.sb_shift));
-                nr += __ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b1.blk >> ix.sb_shift));
-            }
-            nr -= 1;
+        const SectorPrefix pf0 = sector_prefix(s0);
+        const SectorPrefix pf1 = two ? sector_prefix(s1) : pf0;
+        pos_t nl = (pos_t)sector_rank_fast(s0, pf0, b0.off);
+        pos_t nr = (pos_t)sector_rank_fast(s1, pf1, b1.off);
+        if (WIDE && step) {
+            nl += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b0.blk >> ix.sb_shift));
+            nr += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b1.blk >> ix.sb_shift));
         }
+        nr -= 1;
+        bool miss = nl > nr; // empty interval (SBWT.hh:433)
         if (pre) {
-            const bool hi = (pidx & 1) != 0;
+            const bool hi = r != 0;
             const uint32_t e0 = hi ? s0.w[4] : s0.w[0], e1 = hi ? s0.w[5] : s0.w[1];
             const uint32_t e2 = hi ? s0.w[6] : s0.w[2], e3 = hi ? s0.w[7] : s0.w[3];
-            nl = (int64_t)(((uint64_t)e1 << 32) | e0);
-            nr = (int64_t)(((uint64_t)e3 << 32) | e2);
+            nl = WIDE ? (pos_t)(((uint64_t)e1 << 32) | e0) : (pos_t)e0;
+            nr = WIDE ? (pos_t)(((uint64_t)e3 << 32) | e2) : (pos_t)e2;
+            miss = (int32_t)e1 < 0; // absent p-mer: {-1,-1} (SBWT.hh:424)
         }
-        bool miss = pre ? (nl < 0) : (nl > nr); // absent p-mer (SBWT.hh:424) / empty interval (SBWT.hh:433)
         if (COUNT) {
             if (step) { st_ranks += 2; st_sectors += two ? 2 : 1; }
             if (pre) st_sectors++;
         }
-        if (STREAMING && from_stream && step && (miss || !ix.edges_at_starts)) {
-            // literal form (SBWT.hh:562-563): the step must start from the suffix-group start of col.
-            // With edges only at group starts a set bit proves col is the start, so only a clear bit
-            // (or an index that violates the invariant) gets here.
-            int64_t s = l;
+        if (STREAMING && fs && step && (miss || !ix.edges_at_starts)) {
+            // literal form (SBWT.hh:562-563): the step has to start from the suffix-group start of
+            // column l. With edges only at group starts a set bit proves l is the start, so only a
+            // clear bit (or an index that violates the invariant) gets here.
+            int64_t s = (int64_t)l;
             while (true) {
                 const uint32_t w = __ldg(ix.sgs + (s >> 5)) & (0xFFFFFFFFu >> (31 - (int)(s & 31)));
                 if (w) { s = (s & ~31ll) + (31 - __clz(w)); break; }
                 s = (s & ~31ll) - 1;
             }
             if (COUNT) st_sectors++;
-            if (s != l) {
+            if (s != (int64_t)l) {
                 const BlockPos bs = split_pos<WIDE>(s);
-                const Sector ss = ld_sector(sector_addr<WIDE>(ix, bs.blk, c));
+                const Sector ss = ld_sector(sec_base + ((bs.blk << 2) + c));
                 if (COUNT) st_sectors += bs.blk != b0.blk;
                 miss = sector_bit(ss, bs.off) == 0;
-                nl = lf_value<WIDE>(ix, ss, bs.blk, bs.off, c);
+                nl = (pos_t)lf_value<WIDE>(ix, ss, bs.blk, bs.off, c);
                 nr = nl;
             }
         }
         const int nj = pre ? p : j + 1;
-        const bool done = (pre || step) && !miss && nj == k; // a k-mer interval is a singleton (SBWT.hh:410-413)
-        if (pre || step) {
+        const bool live = pre || step;
+        const bool done = live && !miss && nj == k; // a k-mer interval is a singleton (SBWT.hh:410-413)
+        if (live) {
             l = nl;
             r = nr;
             j = nj;
-            mode = M_WALK;
+            mode = M_STEP;
+            fs = false;
         }
 
-        // ---- emit: one result, advance to the next k-mer of the item
-        if (invalid || ((pre || step) && (miss || done))) {
-            const int64_t ans = done ? nl : -1;
+        // ---- ADVANCE: one result, slide to the next k-mer of the item
+        if (live && (miss || done)) {
+            const int64_t ans = done ? (int64_t)nl : (int64_t)-1;
             __stcs(P.out + outp, ans);
             outp++;
-            if (COUNT) { st_lookups++; st_hits += ans >= 0; }
-            mode = (STREAMING && done) ? M_STREAM : M_START;
-            if (--remaining == 0) mode = M_NEED;
-            else win.shift(P.codes, P.invalid);
+            if (COUNT) { st_lookups++; st_hits += done; }
+            if (--remaining) win.shift(P.codes, P.invalid);
+            setup(done);
         }
     }
 
