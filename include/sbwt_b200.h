@@ -84,6 +84,15 @@ int64_t sbwt_gpu_index_device_bytes(const sbwt_gpu_index *idx);
  * reference builds; lets the streaming step use one sector instead of a walk-back). */
 int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index *idx);
 
+/* The walk starts from a device-side table of the intervals of all tp-mers. By default tp is a
+ * few characters longer than the file's precalc length (runtime only: built on the device from
+ * the bit vectors, never serialized; results are identical because a table row is exactly the
+ * interval the walk would reach, SBWT.hh:617-645). set_table_length rebuilds it (0 = no table,
+ * every search walks all k characters as with precalc_k == 0). If the file's own table does not
+ * follow from its bit vectors only tp == precalc_k is accepted. */
+int sbwt_gpu_index_set_table_length(sbwt_gpu_index *idx, int tp);
+int sbwt_gpu_index_table_length(const sbwt_gpu_index *idx);
+
 /* get_precalc(): copies the 4^p (l,r) pairs of the device's table to out_lr (2*4^p values). */
 int sbwt_gpu_index_get_precalc(const sbwt_gpu_index *idx, int64_t *out_lr);
 

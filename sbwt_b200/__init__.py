@@ -31,6 +31,7 @@ EXPORTS = [
     "sbwt_gpu_host_alloc", "sbwt_gpu_host_free", "sbwt_gpu_pack_device",
     "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
     "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
+    "sbwt_gpu_index_set_table_length", "sbwt_gpu_index_table_length",
 ]
 
 
@@ -66,6 +67,8 @@ def lib():
         L.sbwt_gpu_index_C.restype = None
         L.sbwt_gpu_rank.argtypes = [vp, vp, vp, i64, vp]
         L.sbwt_gpu_index_get_precalc.argtypes = [vp, vp]
+        L.sbwt_gpu_index_set_table_length.argtypes = [vp, i32]
+        L.sbwt_gpu_index_table_length.argtypes = [vp]
         L.sbwt_gpu_session_create.argtypes = [vp, i64, i64, C.POINTER(vp)]
         L.sbwt_gpu_session_destroy.argtypes = [vp]
         L.sbwt_gpu_session_destroy.restype = None
@@ -180,6 +183,13 @@ class Index:
         out = np.zeros(4, dtype=np.int64)
         lib().sbwt_gpu_index_C(self._h, out.ctypes.data)
         return out.tolist()
+
+    @property
+    def table_length(self) -> int:
+        return lib().sbwt_gpu_index_table_length(self._h)
+
+    def set_table_length(self, tp: int) -> None:
+        _check(lib().sbwt_gpu_index_set_table_length(self._h, tp))
 
     def precalc(self) -> np.ndarray:
         out = np.empty((4 ** self.precalc_k if self.precalc_k else 0, 2), dtype=np.int64)

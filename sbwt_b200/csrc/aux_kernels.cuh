@@ -239,8 +239,9 @@ __global__ void __launch_bounds__(256) k0_check_edges_kernel(const uint32_t* __r
 
 // SBWT::do_kmer_prefix_precalc (SBWT.hh:617-645) on the device: one thread per p-mer walks the
 // interval {0, n-1} over its p characters (character j = digit j of the table index).
-template <bool WIDE>
-__global__ void __launch_bounds__(256) precalc_kernel(const DeviceIndexView ix, int p, int64_t* __restrict__ table) {
+// COMPACT writes {u32 l, u32 r} rows (narrow indexes), otherwise {i64 l, i64 r} as in the file.
+template <bool WIDE, bool COMPACT>
+__global__ void __launch_bounds__(256) precalc_kernel(const DeviceIndexView ix, int p, void* __restrict__ table) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (1ull << (2 * p))) return;
     int64_t l = 0, r = ix.n_nodes - 1;
@@ -255,8 +256,25 @@ __global__ void __launch_bounds__(256) precalc_kernel(const DeviceIndexView ix, 
         l = nl;
         r = nr;
     }
-    table[2 * idx] = l;
-    table[2 * idx + 1] = r;
+    if (COMPACT) {
+        reinterpret_cast<uint2*>(table)[idx] = make_uint2((uint32_t)l, (uint32_t)r);
+    } else {
+        reinterpret_cast<int64_t*>(table)[2 * idx] = l;
+        reinterpret_cast<int64_t*>(table)[2 * idx + 1] = r;
+    }
+}
+
+// file-format table (i64 pairs) -> compact rows
+__global__ void __launch_bounds__(256) table_compact_kernel(const int64_t* __restrict__ src, int64_t n, uint2* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_uint2((uint32_t)src[2 * i], (uint32_t)src[2 * i + 1]);
+}
+
+// flag |= 1 where two tables differ
+__global__ void __launch_bounds__(256) table_compare_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, int64_t n,
+                                                            int* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) atomicOr(flag, 1);
 }
 
 // ------------------------------------------------------------------ rank entry point

@@ -36,7 +36,11 @@ struct __align__(32) Sector {
 struct DeviceIndexView {
     const Sector* sectors;     // [n_blocks][4]
     const int64_t* sbbase;     // [4][n_sb], wide mode only
-    const int64_t* precalc;    // 4^p pairs (l, r), 32-byte aligned; nullptr if p == 0
+    const int64_t* precalc;    // the file's table: 4^p pairs (l, r) as int64; nullptr if p == 0
+    const void* table;         // search table over the first tp characters (see walk_kernel.cuh):
+                               //   narrow: 4^tp x {u32 l, u32 r}, 4 rows per sector, absent = {0xFFFFFFFF, 0xFFFFFFFF}
+                               //   wide:   4^tp x {i64 l, i64 r}, 2 rows per sector, absent = {-1, -1}
+    int tp;                    // 0 = no table
     const uint32_t* sgs;       // suffix_group_starts as u32 words (padded), nullptr if absent
     int64_t n_nodes;
     int64_t n_blocks;
@@ -55,6 +59,23 @@ __device__ __forceinline__ Sector ld_sector(const Sector* p) {
                  : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]), "=r"(s.w[4]), "=r"(s.w[5]),
                    "=r"(s.w[6]), "=r"(s.w[7])
                  : "l"(p));
+    return s;
+}
+
+// Same load with an L2 eviction policy (createpolicy): evict_last keeps the index resident in
+// L2 while reads and results stream through it.
+__device__ __forceinline__ uint64_t make_l2_policy(bool evict_last) {
+    uint64_t pol;
+    if (evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ Sector ld_sector(const Sector* p, uint64_t pol) {
+    Sector s;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]), "=r"(s.w[4]), "=r"(s.w[5]),
+                   "=r"(s.w[6]), "=r"(s.w[7])
+                 : "l"(p), "l"(pol));
     return s;
 }
 

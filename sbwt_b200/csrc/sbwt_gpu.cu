@@ -67,6 +67,9 @@ struct sbwt_gpu_index {
     void* d_sectors = nullptr;
     void* d_sbbase = nullptr;
     void* d_precalc = nullptr;
+    void* d_table = nullptr;
+    int64_t table_bytes = 0;
+    bool table_from_bits = true; // the file's table equals what the bit vectors imply, so any table length is admissible
     void* d_sgs = nullptr;
 };
 
@@ -162,6 +165,8 @@ extern "C" int64_t sbwt_gpu_count_outputs(const int64_t* off, int64_t n_reads, i
 
 // ------------------------------------------------------------------ API: index
 
+extern "C" int sbwt_gpu_index_set_table_length(sbwt_gpu_index* ix, int tp);
+
 static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs, int64_t n_nodes, int64_t n_kmers,
                              int64_t k, const int64_t C[4], const int64_t* precalc, int64_t p, int device,
                              sbwt_gpu_index** out) {
@@ -252,14 +257,27 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     v.k = (int)k; v.p = (int)p; v.sb_shift = sb_shift; v.wide = wide; v.edges_at_starts = edges_at_starts;
     if (p > 0) {
         const size_t bytes = (size_t)16 << (2 * p);
+        const int64_t np = 1ll << (2 * p);
         if (dmalloc(&ix->d_precalc, bytes + 32, &ix->device_bytes)) { cleanup_tmp(); return fail(1); }
         CUI(cudaMemset((char*)ix->d_precalc + bytes, 0xFF, 32));
         if (precalc) {
+            // keep the file's table verbatim, and check it against SBWT::do_kmer_prefix_precalc on the device
             CUI(cudaMemcpy(ix->d_precalc, precalc, bytes, cudaMemcpyHostToDevice));
+            int64_t* d_chk = nullptr;
+            CUI(cudaMalloc(&d_chk, bytes));
+            if (wide) precalc_kernel<true, false><<<grid_for(np, 256), 256>>>(v, (int)p, d_chk);
+            else precalc_kernel<false, false><<<grid_for(np, 256), 256>>>(v, (int)p, d_chk);
+            LAUNCHED();
+            CUI(cudaMemset(d_flag, 0, 4));
+            table_compare_kernel<<<grid_for(2 * np, 256), 256>>>((const int64_t*)ix->d_precalc, d_chk, 2 * np, d_flag); LAUNCHED();
+            int flag = 0;
+            cudaError_t e1 = cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost);
+            cudaFree(d_chk);
+            CUI(e1);
+            ix->table_from_bits = flag == 0;
         } else { // SBWT::do_kmer_prefix_precalc on the device
-            const int64_t np = 1ll << (2 * p);
-            if (wide) precalc_kernel<true><<<grid_for(np, 256), 256>>>(v, (int)p, (int64_t*)ix->d_precalc);
-            else precalc_kernel<false><<<grid_for(np, 256), 256>>>(v, (int)p, (int64_t*)ix->d_precalc);
+            if (wide) precalc_kernel<true, false><<<grid_for(np, 256), 256>>>(v, (int)p, ix->d_precalc);
+            else precalc_kernel<false, false><<<grid_for(np, 256), 256>>>(v, (int)p, ix->d_precalc);
             LAUNCHED();
             CUI(cudaGetLastError());
         }
@@ -268,9 +286,58 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     CUI(cudaDeviceSynchronize());
     cleanup_tmp();
 #undef CUI
+    // search table: by default a few characters longer than the file's (same results, fewer dependent steps)
+    int tp = (int)p;
+    if (ix->table_from_bits) {
+        const char* e = getenv("SBWT_B200_TABLE_P");
+        if (e) tp = atoi(e);
+        else {
+            // longest table that stays below half the size of the sector array (it shares L2 / HBM with it)
+            tp = (int)std::min<int64_t>(std::max<int64_t>(p, 12), k);
+            while (tp > p && ((int64_t)(wide ? 16 : 8) << (2 * tp)) > std::max<int64_t>(4 * n_blocks * (int64_t)sizeof(Sector) / 2, 1 << 20)) tp--;
+        }
+    }
+    if (int rc = sbwt_gpu_index_set_table_length(ix, tp)) { sbwt_gpu_index_destroy(ix); return rc; }
     *out = ix;
     return 0;
 }
+
+extern "C" int sbwt_gpu_index_set_table_length(sbwt_gpu_index* ix, int tp) {
+    if (!ix) return set_error("null index");
+    if (tp < 0) return set_error("negative table length");
+    if (tp > ix->k) tp = (int)ix->k;
+    if (tp > 13) tp = 13;
+    if (!ix->table_from_bits && tp != ix->precalc_k)
+        return set_error("the file's precalc table does not follow from its bit vectors; only its own length (%lld) can be used", (long long)ix->precalc_k);
+    DeviceGuard guard(ix->device);
+    CU(cudaDeviceSynchronize());
+    if (ix->d_table) { cudaFree(ix->d_table); ix->device_bytes -= ix->table_bytes; ix->d_table = nullptr; ix->table_bytes = 0; }
+    DeviceIndexView& v = ix->view;
+    v.table = nullptr;
+    v.tp = 0;
+    if (tp == 0) return 0;
+    const int64_t np = 1ll << (2 * tp);
+    const bool wide = v.wide;
+    ix->table_bytes = np * (wide ? 16 : 8) + 32;
+    CU(cudaMalloc(&ix->d_table, ix->table_bytes));
+    ix->device_bytes += ix->table_bytes;
+    CU(cudaMemset((char*)ix->d_table + ix->table_bytes - 32, 0xFF, 32));
+    if (tp == ix->precalc_k) { // the file's own table, re-encoded
+        if (wide) CU(cudaMemcpy(ix->d_table, ix->d_precalc, np * 16, cudaMemcpyDeviceToDevice));
+        else { table_compact_kernel<<<grid_for(np, 256), 256>>>((const int64_t*)ix->d_precalc, np, (uint2*)ix->d_table); LAUNCHED(); }
+    } else {
+        if (wide) precalc_kernel<true, false><<<grid_for(np, 256), 256>>>(v, tp, ix->d_table);
+        else precalc_kernel<false, true><<<grid_for(np, 256), 256>>>(v, tp, ix->d_table);
+        LAUNCHED();
+    }
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    v.table = ix->d_table;
+    v.tp = tp;
+    return 0;
+}
+
+extern "C" int sbwt_gpu_index_table_length(const sbwt_gpu_index* ix) { return ix ? ix->view.tp : 0; }
 
 extern "C" int sbwt_gpu_index_create(const uint64_t* const bits[4], const uint64_t* sgs, int64_t n_nodes, int64_t n_kmers,
                                      int64_t k, const int64_t C[4], const int64_t* precalc, int64_t p, int device,
@@ -295,7 +362,7 @@ extern "C" int sbwt_gpu_index_load(const char* path, int device, sbwt_gpu_index*
 extern "C" void sbwt_gpu_index_destroy(sbwt_gpu_index* ix) {
     if (!ix) return;
     DeviceGuard guard(ix->device);
-    cudaFree(ix->d_sectors); cudaFree(ix->d_sbbase); cudaFree(ix->d_precalc); cudaFree(ix->d_sgs);
+    cudaFree(ix->d_sectors); cudaFree(ix->d_sbbase); cudaFree(ix->d_precalc); cudaFree(ix->d_sgs); cudaFree(ix->d_table);
     delete ix;
 }
 
@@ -425,19 +492,36 @@ static int launch_pack(const char* d_ascii, int64_t n_bases, int case_mode, uint
     return 0;
 }
 
-template <int NW, bool STREAMING, bool WIDE>
-static void launch_walk_t(const WalkParams& P, bool count, unsigned grid, cudaStream_t st) {
-    if (count) walk_kernel<NW, STREAMING, WIDE, true><<<grid, 256, 0, st>>>(P);
-    else walk_kernel<NW, STREAMING, WIDE, false><<<grid, 256, 0, st>>>(P);
+template <int NW, bool STREAMING, bool WIDE, bool COUNT>
+static cudaError_t launch_walk_tt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
+    static int occ = 0; // resident 256-thread blocks per SM of this instantiation
+    if (occ == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<NW, STREAMING, WIDE, COUNT>, 256, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+    }
+    const unsigned grid = (unsigned)(sm_count * (blocks_per_sm > 0 ? blocks_per_sm : occ));
+    walk_kernel<NW, STREAMING, WIDE, COUNT><<<grid, 256, 0, st>>>(P);
+    return cudaGetLastError();
 }
 
-static int launch_walk(const sbwt_gpu_index* ix, const WalkParams& P, bool streaming, bool count, cudaStream_t st) {
-    int blocks_per_sm = 4;
-    if (const char* e = getenv("SBWT_B200_BLOCKS_PER_SM")) blocks_per_sm = std::max(1, atoi(e));
-    const unsigned grid = (unsigned)(ix->sm_count * blocks_per_sm);
+template <int NW, bool STREAMING, bool WIDE>
+static cudaError_t launch_walk_t(const WalkParams& P, bool count, int sm_count, int blocks_per_sm, cudaStream_t st) {
+    return count ? launch_walk_tt<NW, STREAMING, WIDE, true>(P, sm_count, blocks_per_sm, st)
+                 : launch_walk_tt<NW, STREAMING, WIDE, false>(P, sm_count, blocks_per_sm, st);
+}
+
+// One persistent wave: grid = SM count x resident blocks per SM (occupancy query), each warp owning a
+// contiguous range of work items.
+static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, bool count, cudaStream_t st) {
+    int blocks_per_sm = 0;
+    if (const char* e = getenv("SBWT_B200_BLOCKS_PER_SM")) blocks_per_sm = std::max(0, atoi(e));
+    const char* el = getenv("SBWT_B200_L2_EVICT_LAST");
+    P.index_evict_last = el ? atoi(el) : 1;
     const int nw = ix->k <= 32 ? 1 : 2;
     const bool wide = ix->view.wide;
-#define WALK(NW_, S_, W_) launch_walk_t<NW_, S_, W_>(P, count, grid, st)
+    cudaError_t e;
+#define WALK(NW_, S_, W_) e = launch_walk_t<NW_, S_, W_>(P, count, ix->sm_count, blocks_per_sm, st)
     if (nw == 1) {
         if (streaming) { if (wide) WALK(1, true, true); else WALK(1, true, false); }
         else { if (wide) WALK(1, false, true); else WALK(1, false, false); }
@@ -447,7 +531,7 @@ static int launch_walk(const sbwt_gpu_index* ix, const WalkParams& P, bool strea
     }
 #undef WALK
     LAUNCHED();
-    CU(cudaGetLastError());
+    CU(e);
     return 0;
 }
 

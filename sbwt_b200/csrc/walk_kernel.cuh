@@ -10,8 +10,6 @@
 // the SAME instructions (the first profile of this kernel was integer-ALU bound with 14 of 32
 // lanes active per instruction, profiles/r01_walk_v1_summary.txt):
 //
-//   PRE    first p characters -> row of the precalc table (kmer_prefix_precalc, SBWT.hh:404);
-//          the row is fetched with the same 256-bit load as a sector
 //   STEP   one interval step  [l,r] -> [C[c]+rank_c(l), C[c]+rank_c(r+1)-1]  (two sectors, one
 //          when l and r+1 fall into the same 224-column block). A streaming step (previous k-mer
 //          found at column col, SBWT.hh:561-575) is the same step on [col, col] with the new
@@ -21,8 +19,10 @@
 //          walk-back over suffix_group_starts on a slow path.
 //
 // Everything that happens once per k-mer rather than once per step -- storing the result,
-// sliding the read window, validity checks, choosing the next table row -- lives in one
-// divergent ADVANCE block, so lanes in long from-scratch walks, lanes streaming along a matching
+// sliding the read window, validity checks, and the lookup of the first p characters in the
+// search table (kmer_prefix_precalc, SBWT.hh:404; a second, dependent load in the same trip,
+// hidden by the other resident warps because the kernel is issue-bound, not latency-bound) --
+// lives in one divergent ADVANCE block, so lanes in long from-scratch walks, lanes streaming along a matching
 // read and lanes that just fetched a read share the step code at full width. The pointer chase
 // is hidden by the ~1000-2000 resident lanes per SM, each with one or two sector loads in
 // flight. Finished lanes refill from the warp's own contiguous item range (ballot/popc).
@@ -44,43 +44,46 @@ struct WalkParams {
     const int64_t* n_items;   // device scalar
     int64_t* out;
     unsigned long long* stats; // [lookups, hits, rank_ops, sectors] (COUNT only)
+    int index_evict_last;      // L2 policy of the index / table loads
 };
 
-enum : int { M_NEED = 0, M_PRE = 1, M_STEP = 2, M_DONE = 3 };
+enum : int { M_NEED = 0, M_STEP = 1, M_DONE = 2 };
 
 // Sliding window over the packed read: base t of the window (t = 0 is the first character of
 // the current k-mer) sits at bits [2(t%32), 2(t%32)+2) of b[t/32]; v holds the invalid flags.
+// nb / nv hold the not yet consumed bases of the packed word the window will slide into.
 template <int NW>
 struct Window {
     uint64_t b[NW];
     uint32_t v[NW];
-    uint64_t nb; // packed word holding the next base to shift in
-    uint32_t nv;
-    int64_t np;  // global index of that base
+    uint64_t nb; // next bases, already shifted so that the next base sits at bits [0,2)
+    uint32_t nv; // likewise for the invalid flags
+    uint32_t left; // bases left in nb / nv
+    uint32_t wi;   // index of the word nb came from
 
     __device__ __forceinline__ void init(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ invalid, int64_t g) {
-        const int64_t wi = g >> 5;
+        const uint32_t w0 = (uint32_t)(g >> 5);
         const int sh = (int)(g & 31);
-        uint64_t lo = codes[wi];
-        uint32_t vlo = invalid[wi];
+        uint64_t lo = codes[w0];
+        uint32_t vlo = invalid[w0];
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            const uint64_t hi = codes[wi + w + 1];
-            const uint32_t vhi = invalid[wi + w + 1];
+            const uint64_t hi = codes[w0 + w + 1];
+            const uint32_t vhi = invalid[w0 + w + 1];
             b[w] = sh ? ((lo >> (2 * sh)) | (hi << (64 - 2 * sh))) : lo;
             v[w] = __funnelshift_r(vlo, vhi, sh);
             lo = hi;
             vlo = vhi;
         }
-        nb = lo;
-        nv = vlo;
-        np = g + 32 * NW;
+        wi = w0 + NW;
+        nb = lo >> (2 * sh);
+        nv = vlo >> sh;
+        left = 32 - sh;
     }
 
     __device__ __forceinline__ void shift(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ invalid) {
-        const int s = (int)(np & 31);
-        const uint64_t code = (nb >> (2 * s)) & 3ull;
-        const uint32_t inv = (nv >> s) & 1u;
+        const uint64_t code = nb & 3ull;
+        const uint32_t inv = nv & 1u;
 #pragma unroll
         for (int w = 0; w < NW - 1; w++) {
             b[w] = (b[w] >> 2) | (b[w + 1] << 62);
@@ -88,10 +91,13 @@ struct Window {
         }
         b[NW - 1] = (b[NW - 1] >> 2) | (code << 62);
         v[NW - 1] = (v[NW - 1] >> 1) | (inv << 31);
-        np++;
-        if ((np & 31) == 0) {
-            nb = codes[np >> 5];
-            nv = invalid[np >> 5];
+        nb >>= 2;
+        nv >>= 1;
+        if (--left == 0) {
+            wi++;
+            nb = codes[wi];
+            nv = invalid[wi];
+            left = 32;
         }
     }
 
@@ -107,21 +113,17 @@ struct Window {
         for (int i = 1; i < NW; i++) w = ((j >> 5) == i) ? v[i] : w;
         return (w >> (j & 31)) & 1u;
     }
-    // any invalid base among the first k positions
-    __device__ __forceinline__ bool any_invalid(int k) const {
+    // any invalid base among the first k positions; kmask[i] = mask of the k-mer's bases in word i
+    __device__ __forceinline__ bool any_invalid(const uint32_t* kmask) const {
         uint32_t acc = 0;
 #pragma unroll
-        for (int i = 0; i < NW; i++) {
-            const int rem = k - 32 * i; // bases of the k-mer that live in word i
-            const uint32_t m = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-            acc |= v[i] & m;
-        }
+        for (int i = 0; i < NW; i++) acc |= v[i] & kmask[i];
         return acc != 0;
     }
 };
 
 template <int NW, bool STREAMING, bool WIDE, bool COUNT>
-__global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
+__global__ void __launch_bounds__(256, (NW == 1 && !WIDE) ? 5 : 4) walk_kernel(const WalkParams P) {
     typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t; // columns fit 32 bits in narrow mode
     const DeviceIndexView& ix = P.ix;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -134,47 +136,70 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
     int64_t next = (int64_t)(((__int128)n_items * gw) / nw);
     const int64_t end = (int64_t)(((__int128)n_items * (gw + 1)) / nw);
 
-    const int k = ix.k, p = ix.p;
+    const int k = ix.k, p = ix.tp; // p: characters answered by the search table
     const uint32_t pmask = p ? (uint32_t)((1ull << (2 * p)) - 1ull) : 0u;
-    const Sector* const pre_base = reinterpret_cast<const Sector*>(ix.precalc);
+    const Sector* const pre_base = reinterpret_cast<const Sector*>(ix.table);
     const Sector* const sec_base = ix.sectors;
+    const uint64_t pol = make_l2_policy(P.index_evict_last != 0);
+    const pos_t last_col = (pos_t)(ix.n_nodes - 1);
+    uint32_t kmask[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const int rem = k - 32 * i;
+        kmask[i] = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+    }
 
     Window<NW> win;
-    pos_t l = 0, r = 0;       // STEP: current interval.  PRE: l = table row pair index, r = parity
-    int64_t outp = 0;         // next result slot
+    pos_t l = 0, r = 0;       // current interval
+    int64_t* outq = P.out;    // next result slot
     int remaining = 0;        // k-mers left in the item, current one included
     int j = 0;                // characters of the current k-mer already consumed
     int mode = M_NEED;
     bool fs = false;          // this STEP is a streaming step (previous k-mer was found at column l)
     unsigned long long st_lookups = 0, st_hits = 0, st_ranks = 0, st_sectors = 0;
 
-    // Runs when a lane moves on to a new k-mer (window already positioned on it): answers k-mers
-    // that cover a non-ACGT byte on the spot (SBWT.hh:399,428,568) and leaves the lane in PRE or
-    // STEP mode for the first k-mer that needs memory, or in NEED mode when the item is exhausted.
+    // Runs when a lane moves on to a new k-mer (window already positioned on it). Answers on the
+    // spot the k-mers that need no walk -- those covering a non-ACGT byte (SBWT.hh:399,428,568),
+    // those whose first p characters are absent from the table (SBWT.hh:424) and, when p == k,
+    // those the table answers completely -- and leaves the lane in STEP mode for the first k-mer
+    // that needs the index, or in NEED mode when the item is exhausted.
     auto setup = [&](bool stream) {
         while (true) {
             if (remaining == 0) { mode = M_NEED; return; }
+            int64_t ans = -1;
             if (STREAMING && stream) {
                 if (!win.invalid_at(k - 1)) { r = l; j = k - 1; fs = true; mode = M_STEP; return; }
-            } else if (!win.any_invalid(k)) {
+            } else if (!win.any_invalid(kmask)) {
                 fs = false;
-                if (p > 0) {
-                    const uint32_t pidx = (uint32_t)win.b[0] & pmask; // first character = least significant digit (SBWT.hh:396-401)
-                    l = (pos_t)(pidx >> 1);
-                    r = (pos_t)(pidx & 1u);
-                    mode = M_PRE;
+                if (p == 0) { l = 0; r = last_col; j = 0; mode = M_STEP; return; }
+                const uint32_t pidx = (uint32_t)win.b[0] & pmask; // first character = least significant digit (SBWT.hh:396-401)
+                const Sector t = ld_sector(pre_base + (pidx >> (WIDE ? 1 : 2)), pol);
+                if (COUNT) st_sectors++;
+                bool absent;
+                if (WIDE) {
+                    const bool hi = pidx & 1u;
+                    const uint32_t e0 = hi ? t.w[4] : t.w[0], e1 = hi ? t.w[5] : t.w[1];
+                    const uint32_t e2 = hi ? t.w[6] : t.w[2], e3 = hi ? t.w[7] : t.w[3];
+                    l = (pos_t)(((uint64_t)e1 << 32) | e0);
+                    r = (pos_t)(((uint64_t)e3 << 32) | e2);
+                    absent = (int32_t)e1 < 0;
                 } else {
-                    l = 0;
-                    r = (pos_t)(ix.n_nodes - 1);
-                    j = 0;
-                    mode = M_STEP;
+                    const bool q1 = pidx & 1u, q2 = pidx & 2u;
+                    const uint32_t a_l = q1 ? t.w[2] : t.w[0], a_r = q1 ? t.w[3] : t.w[1];
+                    const uint32_t b_l = q1 ? t.w[6] : t.w[4], b_r = q1 ? t.w[7] : t.w[5];
+                    l = (pos_t)(q2 ? b_l : a_l);
+                    r = (pos_t)(q2 ? b_r : a_r);
+                    absent = l == (pos_t)0xFFFFFFFFu;
                 }
-                return;
+                if (!absent) {
+                    if (p < k) { j = p; mode = M_STEP; return; }
+                    ans = (int64_t)l; // p == k: the row is the answer (a singleton, SBWT.hh:410-413)
+                }
             }
-            __stcs(P.out + outp, (int64_t)-1);
-            outp++;
-            if (COUNT) st_lookups++;
-            stream = false;
+            __stcs(outq, ans);
+            outq++;
+            if (COUNT) { st_lookups++; st_hits += ans >= 0; }
+            stream = STREAMING && ans >= 0;
             if (--remaining) win.shift(P.codes, P.invalid);
         }
     };
@@ -188,7 +213,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
             if (mode == M_NEED) {
                 if (mine < end) {
                     const int64_t g = P.item_base[mine];
-                    outp = P.item_out[mine];
+                    outq = P.out + P.item_out[mine];
                     remaining = P.item_cnt[mine];
                     win.init(P.codes, P.invalid, g);
                     setup(false);
@@ -199,15 +224,14 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
             if (__all_sync(FULL, mode == M_DONE)) break;
         }
 
-        // ---- STEP / PRE: the same instructions for every live lane
-        const bool pre = mode == M_PRE, step = mode == M_STEP;
+        // ---- STEP: the same instructions for every live lane
+        const bool step = mode == M_STEP;
         const int c = win.code_at(j);
         const BlockPos b0 = split_pos<WIDE>((int64_t)l), b1 = split_pos<WIDE>((int64_t)r + 1);
-        const Sector* a0 = pre ? pre_base + l : sec_base + ((b0.blk << 2) + c);
         const bool two = step && (b1.blk != b0.blk);
         Sector s0, s1;
-        if (pre || step) s0 = ld_sector(a0);
-        if (two) s1 = ld_sector(sec_base + ((b1.blk << 2) + c));
+        if (step) s0 = ld_sector(sec_base + ((b0.blk << 2) + c), pol);
+        if (two) s1 = ld_sector(sec_base + ((b1.blk << 2) + c), pol);
         else s1 = s0;
 
         const SectorPrefix pf0 = sector_prefix(s0);
@@ -220,18 +244,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
         }
         nr -= 1;
         bool miss = nl > nr; // empty interval (SBWT.hh:433)
-        if (pre) {
-            const bool hi = r != 0;
-            const uint32_t e0 = hi ? s0.w[4] : s0.w[0], e1 = hi ? s0.w[5] : s0.w[1];
-            const uint32_t e2 = hi ? s0.w[6] : s0.w[2], e3 = hi ? s0.w[7] : s0.w[3];
-            nl = WIDE ? (pos_t)(((uint64_t)e1 << 32) | e0) : (pos_t)e0;
-            nr = WIDE ? (pos_t)(((uint64_t)e3 << 32) | e2) : (pos_t)e2;
-            miss = (int32_t)e1 < 0; // absent p-mer: {-1,-1} (SBWT.hh:424)
-        }
-        if (COUNT) {
-            if (step) { st_ranks += 2; st_sectors += two ? 2 : 1; }
-            if (pre) st_sectors++;
-        }
+        if (COUNT && step) { st_ranks += 2; st_sectors += two ? 2 : 1; }
         if (STREAMING && fs && step && (miss || !ix.edges_at_starts)) {
             // literal form (SBWT.hh:562-563): the step has to start from the suffix-group start of
             // column l. With edges only at group starts a set bit proves l is the start, so only a
@@ -245,29 +258,25 @@ __global__ void __launch_bounds__(256) walk_kernel(const WalkParams P) {
             if (COUNT) st_sectors++;
             if (s != (int64_t)l) {
                 const BlockPos bs = split_pos<WIDE>(s);
-                const Sector ss = ld_sector(sec_base + ((bs.blk << 2) + c));
+                const Sector ss = ld_sector(sec_base + ((bs.blk << 2) + c), pol);
                 if (COUNT) st_sectors += bs.blk != b0.blk;
                 miss = sector_bit(ss, bs.off) == 0;
                 nl = (pos_t)lf_value<WIDE>(ix, ss, bs.blk, bs.off, c);
                 nr = nl;
             }
         }
-        const int nj = pre ? p : j + 1;
-        const bool live = pre || step;
-        const bool done = live && !miss && nj == k; // a k-mer interval is a singleton (SBWT.hh:410-413)
-        if (live) {
+        const bool done = step && !miss && (j + 1 == k); // a k-mer interval is a singleton (SBWT.hh:410-413)
+        if (step) {
             l = nl;
             r = nr;
-            j = nj;
-            mode = M_STEP;
+            j++;
             fs = false;
         }
 
         // ---- ADVANCE: one result, slide to the next k-mer of the item
-        if (live && (miss || done)) {
-            const int64_t ans = done ? (int64_t)nl : (int64_t)-1;
-            __stcs(P.out + outp, ans);
-            outp++;
+        if (step && (miss || done)) {
+            __stcs(outq, done ? (int64_t)nl : (int64_t)-1);
+            outq++;
             if (COUNT) { st_lookups++; st_hits += done; }
             if (--remaining) win.shift(P.codes, P.invalid);
             setup(done);
