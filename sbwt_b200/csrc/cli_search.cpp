@@ -1,0 +1,250 @@
+// cli_search.cpp -- `sbwt search` on the GPU path.
+//
+// Mirrors search_main / run_queries / run_file / run_queries_streaming /
+// run_queries_not_streaming / print_vector of the reference (src/CLI/sbwt_search.cpp:21-260) and
+// the dispatcher's error handling (src/CLI/sbwt.cpp:42-57): same options, same list-file mode,
+// same text output (one "<value> " per k-mer, '\n' per read, -1 for a miss), same exit codes,
+// and the same two timing log lines. Only the plain-matrix variant is served; the others are
+// refused (they are out of scope).
+//
+// Differences: reads are answered in batches (sbwt_gpu_query_host through sbwt::SBWT<>), so
+// "us/query (excluding I/O etc)" is the time spent inside the batch calls; extra options
+// --device and --batch-bases.
+//
+//   sbwt_search [search] -o <out | list.txt> -i <index.sbwt> -q <reads.(fa|fq)[.gz] | list.txt> [-z]
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <zlib.h>
+
+#include "SBWT.hh"
+#include "fastx.hpp"
+
+using std::string;
+using std::vector;
+
+static const auto program_start = std::chrono::steady_clock::now();
+
+static long long cur_time_micros() {
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - program_start).count();
+}
+
+// write_log, src/globals.cpp:93-105 (timestamp in the reference's "milliseconds since start" quirk)
+static void write_log(const string& message) {
+    std::time_t t = std::time(nullptr);
+    string ts = std::asctime(std::localtime(&t));
+    ts.pop_back();
+    std::cerr << std::setprecision(4) << std::fixed << cur_time_micros() / 1000.0 << " " << ts << " " << message << std::endl;
+}
+
+static vector<string> readlines(const string& filename) { // src/globals.cpp:27-34
+    vector<string> lines;
+    std::ifstream in(filename);
+    if (!in.good()) throw std::runtime_error("Error opening file: " + filename);
+    string line;
+    while (std::getline(in, line)) lines.push_back(line);
+    return lines;
+}
+
+static void check_readable(const string& filename) { // src/globals.cpp:39-41
+    std::ifstream f(filename);
+    if (!f.good()) throw std::runtime_error("Error opening file: " + filename);
+}
+
+static void check_writable(const string& filename) { // src/globals.cpp:44-46 (opens with app: creates the file)
+    std::ofstream f(filename, std::ofstream::out | std::ofstream::app);
+    if (!f.good()) throw std::runtime_error("Error opening file: " + filename);
+}
+
+// print_vector (sbwt_search.cpp:21-43) for a slice of reads: values of read i are
+// vals[out_off[i] .. out_off[i+1]). A value of 0 prints as an empty field, as in the reference.
+static void format_reads(const int64_t* vals, const int64_t* out_off, int64_t r0, int64_t r1, string& text) {
+    text.clear();
+    text.reserve((size_t)((out_off[r1] - out_off[r0]) * 8 + (r1 - r0)));
+    char buffer[32];
+    for (int64_t i = r0; i < r1; i++) {
+        for (int64_t q = out_off[i]; q < out_off[i + 1]; q++) {
+            int64_t x = vals[q];
+            int n = 0;
+            if (x == -1) {
+                text += "-1 ";
+                continue;
+            }
+            while (x > 0) { buffer[n++] = (char)('0' + x % 10); x /= 10; }
+            while (n) text.push_back(buffer[--n]);
+            text.push_back(' ');
+        }
+        text.push_back('\n');
+    }
+}
+
+struct Writer {
+    FILE* fp = nullptr;
+    gzFile gz = nullptr;
+    Writer(const string& name, bool gzip) {
+        if (gzip) gz = gzopen(name.c_str(), "wb");
+        else fp = fopen(name.c_str(), "wb");
+        if (!gz && !fp) throw std::runtime_error("Error opening file: " + name);
+    }
+    ~Writer() {
+        if (fp) fclose(fp);
+        if (gz) gzclose(gz);
+    }
+    void write(const string& s) {
+        if (s.empty()) return;
+        if (fp) { if (fwrite(s.data(), 1, s.size(), fp) != s.size()) throw std::runtime_error("Error writing output"); }
+        else { if (gzwrite(gz, s.data(), (unsigned)s.size()) != (int)s.size()) throw std::runtime_error("Error writing gzip output"); }
+    }
+};
+
+struct Options {
+    int64_t batch_bases = (int64_t)64 << 20;
+    int64_t batch_reads = (int64_t)1 << 20;
+    int format_threads = 8;
+};
+
+// run_file (sbwt_search.cpp:93-105): streaming search when the index supports it, else search() per k-mer.
+static int64_t run_file(const string& infile, const string& outfile, const sbwt::plain_matrix_sbwt_t& index, bool gzip_output,
+                        const Options& opt, long long& query_micros) {
+    sbwt_b200::FastxReader reader(infile);
+    Writer writer(outfile, gzip_output);
+    const bool streaming = index.has_streaming_query_support();
+    write_log(string(streaming ? "Running streaming queries from input file " : "Running non-streaming queries from input file ") + infile +
+              " to output file " + outfile);
+    const int64_t k = index.get_k();
+    vector<char> ascii;
+    vector<int64_t> offsets, out_off, vals;
+    int64_t n_queries = 0;
+    while (true) {
+        const int64_t n = reader.next_batch(opt.batch_bases, opt.batch_reads, ascii, offsets);
+        if (n == 0) break;
+        out_off.assign((size_t)n + 1, 0);
+        for (int64_t i = 0; i < n; i++) {
+            const int64_t len = offsets[i + 1] - offsets[i];
+            out_off[i + 1] = out_off[i] + (len >= k ? len - k + 1 : 0);
+        }
+        vals.resize((size_t)out_off[n]);
+        const long long t0 = cur_time_micros();
+        index.query_batch_into(ascii.data(), offsets.data(), n, streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH,
+                               SBWT_GPU_CASE_UPPER, vals.data());
+        query_micros += cur_time_micros() - t0;
+        n_queries += out_off[n];
+        // format in parallel, write in order
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(opt.format_threads, n / 256 + 1));
+        vector<string> parts((size_t)T);
+        vector<std::thread> th;
+        for (int t = 0; t < T; t++)
+            th.emplace_back([&, t]() { format_reads(vals.data(), out_off.data(), n * t / T, n * (t + 1) / T, parts[t]); });
+        for (auto& x : th) x.join();
+        for (const string& s : parts) writer.write(s);
+    }
+    write_log("us/query: " + std::to_string((double)query_micros / std::max<int64_t>(n_queries, 1)) + " (excluding I/O etc)");
+    return n_queries;
+}
+
+static void print_help(const char* prog) {
+    std::cerr << "Query all k-mers of all input reads.\nUsage:\n  " << prog << " [OPTION...]\n\n"
+              << "  -o, --out-file arg     Output filename.\n"
+              << "  -i, --index-file arg   Index input file.\n"
+              << "  -q, --query-file arg   The query in FASTA or FASTQ format, possibly gzipped. Multi-line FASTQ is not\n"
+              << "                         supported. If the file extension is .txt, this is interpreted as a list of query\n"
+              << "                         files, one per line. In this case, --out-file is also interpreted as a list of\n"
+              << "                         output files in the same manner, one line for each input file.\n"
+              << "  -z, --gzip-output      Writes output in gzipped form. This can shrink the output files by an order of\n"
+              << "                         magnitude.\n"
+              << "      --device arg       CUDA device (default 0)\n"
+              << "      --batch-bases arg  Read bases per GPU batch (default 67108864)\n"
+              << "  -h, --help             Print usage\n" << std::endl;
+}
+
+static int search_main(int argc, char** argv) {
+    const long long micros_start = cur_time_micros();
+    string out_file, index_file, query_file;
+    bool gzip_output = false, have_o = false, have_i = false, have_q = false;
+    int device = 0;
+    Options opt;
+    if (argc == 1) { print_help(argv[0]); return 1; }
+    for (int i = 1; i < argc; i++) {
+        string a = argv[i];
+        auto value = [&](const char* name) -> string {
+            if (i + 1 >= argc) throw std::runtime_error(string("Option '") + name + "' is missing an argument");
+            return argv[++i];
+        };
+        if (a == "-h" || a == "--help") { print_help(argv[0]); return 1; }
+        else if (a == "-o" || a == "--out-file") { out_file = value("out-file"); have_o = true; }
+        else if (a == "-i" || a == "--index-file") { index_file = value("index-file"); have_i = true; }
+        else if (a == "-q" || a == "--query-file") { query_file = value("query-file"); have_q = true; }
+        else if (a == "-z" || a == "--gzip-output") gzip_output = true;
+        else if (a == "--device") device = std::stoi(value("device"));
+        else if (a == "--batch-bases") opt.batch_bases = std::stoll(value("batch-bases"));
+        else throw std::runtime_error("Option '" + a + "' does not exist");
+    }
+    if (!have_i) throw std::runtime_error("Option 'index-file' has no value");
+    check_readable(index_file);
+    if (!have_q) throw std::runtime_error("Option 'query-file' has no value");
+    vector<string> input_files, output_files;
+    const bool multi_file = query_file.size() >= 4 && query_file.substr(query_file.size() - 4) == ".txt";
+    if (multi_file) input_files = readlines(query_file);
+    else input_files = {query_file};
+    for (const string& f : input_files) check_readable(f);
+    if (!have_o) throw std::runtime_error("Option 'out-file' has no value");
+    if (multi_file) output_files = readlines(out_file);
+    else output_files = {out_file};
+    for (const string& f : output_files) check_writable(f);
+
+    std::ifstream in(index_file, std::ios::binary);
+    if (!in.good()) throw std::runtime_error("Error opening file: " + index_file);
+    const string variant = sbwt_b200::load_variant_string(in); // sbwt_search.cpp:194
+    static const char* known[] = {"plain-matrix", "rrr-matrix", "mef-matrix", "plain-split", "rrr-split", "mef-split",
+                                  "plain-concat", "mef-concat", "plain-subsetwt", "rrr-subsetwt"};
+    if (std::find(std::begin(known), std::end(known), variant) == std::end(known)) {
+        std::cerr << "Error loading index from file: unrecognized variant specified in the file" << std::endl;
+        return 1;
+    }
+    write_log("Loading the index variant " + variant);
+    if (variant != "plain-matrix") {
+        std::cerr << "Error: the GPU query path serves the plain-matrix variant only (index is " << variant << ")" << std::endl;
+        return 1;
+    }
+    sbwt::plain_matrix_sbwt_t index(device);
+    index.load(in);
+
+    if (input_files.size() != output_files.size())
+        throw std::runtime_error("Number of input and output files does not match (" + std::to_string(input_files.size()) + " vs " +
+                                 std::to_string(output_files.size()) + ")");
+    int64_t number_of_queries = 0;
+    for (size_t i = 0; i < input_files.size(); i++) {
+        long long micros = 0;
+        number_of_queries += run_file(input_files[i], output_files[i], index, gzip_output, opt, micros);
+    }
+    const long long total_micros = cur_time_micros() - micros_start;
+    write_log("us/query end-to-end: " + std::to_string((double)total_micros / std::max<int64_t>(number_of_queries, 1)));
+    return 0;
+}
+
+int main(int argc, char** argv) { // sbwt.cpp:19-59: strips the sub-command, reports exceptions, returns 1
+    try {
+        if (argc >= 2 && string(argv[1]) == "search") return search_main(argc - 1, argv + 1);
+        if (argc >= 2 && (string(argv[1]) == "build" || string(argv[1]) == "build-variant" || string(argv[1]) == "ascii-export")) {
+            std::cerr << "Error: only `search` is available in the GPU query build" << std::endl;
+            return 1;
+        }
+        return search_main(argc, argv);
+    } catch (const std::runtime_error& e) {
+        std::cerr << "Runtime error: " << e.what() << std::endl;
+        return 1;
+    } catch (const std::exception& e) {
+        std::cerr << "Error: " << e.what() << std::endl;
+        return 1;
+    }
+}

@@ -237,6 +237,45 @@ def test_random_differential_vs_oracle(tmp_path):
         np.testing.assert_array_equal(res[S.MODE_SEARCH], want, err_msg=f"k={k} p={p}")
 
 
+def test_search_table_lengths(tmp_path):
+    """The runtime search table (longer than the file's precalc table, built on the device) never
+    changes a result; a file whose own table does not follow from its bit vectors is used verbatim."""
+    for name in ("small_k31", "small_k8_p0", "small_k63_rc"):
+        vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+        reads = read_fasta_reads(golden(name, "reads.fna"))
+        a, off = synth.ragged_to_batch(reads)
+        idx = S.Index(golden(name, "index.sbwt"))
+        file_p = idx.precalc_k
+        assert idx.table_length >= file_p
+        np.testing.assert_array_equal(idx.precalc().reshape(-1), read_sbwt(golden(name, "index.sbwt"))["precalc"].reshape(-1))
+        ses = S.Session(idx, a.size, len(reads))
+        for tp in (0, 1, file_p, 5, 8, 9, 11, 12):
+            idx.set_table_length(tp)
+            assert idx.table_length == min(tp, idx.k)
+            for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+                np.testing.assert_array_equal(ses.query_host(a, off, mode), vals, err_msg=f"{name} tp={tp}")
+    # corrupt one row of the file's table: the reference would follow it, so must we (and no other length is allowed)
+    d = read_sbwt(golden("small_k31", "index.sbwt"))
+    raw = np.fromfile(golden("small_k31", "index.sbwt"), dtype=np.uint8)
+    pre = d["precalc"].copy()
+    row = int(np.flatnonzero(pre[:, 0] >= 0)[17])
+    pre[row] = (-1, -1)
+    start = raw.size - 32 - pre.size * 8
+    raw[start:start + pre.size * 8] = pre.reshape(-1).view(np.uint8)
+    p = str(tmp_path / "modtable.sbwt")
+    raw.tofile(p)
+    reads = read_fasta_reads(golden("small_k31", "reads.fna"))
+    a, off = synth.ragged_to_batch(reads)
+    want = oracle.OracleIndex(p).query_batch(a, off, streaming=True)
+    vals, _ = parse_expected(open(golden("small_k31", "expected.txt"), "rb").read())
+    assert (want != vals).any()
+    idx = S.Index(p)
+    assert idx.table_length == 8
+    np.testing.assert_array_equal(S.Session(idx, a.size, len(reads)).query_host(a, off, S.MODE_STREAMING), want)
+    with pytest.raises(S.SbwtGpuError, match="does not follow from its bit vectors"):
+        idx.set_table_length(10)
+
+
 def test_k_above_64_is_refused(tmp_path):
     d = read_sbwt(golden("small_k63_rc", "index.sbwt"))
     arrays = dict(bits=[w for _, w in d["bits"]], sgs=d["sgs"][1], C=d["C"], precalc=d["precalc"].reshape(-1), precalc_k=8,
