@@ -258,16 +258,20 @@ def test_search_table_lengths(tmp_path):
     d = read_sbwt(golden("small_k31", "index.sbwt"))
     raw = np.fromfile(golden("small_k31", "index.sbwt"), dtype=np.uint8)
     pre = d["precalc"].copy()
-    row = int(np.flatnonzero(pre[:, 0] >= 0)[17])
+    reads = read_fasta_reads(golden("small_k31", "reads.fna"))
+    vals, lens = parse_expected(open(golden("small_k31", "expected.txt"), "rb").read())
+    # a row some from-scratch search really uses: the first 8 characters of a read whose first k-mer is found
+    first = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    ri = next(i for i, r in enumerate(reads) if lens[i] > 0 and vals[first[i]] >= 0 and set(r[:8].upper()) <= set(b"ACGT"))
+    row = sum(b"ACGT".index(ch) << (2 * j) for j, ch in enumerate(reads[ri][:8].upper()))
+    assert pre[row, 0] >= 0
     pre[row] = (-1, -1)
     start = raw.size - 32 - pre.size * 8
     raw[start:start + pre.size * 8] = pre.reshape(-1).view(np.uint8)
     p = str(tmp_path / "modtable.sbwt")
     raw.tofile(p)
-    reads = read_fasta_reads(golden("small_k31", "reads.fna"))
     a, off = synth.ragged_to_batch(reads)
     want = oracle.OracleIndex(p).query_batch(a, off, streaming=True)
-    vals, _ = parse_expected(open(golden("small_k31", "expected.txt"), "rb").read())
     assert (want != vals).any()
     idx = S.Index(p)
     assert idx.table_length == 8
