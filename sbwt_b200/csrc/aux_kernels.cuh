@@ -167,9 +167,8 @@ __global__ void __launch_bounds__(256) plan_count_kernel(const int64_t* __restri
 // per read: emit its work items. out_off / win_off are the exclusive scans of the counts.
 __global__ void __launch_bounds__(256) plan_emit_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k,
                                                         int window, const int64_t* __restrict__ out_off,
-                                                        const int64_t* __restrict__ win_off, int64_t out_base,
-                                                        int64_t* __restrict__ item_base, int64_t* __restrict__ item_out,
-                                                        int32_t* __restrict__ item_cnt) {
+                                                        const int64_t* __restrict__ win_off,
+                                                        const uint32_t* __restrict__ invalid, WalkItem* __restrict__ items) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     const int64_t start = offsets[r] - offsets[0];
@@ -177,9 +176,19 @@ __global__ void __launch_bounds__(256) plan_emit_kernel(const int64_t* __restric
     const int64_t nk = len >= k ? len - k + 1 : 0;
     int64_t it = win_off[r];
     for (int64_t done = 0; done < nk; done += window, it++) {
-        item_base[it] = start + done;
-        item_out[it] = out_base + out_off[r] + done;
-        item_cnt[it] = (int32_t)(nk - done < window ? nk - done : window);
+        WalkItem w;
+        const int64_t lo = start + done, hi = lo + k - 1; // the first k-mer's bases but the last: [lo, hi)
+        w.base = (uint32_t)lo;
+        w.out = (uint32_t)(out_off[r] + done);
+        w.cnt = (uint32_t)(nk - done < window ? nk - done : window);
+        w.vfrom = (uint32_t)lo;
+        for (int64_t wi = (hi - 1) >> 5; hi > lo && wi >= (lo >> 5); wi--) {
+            uint32_t bits = invalid[wi];
+            if (wi == ((hi - 1) >> 5) && (hi & 31)) bits &= (1u << (hi & 31)) - 1u;
+            if (wi == (lo >> 5)) bits &= 0xFFFFFFFFu << (lo & 31);
+            if (bits) { w.vfrom = (uint32_t)(wi * 32 + 32 - __clz(bits)); break; }
+        }
+        items[it] = w;
     }
 }
 

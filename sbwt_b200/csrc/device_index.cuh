@@ -133,6 +133,14 @@ __device__ __forceinline__ uint32_t sector_bit(const Sector& s, uint32_t o) {
     return (w >> (o & 31u)) & 1u;
 }
 
+// One unit of work of the walk kernel: up to `window` consecutive k-mers of one read.
+struct __align__(16) WalkItem {
+    uint32_t base;  // index in the packed batch of the first base of the item's first k-mer
+    uint32_t out;   // index of its first result
+    uint32_t cnt;   // k-mers in the item
+    uint32_t vfrom; // one past the last invalid base among [base, base + k - 1), or `base` if there is none
+};
+
 struct BlockPos {
     int64_t blk;
     uint32_t off;
@@ -156,6 +164,12 @@ __device__ __forceinline__ BlockPos split_pos(int64_t pos) {
 template <bool WIDE>
 __device__ __forceinline__ const Sector* sector_addr(const DeviceIndexView& ix, int64_t blk, int c) {
     return ix.sectors + ((blk << 2) + c);
+}
+
+template <bool WIDE>
+__device__ __forceinline__ const Sector* sector_ptr(const Sector* base, int64_t blk, int c) {
+    if (WIDE) return base + ((blk << 2) + c);
+    return base + (uint32_t)(((uint32_t)blk << 2) + (uint32_t)c); // < 2^32 sectors' worth of bytes offset: one IMAD.WIDE.U32
 }
 
 // C[c] + rank_c(pos) given the already loaded sector of pos's block.

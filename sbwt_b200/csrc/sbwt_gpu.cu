@@ -42,6 +42,20 @@ static int set_error(const char* fmt, ...) {
 
 #define LAUNCHED() (g_launches++)
 
+// SBWT_B200_L2_FETCH=32|64|128: cudaLimitMaxL2FetchGranularity (how many bytes an L2 miss brings in from
+// HBM; a random 32-byte sector read costs 128 bytes of DRAM traffic at the default setting, ncu exp2)
+static void apply_l2_fetch_granularity() {
+    const char* e = getenv("SBWT_B200_L2_FETCH");
+    if (!e) return;
+    const int g = atoi(e);
+    if (g == 32 || g == 64 || g == 128) {
+        cudaError_t rc = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[sbwt_b200] cudaLimitMaxL2FetchGranularity <- %d: %s, now %zu\n", g, cudaGetErrorName(rc), got);
+    }
+}
+
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 struct DeviceGuard {
@@ -81,9 +95,8 @@ struct Scratch {
     int64_t* n_win = nullptr;   // per read; becomes the exclusive scan
     int64_t* partials = nullptr;
     int64_t* totals = nullptr;  // [0] = total results, [1] = total items
-    int64_t* item_base = nullptr;
-    int64_t* item_out = nullptr;
-    int32_t* item_cnt = nullptr;
+    WalkItem* items = nullptr;
+    int64_t n_words = 0;        // u64 words allocated for codes (u32 words for invalid)
     unsigned long long* stats = nullptr;
 };
 
@@ -177,6 +190,7 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     if (k > 64) return set_error("k = %lld is not supported by this build (k <= 64)", (long long)k);
     if (p < 0 || p > k || p > 14) return set_error("precalc length %lld is not supported (0 <= p <= min(k,14))", (long long)p);
     DeviceGuard guard(device);
+    apply_l2_fetch_granularity();
     sbwt_gpu_index* ix = new sbwt_gpu_index();
     auto fail = [&](int rc) { sbwt_gpu_index_destroy(ix); return rc; };
     ix->device = device;
@@ -408,23 +422,24 @@ extern "C" int sbwt_gpu_rank(sbwt_gpu_index* ix, const int64_t* pos, const char*
 
 static void scratch_free(Scratch& sc) {
     cudaFree(sc.codes); cudaFree(sc.invalid); cudaFree(sc.n_out); cudaFree(sc.n_win); cudaFree(sc.partials);
-    cudaFree(sc.totals); cudaFree(sc.item_base); cudaFree(sc.item_out); cudaFree(sc.item_cnt); cudaFree(sc.stats);
+    cudaFree(sc.totals); cudaFree(sc.items); cudaFree(sc.stats);
     sc = Scratch();
 }
 
 static int scratch_alloc(Scratch& sc, int64_t max_bases, int64_t max_reads, int window) {
     sc.max_bases = max_bases; sc.max_reads = max_reads;
     sc.max_items = max_reads + max_bases / window + 1;
-    const int64_t words = max_bases / 32 + 8;
+    const int64_t words = (max_bases / 32 + 8 + 1) & ~1ll; // even: the walk kernel reads whole 64-base chunks
+    sc.n_words = words;
     CU(cudaMalloc(&sc.codes, words * 8));
     CU(cudaMalloc(&sc.invalid, words * 4));
+    CU(cudaMemset(sc.codes, 0, words * 8));
+    CU(cudaMemset(sc.invalid, 0xFF, words * 4));
     CU(cudaMalloc(&sc.n_out, (max_reads + 1) * 8));
     CU(cudaMalloc(&sc.n_win, (max_reads + 1) * 8));
     CU(cudaMalloc(&sc.partials, scan_partials_needed(max_reads + 1) * 8));
     CU(cudaMalloc(&sc.totals, 4 * 8));
-    CU(cudaMalloc(&sc.item_base, sc.max_items * 8));
-    CU(cudaMalloc(&sc.item_out, sc.max_items * 8));
-    CU(cudaMalloc(&sc.item_cnt, sc.max_items * 4));
+    CU(cudaMalloc(&sc.items, sc.max_items * sizeof(WalkItem)));
     CU(cudaMalloc(&sc.stats, 8 * 8));
     return 0;
 }
@@ -433,6 +448,8 @@ extern "C" int sbwt_gpu_session_create(sbwt_gpu_index* ix, int64_t max_bases, in
     if (!ix || !out) return set_error("null argument");
     *out = nullptr;
     if (max_bases < 1 || max_reads < 1) return set_error("session capacity must be positive");
+    if (max_bases > (int64_t)0xFFFF0000ll || max_reads > (int64_t)0x7FFF0000ll)
+        return set_error("session capacity too large: at most 2^32 - 65536 bases and 2^31 - 65536 reads per device-side batch (host-side calls are chunked)");
     DeviceGuard guard(ix->device);
     sbwt_gpu_session* s = new sbwt_gpu_session();
     s->idx = ix; s->max_bases = max_bases; s->max_reads = max_reads;
@@ -492,23 +509,47 @@ static int launch_pack(const char* d_ascii, int64_t n_bases, int case_mode, uint
     return 0;
 }
 
-template <int NW, bool STREAMING, bool WIDE, bool COUNT>
+// L2 persistence (SBWT_B200_L2_PERSIST=1): bytes set aside for persisting lines and the largest window
+static size_t g_persist_bytes = 0, g_persist_window_max = 0;
+
+template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32>
 static cudaError_t launch_walk_tt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
     static int occ = 0; // resident 256-thread blocks per SM of this instantiation
     if (occ == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<NW, STREAMING, WIDE, COUNT>, 256, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<STREAMING, WIDE, COUNT, OUT32>, 256, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
     }
     const unsigned grid = (unsigned)(sm_count * (blocks_per_sm > 0 ? blocks_per_sm : occ));
-    walk_kernel<NW, STREAMING, WIDE, COUNT><<<grid, 256, 0, st>>>(P);
+    if (g_persist_bytes > 0) {
+        // L2 persistence window over the sector array (per launch): lines of the index are kept
+        // as "persisting", everything else streams through the rest of L2.
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeAccessPolicyWindow;
+        const size_t bytes = (size_t)P.ix.n_blocks * 4 * sizeof(Sector);
+        const size_t win = std::min(bytes, g_persist_window_max);
+        attr.val.accessPolicyWindow.base_ptr = const_cast<Sector*>(P.ix.sectors);
+        attr.val.accessPolicyWindow.num_bytes = win;
+        attr.val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)g_persist_bytes / (double)std::max<size_t>(win, 1));
+        attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, walk_kernel<STREAMING, WIDE, COUNT, OUT32>, P);
+    }
+    walk_kernel<STREAMING, WIDE, COUNT, OUT32><<<grid, 256, 0, st>>>(P);
     return cudaGetLastError();
 }
 
-template <int NW, bool STREAMING, bool WIDE>
+template <bool STREAMING, bool WIDE>
 static cudaError_t launch_walk_t(const WalkParams& P, bool count, int sm_count, int blocks_per_sm, cudaStream_t st) {
-    return count ? launch_walk_tt<NW, STREAMING, WIDE, true>(P, sm_count, blocks_per_sm, st)
-                 : launch_walk_tt<NW, STREAMING, WIDE, false>(P, sm_count, blocks_per_sm, st);
+    if (P.out32) {
+        if (WIDE || count) return cudaErrorInvalidValue; // int32 results exist only for narrow, uncounted batches
+        return launch_walk_tt<STREAMING, false, false, true>(P, sm_count, blocks_per_sm, st);
+    }
+    return count ? launch_walk_tt<STREAMING, WIDE, true, false>(P, sm_count, blocks_per_sm, st)
+                 : launch_walk_tt<STREAMING, WIDE, false, false>(P, sm_count, blocks_per_sm, st);
 }
 
 // One persistent wave: grid = SM count x resident blocks per SM (occupancy query), each warp owning a
@@ -518,17 +559,30 @@ static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, 
     if (const char* e = getenv("SBWT_B200_BLOCKS_PER_SM")) blocks_per_sm = std::max(0, atoi(e));
     const char* el = getenv("SBWT_B200_L2_EVICT_LAST");
     P.index_evict_last = el ? atoi(el) : 1;
-    const int nw = ix->k <= 32 ? 1 : 2;
+    const char* ns = getenv("SBWT_B200_DEBUG_NOSTORE");
+    P.debug_no_store = ns ? atoi(ns) : 0;
+    {
+        const char* pe = getenv("SBWT_B200_L2_PERSIST");
+        const bool want = pe && atoi(pe) > 0;
+        if (want && g_persist_bytes == 0) {
+            int max_persist = 0, max_win = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device);
+            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ix->device);
+            if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+                g_persist_bytes = (size_t)max_persist;
+                g_persist_window_max = (size_t)max_win;
+                fprintf(stderr, "[sbwt_b200] L2 persistence: set-aside %d MB, max window %d MB\n", max_persist >> 20, max_win >> 20);
+            }
+        } else if (!want && g_persist_bytes) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+            g_persist_bytes = 0;
+        }
+    }
     const bool wide = ix->view.wide;
     cudaError_t e;
-#define WALK(NW_, S_, W_) e = launch_walk_t<NW_, S_, W_>(P, count, ix->sm_count, blocks_per_sm, st)
-    if (nw == 1) {
-        if (streaming) { if (wide) WALK(1, true, true); else WALK(1, true, false); }
-        else { if (wide) WALK(1, false, true); else WALK(1, false, false); }
-    } else {
-        if (streaming) { if (wide) WALK(2, true, true); else WALK(2, true, false); }
-        else { if (wide) WALK(2, false, true); else WALK(2, false, false); }
-    }
+#define WALK(S_, W_) e = launch_walk_t<S_, W_>(P, count, ix->sm_count, blocks_per_sm, st)
+    if (streaming) { if (wide) WALK(true, true); else WALK(true, false); }
+    else { if (wide) WALK(false, true); else WALK(false, false); }
 #undef WALK
     LAUNCHED();
     CU(e);
@@ -552,13 +606,15 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
     plan_count_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, s->window, sc.n_out, sc.n_win); LAUNCHED();
     if (exclusive_scan_inplace(sc.n_out, n_reads, sc.partials, sc.totals + 0, st)) return 1;
     if (exclusive_scan_inplace(sc.n_win, n_reads, sc.partials, sc.totals + 1, st)) return 1;
-    plan_emit_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, s->window, sc.n_out, sc.n_win, 0,
-                                                            sc.item_base, sc.item_out, sc.item_cnt); LAUNCHED();
+    plan_emit_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, s->window, sc.n_out, sc.n_win,
+                                                            sc.invalid, sc.items); LAUNCHED();
     CU(cudaGetLastError());
     WalkParams P;
     P.ix = ix->view;
-    P.codes = sc.codes; P.invalid = sc.invalid;
-    P.item_base = sc.item_base; P.item_out = sc.item_out; P.item_cnt = sc.item_cnt;
+    P.codes = reinterpret_cast<const uint32_t*>(sc.codes); P.invalid = sc.invalid;
+    P.n_chunks = (uint32_t)(sc.n_words / 2);
+    P.items = sc.items;
+    P.out32 = nullptr;
     P.n_items = sc.totals + 1;
     P.out = d_out;
     P.stats = sc.stats;
@@ -712,6 +768,7 @@ extern "C" int sbwt_gpu_sector_probe(int device, int64_t buffer_bytes, int64_t n
     if (bytes_per_load != 32 && bytes_per_load != 64) return set_error("bytes_per_load must be 32 or 64");
     if (sbwt_gpu_device_count() <= 0) return set_error("no CUDA device available");
     DeviceGuard guard(device);
+    apply_l2_fetch_granularity();
     void* buf = nullptr;
     uint32_t* sink = nullptr;
     CU(cudaMalloc(&buf, (size_t)buffer_bytes));
