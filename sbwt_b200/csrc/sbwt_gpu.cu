@@ -113,8 +113,8 @@ struct HostSlot {
     cudaEvent_t done = nullptr;
     bool busy = false;
     // what to do when the slot's work has finished
-    int64_t out_count = 0;
-    int64_t* out_dst = nullptr;
+    int64_t out_bytes = 0;
+    void* out_dst = nullptr;
     bool out_staged = false;
 };
 
@@ -591,12 +591,14 @@ static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, 
 
 // pack -> plan -> walk for one device-resident batch, all on `st`
 static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_ascii, const int64_t* d_offsets, int64_t n_reads,
-                            int64_t n_bases, int mode, int case_mode, int64_t* d_out, bool count, cudaStream_t st) {
+                            int64_t n_bases, int mode, int case_mode, void* d_out, bool out32, bool count, cudaStream_t st) {
     sbwt_gpu_index* ix = s->idx;
     if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
     if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
     if (mode == SBWT_GPU_MODE_STREAMING && !ix->has_sgs) return set_error("Error: streaming search support not built"); // SBWT.hh:546-547
     if (n_reads < 0 || n_bases < 0) return set_error("negative batch size");
+    if (out32 && (ix->n_nodes >= (1ll << 31) || ix->view.wide))
+        return set_error("int32 results need an index with fewer than 2^31 columns (this one has %lld)", (long long)ix->n_nodes);
     if (n_bases > sc.max_bases || n_reads > sc.max_reads)
         return set_error("batch of %lld reads / %lld bases exceeds the session capacity (%lld / %lld)", (long long)n_reads,
                          (long long)n_bases, (long long)sc.max_reads, (long long)sc.max_bases);
@@ -614,9 +616,9 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
     P.codes = reinterpret_cast<const uint32_t*>(sc.codes); P.invalid = sc.invalid;
     P.n_chunks = (uint32_t)(sc.n_words / 2);
     P.items = sc.items;
-    P.out32 = nullptr;
+    P.out32 = out32 ? (int32_t*)d_out : nullptr;
     P.n_items = sc.totals + 1;
-    P.out = d_out;
+    P.out = out32 ? nullptr : (int64_t*)d_out;
     P.stats = sc.stats;
     if (count) CU(cudaMemsetAsync(sc.stats, 0, 64, st));
     const bool timed = s->timing && &sc == &s->sc;
@@ -636,7 +638,15 @@ extern "C" int sbwt_gpu_query_device(sbwt_gpu_session* s, const char* d_ascii, c
     if (!s) return set_error("null session");
     (void)n_out;
     DeviceGuard guard(s->idx->device);
-    return run_device_batch(s, s->sc, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, false, (cudaStream_t)stream);
+    return run_device_batch(s, s->sc, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, false, false, (cudaStream_t)stream);
+}
+
+extern "C" int sbwt_gpu_query_device_i32(sbwt_gpu_session* s, const char* d_ascii, const int64_t* d_offsets, int64_t n_reads,
+                                         int64_t n_bases, int mode, int case_mode, int32_t* d_out, int64_t n_out, void* stream) {
+    if (!s) return set_error("null session");
+    (void)n_out;
+    DeviceGuard guard(s->idx->device);
+    return run_device_batch(s, s->sc, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, true, false, (cudaStream_t)stream);
 }
 
 extern "C" int sbwt_gpu_query_device_counted(sbwt_gpu_session* s, const char* d_ascii, const int64_t* d_offsets, int64_t n_reads,
@@ -646,7 +656,7 @@ extern "C" int sbwt_gpu_query_device_counted(sbwt_gpu_session* s, const char* d_
     (void)n_out;
     DeviceGuard guard(s->idx->device);
     const int64_t before = g_launches;
-    if (run_device_batch(s, s->sc, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, true, (cudaStream_t)stream)) return 1;
+    if (run_device_batch(s, s->sc, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, false, true, (cudaStream_t)stream)) return 1;
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     unsigned long long h[4] = {0, 0, 0, 0};
     if (n_reads > 0) CU(cudaMemcpy(h, s->sc.stats, 32, cudaMemcpyDeviceToHost));
@@ -681,13 +691,13 @@ static int host_slots_init(sbwt_gpu_session* s) {
 static int slot_finish(HostSlot& h) {
     if (!h.busy) return 0;
     CU(cudaEventSynchronize(h.done));
-    if (h.out_staged && h.out_count) memcpy(h.out_dst, h.h_out, (size_t)h.out_count * 8);
+    if (h.out_staged && h.out_bytes) memcpy(h.out_dst, h.h_out, (size_t)h.out_bytes);
     h.busy = false;
     return 0;
 }
 
-extern "C" int sbwt_gpu_query_host(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
-                                   int case_mode, int64_t* out) {
+static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                           int case_mode, void* out, bool out32) {
     if (!s) return set_error("null session");
     if (n_reads < 0) return set_error("negative batch size");
     if (n_reads == 0) return 0;
@@ -730,14 +740,15 @@ extern "C" int sbwt_gpu_query_host(sbwt_gpu_session* s, const char* ascii, const
         }
         CU(cudaMemcpyAsync(h.d_ascii, src, (size_t)bases, cudaMemcpyHostToDevice, h.stream));
         CU(cudaMemcpyAsync(h.d_offsets, osrc, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, h.stream));
-        if (run_device_batch(s, h.sc, h.d_ascii, h.d_offsets, nr, bases, mode, case_mode, h.d_out, false, h.stream)) return 1;
-        int64_t* dst = out + out_pos;
-        h.out_dst = dst; h.out_count = n_out; h.out_staged = !pin_out;
+        if (run_device_batch(s, h.sc, h.d_ascii, h.d_offsets, nr, bases, mode, case_mode, h.d_out, out32, false, h.stream)) return 1;
+        const size_t esz = out32 ? 4 : 8;
+        void* dst = (char*)out + (size_t)out_pos * esz;
+        h.out_dst = dst; h.out_bytes = n_out * (int64_t)esz; h.out_staged = !pin_out;
         if (!pin_out) {
             if (!h.h_out) CU(cudaMallocHost(&h.h_out, std::max<int64_t>(s->max_bases, 1) * 8));
             dst = h.h_out;
         }
-        if (n_out) CU(cudaMemcpyAsync(dst, h.d_out, (size_t)n_out * 8, cudaMemcpyDeviceToHost, h.stream));
+        if (n_out) CU(cudaMemcpyAsync(dst, h.d_out, (size_t)n_out * esz, cudaMemcpyDeviceToHost, h.stream));
         CU(cudaEventRecord(h.done, h.stream));
         h.busy = true;
         out_pos += n_out;
@@ -746,6 +757,17 @@ extern "C" int sbwt_gpu_query_host(sbwt_gpu_session* s, const char* ascii, const
     for (HostSlot& h : s->slots)
         if (slot_finish(h)) return 1;
     return 0;
+}
+
+extern "C" int sbwt_gpu_query_host(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                                   int case_mode, int64_t* out) {
+    return query_host_impl(s, ascii, off, n_reads, mode, case_mode, out, false);
+}
+extern "C" int sbwt_gpu_query_host_i32(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                                       int case_mode, int32_t* out) {
+    if (s && (s->idx->n_nodes >= (1ll << 31) || s->idx->view.wide))
+        return set_error("int32 results need an index with fewer than 2^31 columns (this one has %lld)", (long long)s->idx->n_nodes);
+    return query_host_impl(s, ascii, off, n_reads, mode, case_mode, out, true);
 }
 
 extern "C" int sbwt_gpu_search_batch(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int64_t* out) {
