@@ -121,6 +121,12 @@ int64_t sbwt_gpu_count_outputs(const int64_t *read_offsets, int64_t n_reads, int
 int sbwt_gpu_query_host(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,
                         int64_t n_reads, int mode, int case_mode, int64_t *out);
 
+/* Same, with int32 results: half the device-to-host bytes (the PCIe copy of the results is what bounds
+ * an end-to-end batch). Only for an index with fewer than 2^31 columns (every value, and -1, fits);
+ * fails otherwise. Values are the same numbers sbwt_gpu_query_host returns. */
+int sbwt_gpu_query_host_i32(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,
+                            int64_t n_reads, int mode, int case_mode, int32_t *out);
+
 /* Device-buffer batch: d_ascii / d_read_offsets / d_out are device pointers on the index's
  * device, read_offsets[0] == 0, n_bases == read_offsets[n_reads] <= max_bases, n_reads <=
  * max_reads; d_out holds n_out == count_outputs values. Enqueues pack -> plan -> walk on
@@ -128,6 +134,10 @@ int sbwt_gpu_query_host(sbwt_gpu_session *s, const char *ascii, const int64_t *r
 int sbwt_gpu_query_device(sbwt_gpu_session *s, const char *d_ascii, const int64_t *d_read_offsets,
                           int64_t n_reads, int64_t n_bases, int mode, int case_mode,
                           int64_t *d_out, int64_t n_out, void *cuda_stream);
+
+int sbwt_gpu_query_device_i32(sbwt_gpu_session *s, const char *d_ascii, const int64_t *d_read_offsets,
+                              int64_t n_reads, int64_t n_bases, int mode, int case_mode,
+                              int32_t *d_out, int64_t n_out, void *cuda_stream);
 
 /* The two names of the reference API, as thin wrappers of sbwt_gpu_query_host with CASE_UPPER. */
 int sbwt_gpu_search_batch(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,

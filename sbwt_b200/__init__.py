@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsbwt_b200.so")
+# SBWT_B200_LIB: a differently-compiled build of the same library (kernel A/B measurements only)
+LIB_PATH = os.environ.get("SBWT_B200_LIB") or os.path.join(HERE, "libsbwt_b200.so")
 
 MODE_SEARCH = 0
 MODE_STREAMING = 1
@@ -27,7 +28,7 @@ EXPORTS = [
     "sbwt_gpu_index_has_streaming_support", "sbwt_gpu_index_device", "sbwt_gpu_index_C",
     "sbwt_gpu_index_device_bytes", "sbwt_gpu_index_edges_only_at_group_starts", "sbwt_gpu_rank",
     "sbwt_gpu_session_create", "sbwt_gpu_session_destroy", "sbwt_gpu_count_outputs",
-    "sbwt_gpu_query_host", "sbwt_gpu_query_device", "sbwt_gpu_search_batch", "sbwt_gpu_streaming_batch",
+    "sbwt_gpu_query_host", "sbwt_gpu_query_host_i32", "sbwt_gpu_query_device", "sbwt_gpu_query_device_i32", "sbwt_gpu_search_batch", "sbwt_gpu_streaming_batch",
     "sbwt_gpu_host_alloc", "sbwt_gpu_host_free", "sbwt_gpu_pack_device",
     "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
     "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
@@ -76,6 +77,8 @@ def lib():
         L.sbwt_gpu_count_outputs.restype = i64
         L.sbwt_gpu_query_host.argtypes = [vp, vp, vp, i64, i32, i32, vp]
         L.sbwt_gpu_query_device.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp, i64, vp]
+        L.sbwt_gpu_query_host_i32.argtypes = [vp, vp, vp, i64, i32, i32, vp]
+        L.sbwt_gpu_query_device_i32.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp, i64, vp]
         L.sbwt_gpu_query_device_counted.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp, i64, vp, C.POINTER(Stats)]
         L.sbwt_gpu_search_batch.argtypes = [vp, vp, vp, i64, vp]
         L.sbwt_gpu_streaming_batch.argtypes = [vp, vp, vp, i64, vp]
@@ -239,6 +242,23 @@ class Session:
         _check(lib().sbwt_gpu_query_host(self._h, ascii_.ctypes.data, offsets.ctypes.data, offsets.size - 1, mode, case_mode,
                                          out.ctypes.data))
         return out[:n_out]
+
+    def query_host_i32(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER,
+                       out: np.ndarray | None = None) -> np.ndarray:
+        """sbwt_gpu_query_host_i32: the same values as int32 (indexes with fewer than 2^31 columns)."""
+        assert ascii_.dtype == np.uint8 and ascii_.flags.c_contiguous
+        assert offsets.dtype == np.int64 and offsets.flags.c_contiguous
+        n_out = self.count_outputs(offsets)
+        if out is None:
+            out = np.empty(n_out, dtype=np.int32)
+        assert out.dtype == np.int32 and out.size >= n_out
+        _check(lib().sbwt_gpu_query_host_i32(self._h, ascii_.ctypes.data, offsets.ctypes.data, offsets.size - 1, mode, case_mode,
+                                             out.ctypes.data))
+        return out[:n_out]
+
+    def query_device_i32(self, d_ascii: int, d_offsets: int, n_reads: int, n_bases: int, mode: int, d_out: int, n_out: int,
+                         stream: int = 0, case_mode: int = CASE_UPPER) -> None:
+        _check(lib().sbwt_gpu_query_device_i32(self._h, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, n_out, stream))
 
     def query_device(self, d_ascii: int, d_offsets: int, n_reads: int, n_bases: int, mode: int, d_out: int, n_out: int,
                      stream: int = 0, case_mode: int = CASE_UPPER) -> None:

@@ -192,6 +192,38 @@ __global__ void __launch_bounds__(256) plan_emit_kernel(const int64_t* __restric
     }
 }
 
+// The same, for walk2_kernel: item.vfrom holds `nvalid`, the number of leading k-mers of the item that
+// cover no invalid base (0 = already the first k-mer does).
+__global__ void __launch_bounds__(256) plan_emit2_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k,
+                                                         int window, const int64_t* __restrict__ out_off,
+                                                         const int64_t* __restrict__ win_off,
+                                                         const uint32_t* __restrict__ invalid, WalkItem* __restrict__ items) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int64_t start = offsets[r] - offsets[0];
+    const int64_t len = offsets[r + 1] - offsets[r];
+    const int64_t nk = len >= k ? len - k + 1 : 0;
+    int64_t it = win_off[r];
+    for (int64_t done = 0; done < nk; done += window, it++) {
+        WalkItem w;
+        const int64_t cnt = nk - done < window ? nk - done : window;
+        const int64_t lo = start + done, hi = lo + cnt + k - 1; // bases covered by the item's k-mers: [lo, hi)
+        w.base = (uint32_t)lo;
+        w.out = (uint32_t)(out_off[r] + done);
+        w.cnt = (uint32_t)cnt;
+        int64_t first_bad = hi; // first invalid base in [lo, hi)
+        for (int64_t wi = lo >> 5; wi <= (hi - 1) >> 5; wi++) {
+            uint32_t bits = invalid[wi];
+            if (wi == (lo >> 5)) bits &= 0xFFFFFFFFu << (lo & 31);
+            if (wi == ((hi - 1) >> 5) && (hi & 31)) bits &= (1u << (hi & 31)) - 1u;
+            if (bits) { first_bad = wi * 32 + (__ffs(bits) - 1); break; }
+        }
+        const int64_t nv = first_bad - lo - k + 1; // k-mer t covers [lo + t, lo + t + k)
+        w.vfrom = (uint32_t)(nv < 0 ? 0 : (nv > cnt ? cnt : nv));
+        items[it] = w;
+    }
+}
+
 // ------------------------------------------------------------------ K0: index build
 
 // raw[c] = bit vector c as u32 words, zero padded to n_blocks * 7 words

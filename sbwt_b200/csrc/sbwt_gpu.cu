@@ -16,6 +16,7 @@
 #include "device_index.cuh"
 #include "sbwt_file.hpp"
 #include "walk_kernel.cuh"
+#include "walk2_kernel.cuh"
 
 using namespace sbwt_b200;
 
@@ -428,7 +429,7 @@ static void scratch_free(Scratch& sc) {
 
 static int scratch_alloc(Scratch& sc, int64_t max_bases, int64_t max_reads, int window) {
     sc.max_bases = max_bases; sc.max_reads = max_reads;
-    sc.max_items = max_reads + max_bases / window + 1;
+    sc.max_items = max_reads + max_bases / std::min(window, 32) + 1; // search mode plans 32-k-mer chunks
     const int64_t words = (max_bases / 32 + 8 + 1) & ~1ll; // even: the walk kernel reads whole 64-base chunks
     sc.n_words = words;
     CU(cudaMalloc(&sc.codes, words * 8));
@@ -552,6 +553,41 @@ static cudaError_t launch_walk_t(const WalkParams& P, bool count, int sm_count, 
                  : launch_walk_tt<STREAMING, WIDE, false, false>(P, sm_count, blocks_per_sm, st);
 }
 
+template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL>
+static cudaError_t launch_walk2_ttt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
+    static int occ = 0;
+    if (occ == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk2_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL>, kW2Threads, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+    }
+    const unsigned grid = (unsigned)(sm_count * (blocks_per_sm > 0 ? blocks_per_sm : occ));
+    walk2_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL><<<grid, kW2Threads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW>
+static cudaError_t launch_walk2_tt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
+    if (STREAMING && !P.ix.edges_at_starts) // the reference's control flow to the letter (hand-made index files)
+        return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, STREAMING>(P, sm_count, blocks_per_sm, st);
+    return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false>(P, sm_count, blocks_per_sm, st);
+}
+
+template <bool STREAMING, bool WIDE, int KW>
+static cudaError_t launch_walk2_t(const WalkParams& P, bool count, int sm_count, int blocks_per_sm, cudaStream_t st) {
+    if (P.out32) {
+        if (WIDE || count) return cudaErrorInvalidValue;
+        return launch_walk2_tt<STREAMING, false, false, true, KW>(P, sm_count, blocks_per_sm, st);
+    }
+    return count ? launch_walk2_tt<STREAMING, WIDE, true, false, KW>(P, sm_count, blocks_per_sm, st)
+                 : launch_walk2_tt<STREAMING, WIDE, false, false, KW>(P, sm_count, blocks_per_sm, st);
+}
+
+static int walk_generation() { // SBWT_B200_WALK=1 selects the lane-state-machine kernel of walk_kernel.cuh (A/B measurements)
+    const char* e = getenv("SBWT_B200_WALK");
+    return e ? atoi(e) : 2;
+}
+
 // One persistent wave: grid = SM count x resident blocks per SM (occupancy query), each warp owning a
 // contiguous range of work items.
 static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, bool count, cudaStream_t st) {
@@ -580,6 +616,18 @@ static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, 
     }
     const bool wide = ix->view.wide;
     cudaError_t e;
+    if (walk_generation() >= 2) {
+        CU(cudaMemsetAsync(P.cursor, 0, 8, st));
+        const bool k64 = ix->k > 32;
+#define WALK2(S_, W_) e = k64 ? launch_walk2_t<S_, W_, 2>(P, count, ix->sm_count, blocks_per_sm, st) \
+                              : launch_walk2_t<S_, W_, 1>(P, count, ix->sm_count, blocks_per_sm, st)
+        if (streaming) { if (wide) WALK2(true, true); else WALK2(true, false); }
+        else { if (wide) WALK2(false, true); else WALK2(false, false); }
+#undef WALK2
+        LAUNCHED();
+        CU(e);
+        return 0;
+    }
 #define WALK(S_, W_) e = launch_walk_t<S_, W_>(P, count, ix->sm_count, blocks_per_sm, st)
     if (streaming) { if (wide) WALK(true, true); else WALK(true, false); }
     else { if (wide) WALK(false, true); else WALK(false, false); }
@@ -605,11 +653,17 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
     if (n_reads == 0) return 0;
     if (s->timing && &sc == &s->sc) CU(cudaEventRecord(s->ev_start, st));
     if (launch_pack(d_ascii, n_bases, case_mode, sc.codes, sc.invalid, st)) return 1;
-    plan_count_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, s->window, sc.n_out, sc.n_win); LAUNCHED();
+    const bool gen2 = walk_generation() >= 2;
+    // walk2: search mode is planned as chunks of 32 k-mers (one lane per k-mer), streaming mode as windows of a read
+    const int window = gen2 && mode == SBWT_GPU_MODE_SEARCH ? 32 : (gen2 ? std::min(s->window, (1 << 23)) : s->window);
+    plan_count_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win); LAUNCHED();
     if (exclusive_scan_inplace(sc.n_out, n_reads, sc.partials, sc.totals + 0, st)) return 1;
     if (exclusive_scan_inplace(sc.n_win, n_reads, sc.partials, sc.totals + 1, st)) return 1;
-    plan_emit_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, s->window, sc.n_out, sc.n_win,
-                                                            sc.invalid, sc.items); LAUNCHED();
+    if (gen2) plan_emit2_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win,
+                                                                        sc.invalid, sc.items);
+    else plan_emit_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win,
+                                                                  sc.invalid, sc.items);
+    LAUNCHED();
     CU(cudaGetLastError());
     WalkParams P;
     P.ix = ix->view;
@@ -620,6 +674,7 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
     P.n_items = sc.totals + 1;
     P.out = out32 ? nullptr : (int64_t*)d_out;
     P.stats = sc.stats;
+    P.cursor = sc.stats + 4;
     if (count) CU(cudaMemsetAsync(sc.stats, 0, 64, st));
     const bool timed = s->timing && &sc == &s->sc;
     if (timed) CU(cudaEventRecord(s->ev_walk0, st));

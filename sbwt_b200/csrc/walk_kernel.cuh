@@ -46,6 +46,7 @@ struct WalkParams {
     int64_t* out;             // results as int64 ...
     int32_t* out32;           // ... or as int32 (OUT32 kernels; callers use them only when n_nodes < 2^31)
     unsigned long long* stats; // [lookups, hits, rank_ops, sectors] (COUNT only)
+    unsigned long long* cursor; // next unclaimed work item (walk2_kernel; zeroed before every launch)
     int index_evict_last;      // L2 policy of the index / table loads
     int debug_no_store;        // measurement only (SBWT_B200_DEBUG_NOSTORE): results are not written
 };

@@ -313,3 +313,68 @@ def test_scale_properties_config2_like(tmp_path):
     orc = oracle.OracleIndex(ix)
     m = 3000
     np.testing.assert_array_equal(orc.query_batch(a[:m * 150], off[:m + 1], streaming=True), s[:m * 120])
+
+
+def test_int32_results_match_int64():
+    """sbwt_gpu_query_host_i32 / query_device_i32: the same values in half the bytes (n_nodes < 2^31)."""
+    import torch
+    for name in ("small_k31", "small_k63_rc"):
+        vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+        reads = read_fasta_reads(golden(name, "reads.fna"))
+        a, off = synth.ragged_to_batch(reads)
+        idx = S.Index(golden(name, "index.sbwt"))
+        ses = S.Session(idx, max_bases=5000, max_reads=50)  # several chunks through the pipeline
+        for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+            got = ses.query_host_i32(a, off, mode)
+            assert got.dtype == np.int32
+            np.testing.assert_array_equal(got.astype(np.int64), vals)
+        ses2 = S.Session(idx, a.size, len(reads))
+        da, do = torch.from_numpy(a).cuda(), torch.from_numpy(off).cuda()
+        out = torch.full((vals.size,), -7, dtype=torch.int32, device="cuda")
+        ses2.query_device_i32(da.data_ptr(), do.data_ptr(), len(reads), a.size, S.MODE_STREAMING, out.data_ptr(), vals.size,
+                              torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.cpu().numpy().astype(np.int64), vals)
+
+
+def test_int32_results_refused_on_wide_index(monkeypatch):
+    monkeypatch.setenv("SBWT_B200_FORCE_WIDE", "3")
+    reads = read_fasta_reads(golden("small_k31", "reads.fna"))
+    a, off = synth.ragged_to_batch(reads)
+    idx = S.Index(golden("small_k31", "index.sbwt"))
+    ses = S.Session(idx, a.size, len(reads))
+    with pytest.raises(S.SbwtGpuError, match="int32 results need"):
+        ses.query_host_i32(a, off, S.MODE_SEARCH)
+
+
+def test_long_reads_and_mixed_runs(tmp_path):
+    """Reads far longer than a work-item window, with planted stretches, substitutions and Ns in between:
+    every switch between streaming and from-scratch search, across window boundaries."""
+    ref = synth.random_contigs(2, 50_000, seed=7)
+    fa = str(tmp_path / "r.fna")
+    synth.write_fasta(fa, [ref[i] for i in range(2)])
+    ix = str(tmp_path / "i.sbwt")
+    build_index(fa, ix, k=31, precalc=8, add_rc=True)
+    rng = np.random.default_rng(11)
+    reads = []
+    for i in range(60):
+        parts = []
+        for _ in range(int(rng.integers(1, 12))):
+            L = int(rng.integers(1, 900))
+            if rng.random() < 0.6:
+                o = int(rng.integers(0, 50_000 - L))
+                seg = ref[int(rng.integers(0, 2)), o:o + L].copy()
+                for _ in range(int(rng.integers(0, 3))):
+                    seg[int(rng.integers(0, L))] = synth.LUT[int(rng.integers(0, 4))]
+            else:
+                seg = synth.LUT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+            if rng.random() < 0.2:
+                seg[int(rng.integers(0, L))] = ord("N")
+            parts.append(seg)
+        reads.append(bytes(np.concatenate(parts)))
+    a, off = synth.ragged_to_batch(reads)
+    want = oracle.OracleIndex(ix).query_batch(a, off, streaming=True)
+    assert 0.2 < (want >= 0).mean() < 0.8
+    res = run_both(ix, reads)
+    np.testing.assert_array_equal(res[S.MODE_STREAMING], want)
+    np.testing.assert_array_equal(res[S.MODE_SEARCH], want)
