@@ -42,6 +42,8 @@ WORKLOADS = {
                ref=("contigs", 100, 1_000_000, 42), k=31, streaming=False, rc=False, reads=10_000_000),
     "c4s": dict(desc="configs[3] scaled: pangenome-like 40 x 5 Mbp mutated copies (5% subst.), k=31 +RC, index > L2, streaming_search",
                 ref=("pangenome", 40, 5_000_000, 44), k=31, streaming=True, rc=True, reads=10_000_000),
+    "c5s": dict(desc="configs[4] scaled: the same pangenome-like reference, k=63 (+RC), index > L2, streaming_search, 88 lookups per 150-bp read",
+                ref=("pangenome", 40, 5_000_000, 44), k=63, streaming=True, rc=True, reads=10_000_000),
     "tiny": dict(desc="smoke-sized: 2 Mbp random DNA, k=31, streaming", ref=("contigs", 2, 1_000_000, 42), k=31, streaming=True,
                  rc=False, reads=200_000),
 }
@@ -314,7 +316,24 @@ def main() -> None:
             sec = float(t.item())
         e2e = {"value": world * n_out / sec, "unit": "lookups/s", "h2d_bytes_per_step": int(a.nbytes + off.nbytes),
                "d2h_bytes_per_step": int(n_out * 8), "ms_per_step": sec * 1e3, "steps": n_e2e,
-               "api": "sbwt_gpu_query_host (pinned host buffers, int64 results)"}
+               "api": "sbwt_gpu_query_host (pinned host buffers, int64 results: what SBWT::streaming_search returns)"}
+        if idx.n_nodes < (1 << 31):
+            # the same call with int32 results (same values; half the PCIe bytes of the result copy, which bounds e2e)
+            h_out32 = S.pinned_empty(n_out, np.int32)
+            ses_h.query_host_i32(h_a, h_off, mode, out=h_out32)
+            assert np.array_equal(h_out32[: 120 * 50].astype(np.int64), h_out[: 120 * 50])
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                ses_h.query_host_i32(h_a, h_off, mode, out=h_out32)
+            sec32 = (time.perf_counter() - t0) / n_e2e
+            if dist is not None:
+                t = torch.tensor([sec32], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sec32 = float(t.item())
+            e2e["int32_results"] = {"value": world * n_out / sec32, "unit": "lookups/s", "d2h_bytes_per_step": int(n_out * 4),
+                                    "ms_per_step": sec32 * 1e3, "api": "sbwt_gpu_query_host_i32"}
+            del h_out32
         ses_h.close()
 
     if rank != 0:

@@ -41,8 +41,11 @@ namespace sbwt_b200 {
 constexpr int kW2Threads = 256;
 constexpr int kW2Warps = kW2Threads / 32;
 constexpr int kQCap = 64; // entries per queue: at most 32 are waiting when up to 32 more are pushed
+#ifndef SBWT_B200_W2_MINBLOCKS
+#define SBWT_B200_W2_MINBLOCKS 6
+#endif
 #ifndef SBWT_B200_SINGLE_HOLD
-#define SBWT_B200_SINGLE_HOLD 1
+#define SBWT_B200_SINGLE_HOLD 2
 #endif
 constexpr uint32_t kSingleHold = SBWT_B200_SINGLE_HOLD; // extra NARROW steps on a singleton interval before it is queued (drops most chance survivors)
 
@@ -112,7 +115,7 @@ __device__ __forceinline__ void store_result(const WalkParams& P, uint32_t o, in
 // control flow is followed to the letter -- after a miss the k-mers are searched one at a time and
 // streaming resumes from the first one found (SBWT.hh:556-576); invalid bases are met by the chain.
 template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL>
-__global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : 4) walk2_kernel(const WalkParams P) {
+__global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS) walk2_kernel(const WalkParams P) {
     static_assert(STREAMING || !LITERAL, "LITERAL is a streaming-mode variant");
     typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
     __shared__ W2Queues<WIDE> queues[kW2Warps];
