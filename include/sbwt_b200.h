@@ -145,6 +145,29 @@ int sbwt_gpu_search_batch(sbwt_gpu_session *s, const char *ascii, const int64_t 
 int sbwt_gpu_streaming_batch(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,
                              int64_t n_reads, int64_t *out);
 
+/* ---- text output ---------------------------------------------------------
+ * print_vector (src/CLI/sbwt_search.cpp:21-43) on the device: per read "<value> " for every k-mer and
+ * then '\n'; -1 prints as "-1"; any other value <= 0 prints as an empty field, as in the reference. */
+
+/* Bytes that always hold the text of n_values results of this index in n_reads lines. */
+int64_t sbwt_gpu_text_capacity(const sbwt_gpu_index *idx, int64_t n_values, int64_t n_reads);
+
+/* Formats device-resident results (int64, or int32 when vals_are_i32) of the reads described by
+ * d_read_offsets (as given to sbwt_gpu_query_device; read i yields max(0, len_i - k + 1) values, consecutive
+ * in d_vals) into d_text. *d_text_bytes (device, may be NULL) receives the text length; when it exceeds
+ * text_capacity nothing is written. n_reads <= the session's max_reads. Asynchronous on cuda_stream. */
+int sbwt_gpu_format_device(sbwt_gpu_session *s, const void *d_vals, int vals_are_i32, const int64_t *d_read_offsets,
+                           int64_t n_reads, char *d_text, int64_t text_capacity, int64_t *d_text_bytes, void *cuda_stream);
+
+/* Receives consecutive pieces of the output text, in order; a nonzero return aborts the call. */
+typedef int (*sbwt_gpu_text_sink)(void *user, const char *text, int64_t n_bytes);
+
+/* run_queries_* + print_vector for a host batch (what `sbwt search` does per file, sbwt_search.cpp:45-91):
+ * H2D -> pack -> walk -> format on the device -> D2H of the text, double-buffered; the text reaches `sink`
+ * in order. *n_lookups (may be NULL) receives the number of k-mers answered. */
+int sbwt_gpu_query_host_text(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets, int64_t n_reads,
+                             int mode, int case_mode, sbwt_gpu_text_sink sink, void *user, int64_t *n_lookups);
+
 /* Page-locked host memory for the buffers handed to sbwt_gpu_query_host: pinned buffers are
  * DMA'd directly, pageable ones are staged through the session's own pinned buffers. */
 int sbwt_gpu_host_alloc(size_t bytes, void **out);

@@ -33,7 +33,10 @@ EXPORTS = [
     "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
     "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
     "sbwt_gpu_index_set_table_length", "sbwt_gpu_index_table_length",
+    "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text",
 ]
+
+TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
 
 
 class Stats(C.Structure):
@@ -91,6 +94,10 @@ def lib():
         L.sbwt_gpu_launch_count.argtypes = [i32]
         L.sbwt_gpu_launch_count.restype = i64
         L.sbwt_gpu_sector_probe.argtypes = [i32, i64, i64, i32, i32, C.POINTER(C.c_double)]
+        L.sbwt_gpu_text_capacity.argtypes = [vp, i64, i64]
+        L.sbwt_gpu_text_capacity.restype = i64
+        L.sbwt_gpu_format_device.argtypes = [vp, vp, i32, vp, i64, vp, i64, vp, vp]
+        L.sbwt_gpu_query_host_text.argtypes = [vp, vp, vp, i64, i32, i32, TEXT_SINK, vp, C.POINTER(i64)]
         _lib = L
     return _lib
 
@@ -264,6 +271,33 @@ class Session:
                      stream: int = 0, case_mode: int = CASE_UPPER) -> None:
         """sbwt_gpu_query_device: raw device pointers, asynchronous on `stream`."""
         _check(lib().sbwt_gpu_query_device(self._h, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, n_out, stream))
+
+    def query_host_text(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER,
+                        sink=None) -> tuple[bytes | None, int]:
+        """sbwt_gpu_query_host_text: the print_vector text of the batch (formatted on the device).
+        Returns (text, n_lookups); with `sink(piece: bytes)` given the pieces go there and text is None."""
+        assert ascii_.dtype == np.uint8 and ascii_.flags.c_contiguous
+        assert offsets.dtype == np.int64 and offsets.flags.c_contiguous
+        parts: list[bytes] = []
+
+        def _cb(_user, ptr, n):
+            piece = C.string_at(ptr, n)
+            (sink or parts.append)(piece)
+            return 0
+
+        n = C.c_int64()
+        _check(lib().sbwt_gpu_query_host_text(self._h, ascii_.ctypes.data, offsets.ctypes.data, offsets.size - 1, mode, case_mode,
+                                              TEXT_SINK(_cb), None, C.byref(n)))
+        return (None if sink else b"".join(parts)), n.value
+
+    def text_capacity(self, n_values: int, n_reads: int) -> int:
+        return lib().sbwt_gpu_text_capacity(self.index._h, n_values, n_reads)
+
+    def format_device(self, d_vals: int, vals_are_i32: bool, d_offsets: int, n_reads: int, d_text: int, capacity: int,
+                      d_text_bytes: int = 0, stream: int = 0) -> None:
+        """sbwt_gpu_format_device: raw device pointers, asynchronous on `stream`."""
+        _check(lib().sbwt_gpu_format_device(self._h, d_vals, int(vals_are_i32), d_offsets, n_reads, d_text, capacity,
+                                            d_text_bytes or None, stream))
 
     def set_timing(self, enable: bool = True) -> None:
         _check(lib().sbwt_gpu_session_set_timing(self._h, int(enable)))

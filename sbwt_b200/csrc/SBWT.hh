@@ -227,6 +227,21 @@ public:
                                       n_reads, mode, case_mode, out));
     }
 
+    // The same batch answered as the text `sbwt search` writes (print_vector, sbwt_search.cpp:21-43), formatted on the
+    // device; pieces of the text reach `sink` in order. Returns the number of k-mers answered.
+    int64_t query_batch_text(const char* ascii, const int64_t* offsets, int64_t n_reads, int mode, int case_mode, sbwt_gpu_text_sink sink,
+                             void* user) const {
+        if (n_reads == 0) return 0;
+        if (mode == SBWT_GPU_MODE_STREAMING && suffix_group_starts.empty()) throw std::runtime_error("Error: streaming search support not built");
+        const int64_t bases = offsets[n_reads] - offsets[0];
+        const int64_t cap_bases = std::min<int64_t>(std::max<int64_t>(bases, 1), (int64_t)96 << 20);
+        int64_t longest = 0, n_lookups = 0;
+        for (int64_t i = 0; i < n_reads; i++) longest = std::max(longest, offsets[i + 1] - offsets[i]);
+        gpu_check(sbwt_gpu_query_host_text(get_session(std::max(cap_bases, longest), std::min<int64_t>(n_reads, (int64_t)4 << 20)), ascii,
+                                           offsets, n_reads, mode, case_mode, sink, user, &n_lookups));
+        return n_lookups;
+    }
+
     // SBWT.hh:418-437: extend the interval I by the characters of S. Two device rank queries per character.
     std::pair<int64_t, int64_t> update_sbwt_interval(const std::string& S, std::pair<int64_t, int64_t> I) const {
         return update_sbwt_interval(S.c_str(), (int64_t)S.size(), I);

@@ -7,12 +7,14 @@
 // and the same two timing log lines. Only the plain-matrix variant is served; the others are
 // refused (they are out of scope).
 //
-// Differences: reads are answered in batches (sbwt_gpu_query_host through sbwt::SBWT<>), so
-// "us/query (excluding I/O etc)" is the time spent inside the batch calls; extra options
-// --device and --batch-bases.
+// Differences: reads are answered in batches and the output text is formatted on the device
+// (sbwt_gpu_query_host_text through sbwt::SBWT<>), so "us/query (excluding I/O etc)" is the time spent inside
+// the batch calls, which here includes handing the text to the output file; extra options --device,
+// --batch-bases and --threads (gzip blocks are deflated in parallel).
 //
 //   sbwt_search [search] -o <out | list.txt> -i <index.sbwt> -q <reads.(fa|fq)[.gz] | list.txt> [-z]
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -66,88 +68,119 @@ static void check_writable(const string& filename) { // src/globals.cpp:44-46 (o
     if (!f.good()) throw std::runtime_error("Error opening file: " + filename);
 }
 
-// print_vector (sbwt_search.cpp:21-43) for a slice of reads: values of read i are
-// vals[out_off[i] .. out_off[i+1]). A value of 0 prints as an empty field, as in the reference.
-static void format_reads(const int64_t* vals, const int64_t* out_off, int64_t r0, int64_t r1, string& text) {
-    text.clear();
-    text.reserve((size_t)((out_off[r1] - out_off[r0]) * 8 + (r1 - r0)));
-    char buffer[32];
-    for (int64_t i = r0; i < r1; i++) {
-        for (int64_t q = out_off[i]; q < out_off[i + 1]; q++) {
-            int64_t x = vals[q];
-            int n = 0;
-            if (x == -1) {
-                text += "-1 ";
-                continue;
-            }
-            while (x > 0) { buffer[n++] = (char)('0' + x % 10); x /= 10; }
-            while (n) text.push_back(buffer[--n]);
-            text.push_back(' ');
-        }
-        text.push_back('\n');
-    }
-}
-
+// Output file. The text itself (print_vector, sbwt_search.cpp:21-43) is produced on the device
+// (sbwt_gpu_query_host_text) and arrives here in pieces. With -z every piece is cut into blocks that are
+// deflated in parallel, each as its own gzip member; the concatenation is a valid gzip file that
+// decompresses to the same bytes as the reference's zstr output (tests/test_CLI.hh:12-18 compares
+// decompressed content).
 struct Writer {
     FILE* fp = nullptr;
-    gzFile gz = nullptr;
-    Writer(const string& name, bool gzip) {
-        if (gzip) gz = gzopen(name.c_str(), "wb");
-        else fp = fopen(name.c_str(), "wb");
-        if (!gz && !fp) throw std::runtime_error("Error opening file: " + name);
+    bool gzip = false;
+    int threads = 8;
+    static constexpr size_t kGzBlock = (size_t)1 << 20;
+    Writer(const string& name, bool gzip, int threads) : gzip(gzip), threads(std::max(1, threads)) {
+        fp = fopen(name.c_str(), "wb");
+        if (!fp) throw std::runtime_error("Error opening file: " + name);
     }
     ~Writer() {
         if (fp) fclose(fp);
-        if (gz) gzclose(gz);
     }
-    void write(const string& s) {
-        if (s.empty()) return;
-        if (fp) { if (fwrite(s.data(), 1, s.size(), fp) != s.size()) throw std::runtime_error("Error writing output"); }
-        else { if (gzwrite(gz, s.data(), (unsigned)s.size()) != (int)s.size()) throw std::runtime_error("Error writing gzip output"); }
+    void put(const char* p, size_t n) {
+        if (n && fwrite(p, 1, n, fp) != n) throw std::runtime_error("Error writing output");
+    }
+    static void deflate_member(const char* src, size_t n, string& out) {
+        z_stream z;
+        memset(&z, 0, sizeof z);
+        if (deflateInit2(&z, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK)
+            throw std::runtime_error("Error writing gzip output");
+        out.resize(deflateBound(&z, (uLong)n) + 32);
+        z.next_in = (Bytef*)src;
+        z.avail_in = (uInt)n;
+        z.next_out = (Bytef*)&out[0];
+        z.avail_out = (uInt)out.size();
+        const int rc = deflate(&z, Z_FINISH);
+        const size_t produced = out.size() - z.avail_out;
+        deflateEnd(&z);
+        if (rc != Z_STREAM_END) throw std::runtime_error("Error writing gzip output");
+        out.resize(produced);
+    }
+    void write(const char* text, size_t n) {
+        if (n == 0) return;
+        if (!gzip) { put(text, n); return; }
+        const size_t nb = (n + kGzBlock - 1) / kGzBlock;
+        vector<string> parts(nb);
+        std::atomic<size_t> next{0};
+        std::atomic<bool> failed{false};
+        auto work = [&]() {
+            for (size_t b; (b = next.fetch_add(1)) < nb;) {
+                try { deflate_member(text + b * kGzBlock, std::min(kGzBlock, n - b * kGzBlock), parts[b]); }
+                catch (...) { failed = true; }
+            }
+        };
+        vector<std::thread> th;
+        for (int t = 1; t < (int)std::min<size_t>((size_t)threads, nb); t++) th.emplace_back(work);
+        work();
+        for (auto& x : th) x.join();
+        if (failed) throw std::runtime_error("Error writing gzip output");
+        for (const string& part : parts) put(part.data(), part.size());
+    }
+    void finish() { // an empty output is still a valid (empty) gzip stream
+        if (gzip && ftell(fp) == 0) {
+            string part;
+            deflate_member("", 0, part);
+            put(part.data(), part.size());
+        }
     }
 };
+
+struct SinkState {
+    Writer* writer;
+    string error;
+};
+
+static int text_sink(void* user, const char* text, int64_t n_bytes) {
+    SinkState* st = (SinkState*)user;
+    try {
+        st->writer->write(text, (size_t)n_bytes);
+        return 0;
+    } catch (const std::exception& e) {
+        st->error = e.what();
+        return 1;
+    }
+}
 
 struct Options {
     int64_t batch_bases = (int64_t)64 << 20;
     int64_t batch_reads = (int64_t)1 << 20;
-    int format_threads = 8;
+    int threads = 8;
 };
 
 // run_file (sbwt_search.cpp:93-105): streaming search when the index supports it, else search() per k-mer.
 static int64_t run_file(const string& infile, const string& outfile, const sbwt::plain_matrix_sbwt_t& index, bool gzip_output,
                         const Options& opt, long long& query_micros) {
     sbwt_b200::FastxReader reader(infile);
-    Writer writer(outfile, gzip_output);
+    Writer writer(outfile, gzip_output, opt.threads);
+    SinkState sink{&writer, ""};
     const bool streaming = index.has_streaming_query_support();
     write_log(string(streaming ? "Running streaming queries from input file " : "Running non-streaming queries from input file ") + infile +
               " to output file " + outfile);
-    const int64_t k = index.get_k();
     vector<char> ascii;
-    vector<int64_t> offsets, out_off, vals;
+    vector<int64_t> offsets;
     int64_t n_queries = 0;
     while (true) {
         const int64_t n = reader.next_batch(opt.batch_bases, opt.batch_reads, ascii, offsets);
         if (n == 0) break;
-        out_off.assign((size_t)n + 1, 0);
-        for (int64_t i = 0; i < n; i++) {
-            const int64_t len = offsets[i + 1] - offsets[i];
-            out_off[i + 1] = out_off[i] + (len >= k ? len - k + 1 : 0);
-        }
-        vals.resize((size_t)out_off[n]);
         const long long t0 = cur_time_micros();
-        index.query_batch_into(ascii.data(), offsets.data(), n, streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH,
-                               SBWT_GPU_CASE_UPPER, vals.data());
+        try {
+            n_queries += index.query_batch_text(ascii.data(), offsets.data(), n, streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH,
+                                                SBWT_GPU_CASE_UPPER, text_sink, &sink);
+        } catch (const std::runtime_error&) {
+            if (!sink.error.empty()) throw std::runtime_error(sink.error);
+            throw;
+        }
         query_micros += cur_time_micros() - t0;
-        n_queries += out_off[n];
-        // format in parallel, write in order
-        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(opt.format_threads, n / 256 + 1));
-        vector<string> parts((size_t)T);
-        vector<std::thread> th;
-        for (int t = 0; t < T; t++)
-            th.emplace_back([&, t]() { format_reads(vals.data(), out_off.data(), n * t / T, n * (t + 1) / T, parts[t]); });
-        for (auto& x : th) x.join();
-        for (const string& s : parts) writer.write(s);
     }
+    writer.finish();
     write_log("us/query: " + std::to_string((double)query_micros / std::max<int64_t>(n_queries, 1)) + " (excluding I/O etc)");
     return n_queries;
 }
@@ -164,6 +197,7 @@ static void print_help(const char* prog) {
               << "                         magnitude.\n"
               << "      --device arg       CUDA device (default 0)\n"
               << "      --batch-bases arg  Read bases per GPU batch (default 67108864)\n"
+              << "      --threads arg      Host threads for gzip output (default 8)\n"
               << "  -h, --help             Print usage\n" << std::endl;
 }
 
@@ -187,6 +221,7 @@ static int search_main(int argc, char** argv) {
         else if (a == "-z" || a == "--gzip-output") gzip_output = true;
         else if (a == "--device") device = std::stoi(value("device"));
         else if (a == "--batch-bases") opt.batch_bases = std::stoll(value("batch-bases"));
+        else if (a == "--threads") opt.threads = std::stoi(value("threads"));
         else throw std::runtime_error("Option '" + a + "' does not exist");
     }
     if (!have_i) throw std::runtime_error("Option 'index-file' has no value");

@@ -14,6 +14,7 @@
 #include "../../include/sbwt_b200.h"
 #include "aux_kernels.cuh"
 #include "device_index.cuh"
+#include "format_kernels.cuh"
 #include "sbwt_file.hpp"
 #include "walk_kernel.cuh"
 #include "walk2_kernel.cuh"
@@ -106,6 +107,8 @@ struct HostSlot {
     char* d_ascii = nullptr;
     int64_t* d_offsets = nullptr;
     int64_t* d_out = nullptr;
+    char* d_text = nullptr;       // print_vector text of the slot's batch (text queries only)
+    int64_t text_capacity = 0;
     char* h_ascii = nullptr;      // pinned staging, used only for pageable caller buffers
     int64_t* h_offsets = nullptr;
     int64_t* h_out = nullptr;
@@ -128,6 +131,8 @@ struct sbwt_gpu_session {
     cudaEvent_t ev_start = nullptr, ev_walk0 = nullptr, ev_walk1 = nullptr;
     bool host_ready = false;
     HostSlot slots[2];
+    char* h_text[2] = {nullptr, nullptr}; // pinned staging the text leaves the device through, piece by piece
+    cudaEvent_t text_ev[2] = {nullptr, nullptr};
 };
 
 // ------------------------------------------------------------------ small helpers
@@ -489,10 +494,14 @@ extern "C" void sbwt_gpu_session_destroy(sbwt_gpu_session* s) {
     if (s->ev_start) { cudaEventDestroy(s->ev_start); cudaEventDestroy(s->ev_walk0); cudaEventDestroy(s->ev_walk1); }
     for (HostSlot& h : s->slots) {
         scratch_free(h.sc);
-        cudaFree(h.d_ascii); cudaFree(h.d_offsets); cudaFree(h.d_out);
+        cudaFree(h.d_ascii); cudaFree(h.d_offsets); cudaFree(h.d_out); cudaFree(h.d_text);
         cudaFreeHost(h.h_ascii); cudaFreeHost(h.h_offsets); cudaFreeHost(h.h_out); cudaFreeHost(h.h_totals);
         if (h.stream) cudaStreamDestroy(h.stream);
         if (h.done) cudaEventDestroy(h.done);
+    }
+    for (int b = 0; b < 2; b++) {
+        cudaFreeHost(s->h_text[b]);
+        if (s->text_ev[b]) cudaEventDestroy(s->text_ev[b]);
     }
     delete s;
 }
@@ -830,6 +839,157 @@ extern "C" int sbwt_gpu_search_batch(sbwt_gpu_session* s, const char* ascii, con
 }
 extern "C" int sbwt_gpu_streaming_batch(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int64_t* out) {
     return sbwt_gpu_query_host(s, ascii, off, n_reads, SBWT_GPU_MODE_STREAMING, SBWT_GPU_CASE_UPPER, out);
+}
+
+// ------------------------------------------------------------------ text output (print_vector on the device)
+
+static int text_digits(int64_t n_nodes) { // longest printed value: n_nodes - 1, and "-1"
+    int d = 1;
+    for (int64_t v = std::max<int64_t>(n_nodes - 1, 1); v >= 10; v /= 10) d++;
+    return std::max(d, 2);
+}
+
+extern "C" int64_t sbwt_gpu_text_capacity(const sbwt_gpu_index* ix, int64_t n_values, int64_t n_reads) {
+    if (!ix || n_values < 0 || n_reads < 0) return -1;
+    return n_values * (text_digits(ix->n_nodes) + 1) + n_reads + 16;
+}
+
+// values -> text on `st`. voff_ready: sc.n_out already holds the exclusive scan of the per-read result
+// counts of exactly these reads (the batch has just been planned on the same stream).
+template <typename T>
+static int run_format_t(Scratch& sc, int64_t k, const T* d_vals, const int64_t* d_offsets, int64_t n_reads, bool voff_ready,
+                        char* d_text, int64_t capacity, int64_t* d_text_bytes, cudaStream_t st) {
+    if (n_reads > sc.max_reads) return set_error("%lld reads exceed the session capacity (%lld)", (long long)n_reads, (long long)sc.max_reads);
+    if (n_reads == 0) {
+        if (d_text_bytes) CU(cudaMemsetAsync(d_text_bytes, 0, 8, st));
+        CU(cudaMemsetAsync(sc.totals + 2, 0, 8, st));
+        return 0;
+    }
+    if (!voff_ready) {
+        plan_count_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)k, 1 << 30, sc.n_out, sc.n_win); LAUNCHED();
+        if (exclusive_scan_inplace(sc.n_out, n_reads, sc.partials, sc.totals + 0, st)) return 1;
+    }
+    const int64_t warps = (n_reads + kFmtReadsPerWarp - 1) / kFmtReadsPerWarp;
+    const unsigned grid = grid_for(warps * 32, kFmtThreads);
+    fmt_len_kernel<T><<<grid, kFmtThreads, 0, st>>>(d_vals, sc.n_out, sc.totals + 0, n_reads, sc.n_win); LAUNCHED();
+    if (exclusive_scan_inplace(sc.n_win, n_reads, sc.partials, sc.totals + 2, st)) return 1;
+    fmt_emit_kernel<T><<<grid, kFmtThreads, 0, st>>>(d_vals, sc.n_out, sc.totals + 0, sc.n_win, sc.totals + 2, n_reads, d_text, capacity); LAUNCHED();
+    CU(cudaGetLastError());
+    if (d_text_bytes) CU(cudaMemcpyAsync(d_text_bytes, sc.totals + 2, 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int sbwt_gpu_format_device(sbwt_gpu_session* s, const void* d_vals, int vals_are_i32, const int64_t* d_read_offsets,
+                                      int64_t n_reads, char* d_text, int64_t text_capacity, int64_t* d_text_bytes, void* stream) {
+    if (!s) return set_error("null session");
+    if (n_reads < 0 || text_capacity < 0) return set_error("negative size");
+    if (n_reads > 0 && (!d_vals || !d_read_offsets || !d_text)) return set_error("null buffer");
+    DeviceGuard guard(s->idx->device);
+    if (vals_are_i32)
+        return run_format_t<int32_t>(s->sc, s->idx->k, (const int32_t*)d_vals, d_read_offsets, n_reads, false, d_text, text_capacity,
+                                     d_text_bytes, (cudaStream_t)stream);
+    return run_format_t<int64_t>(s->sc, s->idx->k, (const int64_t*)d_vals, d_read_offsets, n_reads, false, d_text, text_capacity,
+                                 d_text_bytes, (cudaStream_t)stream);
+}
+
+constexpr int64_t kTextPiece = (int64_t)32 << 20; // bytes per D2H piece handed to the sink
+
+// waits for the slot's kernels, then moves its text to the host piece by piece (two pinned buffers) and hands
+// every piece to the sink, in order. The other slot's kernels keep the GPU busy meanwhile.
+static int slot_deliver_text(sbwt_gpu_session* s, HostSlot& h, sbwt_gpu_text_sink sink, void* user, int64_t* n_lookups) {
+    if (!h.busy) return 0;
+    CU(cudaEventSynchronize(h.done));
+    h.busy = false;
+    const int64_t total = h.h_totals[2];
+    if (n_lookups) *n_lookups += h.h_totals[0];
+    if (total > h.text_capacity) return set_error("internal error: text of %lld bytes exceeds the slot capacity %lld", (long long)total, (long long)h.text_capacity);
+    int64_t issued = 0, delivered = 0, size[2] = {0, 0};
+    auto issue = [&](int b) -> int {
+        const int64_t sz = std::min(kTextPiece, total - issued);
+        CU(cudaMemcpyAsync(s->h_text[b], h.d_text + issued, (size_t)sz, cudaMemcpyDeviceToHost, h.stream));
+        CU(cudaEventRecord(s->text_ev[b], h.stream));
+        size[b] = sz;
+        issued += sz;
+        return 0;
+    };
+    if (total > 0 && issue(0)) return 1;
+    for (int b = 0; delivered < total; b ^= 1) {
+        if (issued < total && issue(b ^ 1)) return 1;
+        CU(cudaEventSynchronize(s->text_ev[b]));
+        if (sink(user, s->h_text[b], size[b]) != 0) return set_error("the text sink reported an error");
+        delivered += size[b];
+    }
+    return 0;
+}
+
+extern "C" int sbwt_gpu_query_host_text(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                                        int case_mode, sbwt_gpu_text_sink sink, void* user, int64_t* n_lookups) {
+    if (!s) return set_error("null session");
+    if (n_lookups) *n_lookups = 0;
+    if (n_reads < 0) return set_error("negative batch size");
+    if (n_reads == 0) return 0;
+    if (!ascii || !off || !sink) return set_error("null argument");
+    sbwt_gpu_index* ix = s->idx;
+    if (mode == SBWT_GPU_MODE_STREAMING && !ix->has_sgs) return set_error("Error: streaming search support not built");
+    DeviceGuard guard(ix->device);
+    if (host_slots_init(s)) return 1;
+    for (int b = 0; b < 2; b++)
+        if (!s->h_text[b]) {
+            CU(cudaMallocHost(&s->h_text[b], (size_t)kTextPiece));
+            CU(cudaEventCreateWithFlags(&s->text_ev[b], cudaEventDisableTiming));
+        }
+    const bool out32 = ix->n_nodes < (1ll << 31) && !ix->view.wide; // same values; halves what the formatter reads
+    for (HostSlot& h : s->slots)
+        if (!h.d_text) {
+            h.text_capacity = sbwt_gpu_text_capacity(ix, s->max_bases, s->max_reads);
+            CU(cudaMalloc(&h.d_text, (size_t)h.text_capacity));
+        }
+    const bool pin_in = is_pinned(ascii), pin_off = is_pinned(off);
+    int64_t r0 = 0;
+    int turn = 0;
+    HostSlot* prev = nullptr;
+    while (r0 < n_reads) {
+        int64_t r1 = r0, bases = 0;
+        while (r1 < n_reads && r1 - r0 < s->max_reads) {
+            const int64_t len = off[r1 + 1] - off[r1];
+            if (len < 0) return set_error("read offsets must be non-decreasing");
+            if (len > s->max_bases) return set_error("read %lld (%lld bases) is longer than the session capacity (%lld bases)", (long long)r1, (long long)len, (long long)s->max_bases);
+            if (bases + len > s->max_bases) break;
+            bases += len;
+            r1++;
+        }
+        const int64_t nr = r1 - r0;
+        HostSlot& h = s->slots[turn & 1]; // free: its previous batch was delivered one iteration ago
+        turn++;
+        const char* src = ascii + off[r0];
+        if (!pin_in) {
+            if (!h.h_ascii) CU(cudaMallocHost(&h.h_ascii, s->max_bases + 64));
+            memcpy(h.h_ascii, src, (size_t)bases);
+            src = h.h_ascii;
+        }
+        const int64_t* osrc = off + r0;
+        if (!pin_off) {
+            if (!h.h_offsets) CU(cudaMallocHost(&h.h_offsets, (s->max_reads + 1) * 8));
+            memcpy(h.h_offsets, osrc, (size_t)(nr + 1) * 8);
+            osrc = h.h_offsets;
+        }
+        CU(cudaMemcpyAsync(h.d_ascii, src, (size_t)bases, cudaMemcpyHostToDevice, h.stream));
+        CU(cudaMemcpyAsync(h.d_offsets, osrc, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, h.stream));
+        if (run_device_batch(s, h.sc, h.d_ascii, h.d_offsets, nr, bases, mode, case_mode, h.d_out, out32, false, h.stream)) return 1;
+        const int rc = out32 ? run_format_t<int32_t>(h.sc, ix->k, (const int32_t*)h.d_out, h.d_offsets, nr, true, h.d_text, h.text_capacity, nullptr, h.stream)
+                             : run_format_t<int64_t>(h.sc, ix->k, h.d_out, h.d_offsets, nr, true, h.d_text, h.text_capacity, nullptr, h.stream);
+        if (rc) return 1;
+        CU(cudaMemcpyAsync(h.h_totals, h.sc.totals, 32, cudaMemcpyDeviceToHost, h.stream));
+        CU(cudaEventRecord(h.done, h.stream));
+        h.busy = true;
+        h.out_staged = false;
+        h.out_bytes = 0;
+        if (prev && slot_deliver_text(s, *prev, sink, user, n_lookups)) return 1;
+        prev = &h;
+        r0 = r1;
+    }
+    if (prev && slot_deliver_text(s, *prev, sink, user, n_lookups)) return 1;
+    return 0;
 }
 
 extern "C" int sbwt_gpu_host_alloc(size_t bytes, void** out) {
