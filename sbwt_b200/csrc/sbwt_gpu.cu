@@ -606,6 +606,17 @@ static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, 
     P.index_evict_last = el ? atoi(el) : 1;
     const char* ns = getenv("SBWT_B200_DEBUG_NOSTORE");
     P.debug_no_store = ns ? atoi(ns) : 0;
+    // probe stride of the streaming walk: a from-scratch walk on this index dies after about log4(n) characters, and a
+    // probe that dies at character j proves k - j k-mers absent. Any stride >= 1 gives the same results; it needs the
+    // search table to follow from the bit vectors (monotonicity of the interval step), else every k-mer is searched.
+    P.probe_stride = 0;
+    if (streaming && ix->table_from_bits) {
+        int log4n = 0;
+        while (log4n < 32 && (1ll << (2 * log4n)) < ix->n_nodes) log4n++;
+        const int64_t d = ix->k - log4n - 2;
+        P.probe_stride = d >= 8 ? (uint32_t)d : 0u;
+        if (const char* pe = getenv("SBWT_B200_PROBE")) P.probe_stride = (uint32_t)std::max(0, atoi(pe));
+    }
     {
         const char* pe = getenv("SBWT_B200_L2_PERSIST");
         const bool want = pe && atoi(pe) > 0;

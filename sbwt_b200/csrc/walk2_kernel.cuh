@@ -27,6 +27,17 @@
 //           rest of the item goes to the warp's TODO queue and is answered by NARROW + CHAIN with
 //           one lane per k-mer (streaming_search's answers equal search()'s, SURVEY.md 8(a) note 3).
 //
+//   PROBE   (streaming mode) runs of absent k-mers are not searched one by one. If the walk over
+//           S = read[m .. m+j] dies at character j, no node's label ends with S, and because the
+//           SBWT holds every prefix of every k-mer as (a suffix of) some node, no indexed k-mer
+//           contains S anywhere: every k-mer of the read that covers [m, m+j] is absent, i.e. the
+//           k-mers starting in [m+j-k+1, m]. So a range of k-mers left behind by a miss is probed at
+//           every D-th k-mer only (D = P.probe_stride, about k - log4(n) - 2); probes that die early
+//           enough prove their whole segment absent and the -1s are written with coalesced stores.
+//           The first segment that is not proven absent restarts the read there as a fresh item
+//           (FIRST pass: one full search, then the streaming chain again), exactly the control flow
+//           of SBWT.hh:556-576 -- only the proofs of absence are cheaper. Results are identical.
+//
 // Work (32-k-mer chunks in search mode, work items in streaming mode) is handed out through one
 // global cursor, so the grid is persistent and self-balancing.
 #pragma once
@@ -42,7 +53,7 @@ constexpr int kW2Threads = 256;
 constexpr int kW2Warps = kW2Threads / 32;
 constexpr int kQCap = 64; // entries per queue: at most 32 are waiting when up to 32 more are pushed
 #ifndef SBWT_B200_W2_MINBLOCKS
-#define SBWT_B200_W2_MINBLOCKS 6
+#define SBWT_B200_W2_MINBLOCKS 4
 #endif
 #ifndef SBWT_B200_SINGLE_HOLD
 #define SBWT_B200_SINGLE_HOLD 2
@@ -60,6 +71,10 @@ struct W2Queues {
     pos_t s_col[kQCap];
     // ranges of k-mers to be answered one lane per k-mer
     uint32_t t_base[kQCap], t_out[kQCap], t_cnt[kQCap];
+    // streaming mode: ranges (free of invalid bases) to be probed, and fresh items (restarts inside a read)
+    uint32_t p_base[kQCap], p_out[kQCap], p_cnt[kQCap];
+    uint32_t f_base[kQCap], f_out[kQCap], f_cnt[kQCap];
+    uint32_t own[32]; // PROBE: lane -> (range, probe number)
 };
 
 // the k-mer starting at base b as 2-bit codes, 16 per word, character j at bits [2j, 2j+2) of the window
@@ -132,19 +147,27 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
     const pos_t last_col = (pos_t)(ix.n_nodes - 1);
     constexpr uint32_t kGrab = STREAMING ? 32u : 8u; // items (streaming) or chunks (search) per cursor bump
 
-    uint32_t nV = 0, nS = 0, nT = 0;     // queue fill, warp-uniform
+    uint32_t nV = 0, nS = 0, nT = 0, nP = 0, nF = 0; // queue fill, warp-uniform
     uint32_t in_next = 0, in_end = 0;    // grabbed input range
     bool input_done = false;
     unsigned long long st_lookups = 0, st_hits = 0, st_ranks = 0, st_sectors = 0;
+    // probe stride in k-mers (0 = no probing: every k-mer after a miss is searched on its own)
+    const uint32_t D = (STREAMING && !LITERAL) ? P.probe_stride : 0u;
 
     while (true) {
         // ---- what to do next (warp-uniform)
-        enum : int { T_CHAIN_V, T_CHAIN_S, T_NARROW_TODO, T_NARROW_INPUT, T_EXIT };
+        // Every S, P or F entry becomes at most one entry downstream (S -> P -> F -> S|P), so their
+        // total only grows when input is taken, and input is taken only while it is <= 32: no queue
+        // ever holds more than kQCap entries.
+        enum : int { T_CHAIN_V, T_CHAIN_S, T_NARROW_TODO, T_NARROW_INPUT, T_PROBE, T_EXIT };
         int task;
+        bool take_input = false;
         if (nV >= 32) task = T_CHAIN_V;
         else if (STREAMING && nS >= 32 && nT <= 32) task = T_CHAIN_S;
         else if (nT > 0) task = T_NARROW_TODO;
-        else if (!input_done) {
+        else if (STREAMING && nP >= 16) task = T_PROBE;
+        else if (STREAMING && nF >= 32) task = T_NARROW_INPUT;
+        else if (!input_done && (!STREAMING || nS + nP + nF <= 32)) {
             if (in_next >= in_end) {
                 uint32_t g = 0;
                 if (lane == 0) g = (uint32_t)atomicAdd(P.cursor, (unsigned long long)kGrab);
@@ -154,7 +177,10 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                 in_end = min(g + kGrab, n_items);
             }
             task = T_NARROW_INPUT;
-        } else if (STREAMING && nS > 0) task = T_CHAIN_S;
+            take_input = true;
+        } else if (STREAMING && nP > 0) task = T_PROBE;
+        else if (STREAMING && nF > 0) task = T_NARROW_INPUT;
+        else if (STREAMING && nS > 0) task = T_CHAIN_S;
         else if (nV > 0) task = T_CHAIN_V;
         else task = T_EXIT;
         if (task == T_EXIT) break;
@@ -244,10 +270,13 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                 if (STREAMING) { // the k-mers after a miss are searched from scratch (SBWT.hh:557-559), one lane each
                     const bool push = ended && rem > 0;
                     const unsigned pm = __ballot_sync(FULL, push);
-                    if (pm) {
-                        const uint32_t at = nT + __popc(pm & lt_mask);
-                        if (push) { Q.t_base[at] = pos - j + 1; Q.t_out[at] = o; Q.t_cnt[at] = rem; }
-                        nT += __popc(pm);
+                    if (pm) { // (the chain only covers k-mers free of invalid bases, so the range may be probed)
+                        const uint32_t at = (D ? nP : nT) + __popc(pm & lt_mask);
+                        if (push) {
+                            if (D) { Q.p_base[at] = pos - j + 1; Q.p_out[at] = o; Q.p_cnt[at] = rem; }
+                            else { Q.t_base[at] = pos - j + 1; Q.t_out[at] = o; Q.t_cnt[at] = rem; }
+                        }
+                        if (D) nP += __popc(pm); else nT += __popc(pm);
                         __syncwarp();
                     }
                 }
@@ -256,11 +285,43 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
         }
 
         // ==================================================================== NARROW
-        // lanes = first k-mers of 32 work items (LITERAL: also the next k-mer of a TODO range, alone)
+        // lanes = first k-mers of up to 32 work items or fresh items (LITERAL: also the next k-mer of a TODO
+        // range, alone); or 32 k-mers of a TODO range / search chunk; or the probes of a few P ranges
+        const bool probe = STREAMING && task == T_PROBE;
         const bool first = STREAMING && (task == T_NARROW_INPUT || LITERAL);
         bool act = false;
         uint32_t b = 0, o = 0, cnt = 1, nvalid = 1;
-        if (task == T_NARROW_TODO) {
+        uint32_t pr_tb = 0, pr_to = 0, pr_tc = 0, pr_np = 0, pr_S = 0, G = 0, seg_lo = 0, xm = 0; // PROBE
+        if (probe) {
+            // lanes 0 .. G-1 hold the top G ranges of P (as many as give <= 32 probes), then every lane takes one probe
+            const uint32_t n_take = min(nP, 32u);
+            if ((uint32_t)lane < n_take) {
+                const uint32_t t = nP - 1 - lane;
+                pr_tb = Q.p_base[t]; pr_to = Q.p_out[t]; pr_tc = Q.p_cnt[t];
+                pr_np = min((pr_tc + D - 1) / D, 32u);
+            }
+            pr_S = pr_np;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, pr_S, s);
+                if (lane >= s) pr_S += t;
+            }
+            G = __popc(__ballot_sync(FULL, (uint32_t)lane < n_take && pr_S <= 32u));
+            const uint32_t total = __shfl_sync(FULL, pr_S, G - 1);
+            __syncwarp();
+            if ((uint32_t)lane < G)
+                for (uint32_t t = 0; t < pr_np; t++) Q.own[pr_S - pr_np + t] = (uint32_t)lane | (t << 8);
+            nP -= G;
+            __syncwarp();
+            act = (uint32_t)lane < total;
+            const uint32_t ow = act ? Q.own[lane] : 0u;
+            const uint32_t tb = __shfl_sync(FULL, pr_tb, ow & 0xFFu), to = __shfl_sync(FULL, pr_to, ow & 0xFFu);
+            const uint32_t tc = __shfl_sync(FULL, pr_tc, ow & 0xFFu);
+            seg_lo = (ow >> 8) * D;
+            xm = min(seg_lo + D, tc) - 1u; // the probe is the last k-mer of its segment
+            b = tb + xm;
+            o = to + xm;
+        } else if (task == T_NARROW_TODO) {
             const uint32_t t = nT - 1;
             const uint32_t tb = Q.t_base[t], to = Q.t_out[t], tc = Q.t_cnt[t];
             __syncwarp();
@@ -284,12 +345,23 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
             b = it.x + lane;
             o = it.y + lane;
         } else {
-            const uint32_t idx = in_next + lane;
-            const bool have = idx < in_end;
-            in_next = in_end;
-            if (have) {
-                const uint4 it = __ldg(reinterpret_cast<const uint4*>(P.items) + idx);
-                b = it.x; o = it.y; cnt = it.z; nvalid = it.w;
+            // fresh items first, then new work items
+            const uint32_t n_f = min(nF, 32u);
+            bool have = false;
+            if ((uint32_t)lane < n_f) {
+                const uint32_t t = nF - 1 - lane;
+                b = Q.f_base[t]; o = Q.f_out[t]; cnt = Q.f_cnt[t]; nvalid = cnt;
+                have = true;
+            }
+            nF -= n_f;
+            if (take_input) {
+                const uint32_t m = min(32u - n_f, in_end - in_next);
+                if ((uint32_t)lane >= n_f && (uint32_t)lane - n_f < m) {
+                    const uint4 it = __ldg(reinterpret_cast<const uint4*>(P.items) + in_next + ((uint32_t)lane - n_f));
+                    b = it.x; o = it.y; cnt = it.z; nvalid = it.w;
+                    have = true;
+                }
+                in_next += m;
             }
             act = have && nvalid > 0;
             // an item whose first k-mer covers an invalid base is answered one lane per k-mer
@@ -308,7 +380,7 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
         bool alive = act;
         if (act) {
             win = load_win<KW>(P.codes, b);
-            if (!first || (LITERAL && task == T_NARROW_TODO)) alive = !kmer_invalid<KW>(P.invalid, b, (int)k);
+            if (!probe && (!first || (LITERAL && task == T_NARROW_TODO))) alive = !kmer_invalid<KW>(P.invalid, b, (int)k);
         }
         pos_t l = 0, r = last_col;
         if (p != 0 && alive) {
@@ -319,7 +391,9 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
             if (row.absent()) alive = false;
             if (COUNT) st_sectors++;
         }
-        uint32_t jl = p, single = (alive && l == r) ? 1u : 0u;
+        // jl: characters consumed; when the walk dies, the string of the first jl + 1 characters is absent
+        // (a row missing from the table: its p characters are)
+        uint32_t jl = (p != 0 && act && !alive) ? p - 1u : p, single = (alive && l == r) ? 1u : 0u;
         while (true) {
             const bool go = alive && jl < k && single <= kSingleHold;
             if (!__any_sync(FULL, go)) break;
@@ -355,6 +429,44 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
             }
         }
         const bool dead = act && !alive;
+        if (probe) {
+            // a dead probe proves the k-mers [xm + jl + 1 - k, xm] of its range absent; "covered": its whole segment
+            const bool covered = dead && (int)(xm + jl + 1u) - (int)k <= (int)seg_lo;
+            const unsigned badmask = __ballot_sync(FULL, act && !covered);
+            uint32_t nfill = 0;
+            bool cont = false, fresh = false;
+            if ((uint32_t)lane < G) {
+                const uint32_t lo = pr_S - pr_np;
+                const unsigned bm = badmask & ((pr_np >= 32u ? FULL : ((1u << pr_np) - 1u)) << lo);
+                if (bm) { // restart the read at the first segment that is not proven absent
+                    nfill = (uint32_t)(__ffs(bm) - 1 - (int)lo) * D;
+                    cont = fresh = true;
+                } else { // all probed segments are absent; a range longer than 32 segments goes on being probed
+                    nfill = min(pr_tc, pr_np * D);
+                    cont = nfill < pr_tc;
+                }
+            }
+            const unsigned fm = __ballot_sync(FULL, cont && fresh), rm = __ballot_sync(FULL, cont && !fresh);
+            if (fm) {
+                const uint32_t at = nF + __popc(fm & lt_mask);
+                if (cont && fresh) { Q.f_base[at] = pr_tb + nfill; Q.f_out[at] = pr_to + nfill; Q.f_cnt[at] = pr_tc - nfill; }
+                nF += __popc(fm);
+            }
+            if (rm) {
+                const uint32_t at = nP + __popc(rm & lt_mask);
+                if (cont && !fresh) { Q.p_base[at] = pr_tb + nfill; Q.p_out[at] = pr_to + nfill; Q.p_cnt[at] = pr_tc - nfill; }
+                nP += __popc(rm);
+            }
+            for (uint32_t g = 0; g < G; g++) { // the proven misses, 32 consecutive results per store
+                const uint32_t to = __shfl_sync(FULL, pr_to, g), nf = __shfl_sync(FULL, nfill, g);
+                for (uint32_t x = lane; x < nf; x += 32) {
+                    store_result<OUT32>(P, to + x, -1);
+                    if (COUNT) st_lookups++;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         if (dead) {
             store_result<OUT32>(P, o, -1);
             if (COUNT) st_lookups++;
@@ -374,13 +486,21 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
         } else {
             // what streaming cannot reach is answered one lane per k-mer: everything after a first
             // k-mer that is absent, and everything from the first k-mer that covers an invalid base on
-            const bool pd = dead && cnt > 1, pa = alive && nvalid < cnt;
+            // (with probing: the k-mers up to the first invalid base are probed, the rest is answered per k-mer)
+            const bool pd = dead && cnt > 1 && D == 0, pa = (alive || (dead && D != 0)) && nvalid < cnt;
             const unsigned tm = __ballot_sync(FULL, pd || pa);
             if (tm) {
                 const uint32_t at = nT + __popc(tm & lt_mask);
                 const uint32_t skip = pd ? 1u : nvalid;
                 if (pd || pa) { Q.t_base[at] = b + skip; Q.t_out[at] = o + skip; Q.t_cnt[at] = cnt - skip; }
                 nT += __popc(tm);
+            }
+            const bool pp = dead && D != 0 && nvalid > 1;
+            const unsigned ppm = __ballot_sync(FULL, pp);
+            if (ppm) {
+                const uint32_t at = nP + __popc(ppm & lt_mask);
+                if (pp) { Q.p_base[at] = b + 1; Q.p_out[at] = o + 1; Q.p_cnt[at] = nvalid - 1; }
+                nP += __popc(ppm);
             }
             const unsigned sm = __ballot_sync(FULL, alive);
             if (sm) {

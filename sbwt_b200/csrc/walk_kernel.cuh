@@ -49,6 +49,8 @@ struct WalkParams {
     unsigned long long* cursor; // next unclaimed work item (walk2_kernel; zeroed before every launch)
     int index_evict_last;      // L2 policy of the index / table loads
     int debug_no_store;        // measurement only (SBWT_B200_DEBUG_NOSTORE): results are not written
+    uint32_t probe_stride;     // walk2_kernel, streaming mode: distance in k-mers between the probes of a range of
+                               // presumed misses (0 = every k-mer after a miss is searched on its own)
 };
 
 constexpr int kRingCodeWords = 16; // u32 words of codes per lane: 4 chunks of 64 bases

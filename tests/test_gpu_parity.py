@@ -378,3 +378,52 @@ def test_long_reads_and_mixed_runs(tmp_path):
     res = run_both(ix, reads)
     np.testing.assert_array_equal(res[S.MODE_STREAMING], want)
     np.testing.assert_array_equal(res[S.MODE_SEARCH], want)
+
+
+@pytest.mark.parametrize("stride", ["0", "1", "2", "5", "9", "40"])
+def test_probe_strides_give_identical_results(stride, tmp_path, monkeypatch):
+    """The streaming walk answers runs of misses by probing every D-th k-mer (walk2_kernel PROBE). Any stride,
+    and no probing at all (0), must give the reference's answers: golden fixtures, config 1, and long reads with
+    planted stretches, substitutions every few bases and Ns (restarts, partial coverage, ranges of > 32 segments),
+    with small work-item windows as well."""
+    monkeypatch.setenv("SBWT_B200_PROBE", stride)
+    for name in ("small_k31", "small_k63_rc", "cli_k6"):
+        expected = open(golden(name, "known_answer.txt" if name == "cli_k6" else "expected.txt"), "rb").read()
+        reads = read_fasta_reads(golden(name, "queries.fna" if name == "cli_k6" else "reads.fna"))
+        vals, _ = parse_expected(expected)
+        np.testing.assert_array_equal(run_both(golden(name, "index.sbwt"), reads, modes=(S.MODE_STREAMING,))[S.MODE_STREAMING], vals)
+    vals, _ = parse_expected(c1_expected())
+    np.testing.assert_array_equal(run_both(golden("c1", "index.sbwt"), c1_reads(), modes=(S.MODE_STREAMING,))[S.MODE_STREAMING], vals)
+
+    ref = synth.random_contigs(2, 60_000, seed=17)
+    fa = str(tmp_path / "r.fna")
+    synth.write_fasta(fa, [ref[i] for i in range(2)])
+    ix = str(tmp_path / "i.sbwt")
+    build_index(fa, ix, k=31, precalc=8, add_rc=False)
+    rng = np.random.default_rng(int(stride) + 100)
+    reads = []
+    for i in range(80):
+        parts = []
+        for _ in range(int(rng.integers(1, 8))):
+            L = int(rng.integers(1, 1500))
+            kind = rng.random()
+            if kind < 0.55:  # a stretch of the reference with substitutions at a random density
+                o = int(rng.integers(0, 60_000 - L))
+                seg = ref[int(rng.integers(0, 2)), o:o + L].copy()
+                gap = int(rng.integers(3, 120))
+                for pos in range(int(rng.integers(0, gap)), L, gap):
+                    seg[pos] = synth.LUT[(int(np.where(synth.LUT == seg[pos])[0][0]) + 1) & 3]
+            else:
+                seg = synth.LUT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+            if rng.random() < 0.25:
+                seg[int(rng.integers(0, L))] = ord("N")
+            parts.append(seg)
+        reads.append(bytes(np.concatenate(parts)))
+    a, off = synth.ragged_to_batch(reads)
+    want = oracle.OracleIndex(ix).query_batch(a, off, streaming=True)
+    assert 0.05 < (want >= 0).mean() < 0.9
+    for window in (None, "33", "1"):
+        if window:
+            monkeypatch.setenv("SBWT_B200_WINDOW", window)
+        got = run_both(ix, reads, modes=(S.MODE_STREAMING,))[S.MODE_STREAMING]
+        np.testing.assert_array_equal(got, want)
