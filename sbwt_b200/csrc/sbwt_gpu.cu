@@ -604,6 +604,8 @@ static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, 
     if (const char* e = getenv("SBWT_B200_BLOCKS_PER_SM")) blocks_per_sm = std::max(0, atoi(e));
     const char* el = getenv("SBWT_B200_L2_EVICT_LAST");
     P.index_evict_last = el ? atoi(el) : 1;
+    const char* fr = getenv("SBWT_B200_L2_FRAC");
+    P.l2_frac = fr ? (float)atof(fr) : 1.0f;
     const char* ns = getenv("SBWT_B200_DEBUG_NOSTORE");
     P.debug_no_store = ns ? atoi(ns) : 0;
     // probe stride of the streaming walk: a from-scratch walk on this index dies after about log4(n) characters, and a

@@ -120,10 +120,36 @@ __device__ __forceinline__ bool kmer_invalid(const uint32_t* __restrict__ inv, u
 
 template <bool OUT32>
 __device__ __forceinline__ void store_result(const WalkParams& P, uint32_t o, int64_t v) {
-    if (P.debug_no_store) return;
+    if (P.debug_no_store) { // measurement only: 1 = no store, 2 = plain write-back store instead of the streaming one
+        if (P.debug_no_store == 2) {
+            if (OUT32) P.out32[o] = (int32_t)v;
+            else P.out[o] = v;
+        }
+        return;
+    }
     if (OUT32) asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(P.out32 + o), "r"((int32_t)v) : "memory");
     else asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(P.out + o), "l"(v) : "memory");
 }
+
+// One whole 32-byte sector of results (4 x int64 or 8 x int32) in one store (STG.E.256).
+__device__ __forceinline__ void st_sector_cs(void* p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+
+// CHAIN writes one result per lane per step, each lane into its own read's slice of the output: as
+// single stores those are 32 partial-sector writes per warp and step, which L2 has to merge (and
+// fill from DRAM when the sector is gone again before its last part arrives: ncu r01d, 463 M
+// write-lookup misses and 17 GB of extra DRAM reads per 9.6 GB of results). So every lane collects
+// the results of one output sector in shared memory ([slot][lane]: conflict-free) and writes the
+// sector with one 256-bit store; only the ragged ends of a lane's run are written one by one.
+template <bool OUT32>
+struct OutStage {
+    typedef typename std::conditional<OUT32, int32_t, int64_t>::type val_t;
+    static constexpr uint32_t R = OUT32 ? 8u : 4u; // results per sector
+    val_t v[R][32];
+};
 
 // LITERAL (streaming mode on an index that violates "only suffix-group starts carry edges", i.e. a
 // hand-made file): streaming answers may then differ from search() answers, so the reference's
@@ -135,6 +161,11 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
     typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
     __shared__ W2Queues<WIDE> queues[kW2Warps];
     W2Queues<WIDE>& Q = queues[threadIdx.x >> 5];
+    __shared__ OutStage<OUT32> stages[kW2Warps];
+    OutStage<OUT32>& OS = stages[threadIdx.x >> 5];
+    constexpr uint32_t OR = OutStage<OUT32>::R;
+    // phase of result 0 inside its sector
+    const uint32_t oph = OUT32 ? (uint32_t)(((uintptr_t)P.out32 >> 2) & 7u) : (uint32_t)(((uintptr_t)P.out >> 3) & 3u);
     const DeviceIndexView& ix = P.ix;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
@@ -143,7 +174,10 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
     const uint32_t k = (uint32_t)ix.k, p = (uint32_t)ix.tp; // p: characters answered by the search table
     const uint32_t pmask = p ? (uint32_t)((1ull << (2 * p)) - 1ull) : 0u;
     const Sector* const sec_base = ix.sectors;
-    const uint64_t pol = make_l2_policy(P.index_evict_last != 0);
+    uint64_t pol = make_l2_policy(P.index_evict_last != 0);
+    const uint64_t pol_t = pol; // table rows
+    if (P.index_evict_last == 2) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(P.l2_frac));
+    if (P.index_evict_last == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(pol) : "f"(P.l2_frac));
     const pos_t last_col = (pos_t)(ix.n_nodes - 1);
     constexpr uint32_t kGrab = STREAMING ? 32u : 8u; // items (streaming) or chunks (search) per cursor bump
 
@@ -210,13 +244,51 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
             }
             __syncwarp();
             bool fs = false; // the lane is past its first k-mer: its steps are streaming steps (SBWT.hh:561-575)
+            uint32_t gs = o; // first result staged and not yet written
+            // result number x of this lane -> stage; a completed sector goes out in one store
+            auto emit = [&](uint32_t x, int64_t v) {
+                if (!sb) { // one result per lane: nothing to collect
+                    store_result<OUT32>(P, x, v);
+                    gs = x + 1u;
+                    return;
+                }
+                const uint32_t sl = (x + oph) & (OR - 1u);
+                OS.v[sl][lane] = (typename OutStage<OUT32>::val_t)v;
+                if (sl == OR - 1u) {
+                    if (x - gs == OR - 1u) {
+                        if (!P.debug_no_store) {
+                            uint32_t wv[8];
+                            if (OUT32) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) wv[i] = (uint32_t)OS.v[i & (OR - 1u)][lane];
+                                st_sector_cs(P.out32 + (x - 7u), wv);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    const unsigned long long q = (unsigned long long)OS.v[i & (OR - 1u)][lane];
+                                    wv[2 * i] = (uint32_t)q;
+                                    wv[2 * i + 1] = (uint32_t)(q >> 32);
+                                }
+                                st_sector_cs(P.out + (x - 3u), wv);
+                            }
+                        }
+                    } else {
+                        for (uint32_t y = gs; y <= x; y++) store_result<OUT32>(P, y, (int64_t)OS.v[(y + oph) & (OR - 1u)][lane]);
+                    }
+                    gs = x + 1u;
+                }
+            };
+            auto drain = [&](uint32_t end) { // the lane's run is over: write what is still staged, [gs, end)
+                for (uint32_t y = gs; y < end; y++) store_result<OUT32>(P, y, (int64_t)OS.v[(y + oph) & (OR - 1u)][lane]);
+                gs = end;
+            };
             while (true) {
                 if (act && j == k) { // a k-mer's interval is a singleton (SBWT.hh:410-413): its column is the answer
-                    store_result<OUT32>(P, o, (int64_t)col);
+                    emit(o, (int64_t)col);
                     if (COUNT) { st_lookups++; st_hits++; }
                     o++;
                     rem--;
-                    if (rem == 0) act = false;
+                    if (rem == 0) { act = false; drain(o); }
                     else { j = k - 1; fs = true; }
                 }
                 if (!__any_sync(FULL, act)) break;
@@ -261,11 +333,12 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                 }
                 const bool ended = act && miss;
                 if (ended) {
-                    store_result<OUT32>(P, o, -1);
+                    emit(o, -1);
                     if (COUNT) st_lookups++;
                     o++;
                     rem--;
                     act = false;
+                    drain(o);
                 }
                 if (STREAMING) { // the k-mers after a miss are searched from scratch (SBWT.hh:557-559), one lane each
                     const bool push = ended && rem > 0;
@@ -385,7 +458,7 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
         pos_t l = 0, r = last_col;
         if (p != 0 && alive) {
             // first character = least significant digit of the table index (SBWT.hh:396-401)
-            const TableRow<WIDE> row = TableRow<WIDE>::load(ix.table, win.w[0] & pmask, pol);
+            const TableRow<WIDE> row = TableRow<WIDE>::load(ix.table, win.w[0] & pmask, pol_t);
             l = (pos_t)row.l;
             r = (pos_t)row.r;
             if (row.absent()) alive = false;

@@ -47,7 +47,8 @@ struct WalkParams {
     int32_t* out32;           // ... or as int32 (OUT32 kernels; callers use them only when n_nodes < 2^31)
     unsigned long long* stats; // [lookups, hits, rank_ops, sectors] (COUNT only)
     unsigned long long* cursor; // next unclaimed work item (walk2_kernel; zeroed before every launch)
-    int index_evict_last;      // L2 policy of the index / table loads
+    int index_evict_last;      // L2 policy of the index / table loads (1 = evict_last; 2, 3: experiments with l2_frac)
+    float l2_frac;
     int debug_no_store;        // measurement only (SBWT_B200_DEBUG_NOSTORE): results are not written
     uint32_t probe_stride;     // walk2_kernel, streaming mode: distance in k-mers between the probes of a range of
                                // presumed misses (0 = every k-mer after a miss is searched on its own)
