@@ -316,7 +316,41 @@ def main() -> None:
             sec = float(t.item())
         e2e = {"value": world * n_out / sec, "unit": "lookups/s", "h2d_bytes_per_step": int(a.nbytes + off.nbytes),
                "d2h_bytes_per_step": int(n_out * 8), "ms_per_step": sec * 1e3, "steps": n_e2e,
-               "api": "sbwt_gpu_query_host (pinned host buffers, int64 results: what SBWT::streaming_search returns)"}
+               "api": "sbwt_gpu_query_host (pinned host buffers, int64 results: what SBWT::streaming_search returns)",
+               "result_wire_format": ("int32 over PCIe, sign-extended into the caller's int64 array by host threads "
+                                      "(host_widen.hpp; SBWT_B200_WIDEN_THREADS, default = hardware threads / visible GPUs, <= 16)")
+               if ses_h.widen_threads() > 0 else "int64 over PCIe",
+               "widen_threads": ses_h.widen_threads(), "host_threads": os.cpu_count()}
+        if ses_h.widen_threads() > 0:
+            e2e["d2h_bytes_per_step"] = int(n_out * 4)
+
+        def timed_leg(session, fn_name, out_buf):
+            getattr(session, fn_name)(h_a, h_off, mode, out=out_buf)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                getattr(session, fn_name)(h_a, h_off, mode, out=out_buf)
+            s_ = (time.perf_counter() - t0) / n_e2e
+            if dist is not None:
+                t_ = torch.tensor([s_], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                s_ = float(t_.item())
+            return s_
+
+        if ses_h.widen_threads() > 0:
+            # the same call with the int64 values themselves crossing PCIe (no host threads involved)
+            prev_env = os.environ.get("SBWT_B200_WIDEN_THREADS")
+            os.environ["SBWT_B200_WIDEN_THREADS"] = "0"
+            ses_d = S.Session(idx, chunk_bases, chunk_bases // max(1, L - 2) + 16)
+            h_out[:4096] = -7
+            sec_d = timed_leg(ses_d, "query_host", h_out)
+            os.environ.pop("SBWT_B200_WIDEN_THREADS")
+            if prev_env is not None:
+                os.environ["SBWT_B200_WIDEN_THREADS"] = prev_env
+            assert np.array_equal(h_out[: 120 * 50], d_out[: 120 * 50].cpu().numpy())
+            e2e["int64_over_pcie"] = {"value": world * n_out / sec_d, "unit": "lookups/s", "d2h_bytes_per_step": int(n_out * 8),
+                                      "ms_per_step": sec_d * 1e3, "api": "sbwt_gpu_query_host with SBWT_B200_WIDEN_THREADS=0"}
+            ses_d.close()
         if idx.n_nodes < (1 << 31):
             # the same call with int32 results (same values; half the PCIe bytes of the result copy, which bounds e2e)
             h_out32 = S.pinned_empty(n_out, np.int32)
@@ -350,7 +384,7 @@ def main() -> None:
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel": "walk_kernel",
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel": "walk2_kernel",
                 "kernel_ms": w_ms, "kernel_share_of_step": w_ms / ms_per_step, "prep_ms": float(np.mean(prep_ms)),
                 "algorithmic_sectors_per_step": stats.index_sectors, "sectors_per_s": stats.index_sectors / (w_ms * 1e-3),
                 "rank_ops_per_step": stats.rank_ops, "rank_ops_per_s": stats.rank_ops / (w_ms * 1e-3),

@@ -208,6 +208,16 @@ int64_t sbwt_gpu_launch_count(int reset);
 int sbwt_gpu_sector_probe(int device, int64_t buffer_bytes, int64_t n_loads, int bytes_per_load,
                           int iters, double *best_ms);
 
+/* Host half of the 32-bit result wire format (no device work): sbwt_gpu_query_host on an index with fewer
+ * than 2^31 columns lets the kernel write int32, copies those over PCIe and sign-extends them into the
+ * caller's int64 array with `threads` host threads (SBWT_B200_WIDEN_THREADS; default = hardware threads /
+ * visible GPUs, at most 16; below 4 the int64 values are copied directly). This entry runs that widening
+ * step alone: out[i] = in[i] for i < n. Values are what SBWT::search returns (SBWT.hh:390-415). */
+int sbwt_gpu_widen_i32(const int32_t *in, int64_t *out, int64_t n, int threads);
+/* Host threads this session's sbwt_gpu_query_host calls widen with: 0 = int64 values cross PCIe, -1 = not
+ * decided yet (decided by the first sbwt_gpu_query_host call). */
+int sbwt_gpu_session_widen_threads(const sbwt_gpu_session *s);
+
 #ifdef __cplusplus
 }
 #endif

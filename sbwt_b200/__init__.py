@@ -33,7 +33,7 @@ EXPORTS = [
     "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
     "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
     "sbwt_gpu_index_set_table_length", "sbwt_gpu_index_table_length",
-    "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text",
+    "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text", "sbwt_gpu_widen_i32", "sbwt_gpu_session_widen_threads",
 ]
 
 TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
@@ -94,6 +94,8 @@ def lib():
         L.sbwt_gpu_launch_count.argtypes = [i32]
         L.sbwt_gpu_launch_count.restype = i64
         L.sbwt_gpu_sector_probe.argtypes = [i32, i64, i64, i32, i32, C.POINTER(C.c_double)]
+        L.sbwt_gpu_widen_i32.argtypes = [vp, vp, i64, i32]
+        L.sbwt_gpu_session_widen_threads.argtypes = [vp]
         L.sbwt_gpu_text_capacity.argtypes = [vp, i64, i64]
         L.sbwt_gpu_text_capacity.restype = i64
         L.sbwt_gpu_format_device.argtypes = [vp, vp, i32, vp, i64, vp, i64, vp, vp]
@@ -250,6 +252,10 @@ class Session:
                                          out.ctypes.data))
         return out[:n_out]
 
+    def widen_threads(self) -> int:
+        """Host threads query_host widens int32 wire results with (0: int64 over PCIe, -1: undecided)."""
+        return lib().sbwt_gpu_session_widen_threads(self._h)
+
     def query_host_i32(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER,
                        out: np.ndarray | None = None) -> np.ndarray:
         """sbwt_gpu_query_host_i32: the same values as int32 (indexes with fewer than 2^31 columns)."""
@@ -314,6 +320,14 @@ class Session:
         _check(lib().sbwt_gpu_query_device_counted(self._h, d_ascii, d_offsets, n_reads, n_bases, mode, case_mode, d_out, n_out,
                                                    stream, C.byref(st)))
         return st
+
+
+def widen_i32(values: np.ndarray, threads: int = 4) -> np.ndarray:
+    """The host widening step of the 32-bit result wire format alone (no device work)."""
+    values = np.ascontiguousarray(values, dtype=np.int32)
+    out = np.empty(values.size, dtype=np.int64)
+    _check(lib().sbwt_gpu_widen_i32(values.ctypes.data, out.ctypes.data, values.size, threads))
+    return out
 
 
 def sector_probe(device: int, buffer_bytes: int, n_loads: int, bytes_per_load: int = 32, iters: int = 3) -> float:

@@ -15,6 +15,7 @@
 #include "aux_kernels.cuh"
 #include "device_index.cuh"
 #include "format_kernels.cuh"
+#include "host_widen.hpp"
 #include "sbwt_file.hpp"
 #include "walk_kernel.cuh"
 #include "walk2_kernel.cuh"
@@ -120,6 +121,16 @@ struct HostSlot {
     int64_t out_bytes = 0;
     void* out_dst = nullptr;
     bool out_staged = false;
+    // 32-bit wire format (host_widen.hpp): pinned int32 staging + the job a stream callback hands to the pool
+    int32_t* h_out32 = nullptr;
+    struct WidenJob {
+        WidenPool* pool = nullptr;
+        const int32_t* src = nullptr;
+        int64_t* dst = nullptr;
+        size_t n = 0;
+        WidenTicket* ticket = nullptr;
+    } widen_job;
+    WidenTicket widen_ticket;
 };
 
 struct sbwt_gpu_session {
@@ -130,7 +141,10 @@ struct sbwt_gpu_session {
     bool timing = false; // record events around the walk kernel of device-buffer batches
     cudaEvent_t ev_start = nullptr, ev_walk0 = nullptr, ev_walk1 = nullptr;
     bool host_ready = false;
-    HostSlot slots[2];
+    static constexpr int kSlots = 3; // H2D of chunk i+1, kernels + D2H of chunk i, host widening of chunk i-1
+    HostSlot slots[kSlots];
+    WidenPool* widen_pool = nullptr; // created by the first int64 host-buffer call on a narrow index
+    int widen_threads = -1;          // -1 = not decided yet, 0 = results travel as int64
     char* h_text[2] = {nullptr, nullptr}; // pinned staging the text leaves the device through, piece by piece
     cudaEvent_t text_ev[2] = {nullptr, nullptr};
 };
@@ -495,7 +509,7 @@ extern "C" void sbwt_gpu_session_destroy(sbwt_gpu_session* s) {
     for (HostSlot& h : s->slots) {
         scratch_free(h.sc);
         cudaFree(h.d_ascii); cudaFree(h.d_offsets); cudaFree(h.d_out); cudaFree(h.d_text);
-        cudaFreeHost(h.h_ascii); cudaFreeHost(h.h_offsets); cudaFreeHost(h.h_out); cudaFreeHost(h.h_totals);
+        cudaFreeHost(h.h_ascii); cudaFreeHost(h.h_offsets); cudaFreeHost(h.h_out); cudaFreeHost(h.h_totals); cudaFreeHost(h.h_out32);
         if (h.stream) cudaStreamDestroy(h.stream);
         if (h.done) cudaEventDestroy(h.done);
     }
@@ -503,6 +517,7 @@ extern "C" void sbwt_gpu_session_destroy(sbwt_gpu_session* s) {
         cudaFreeHost(s->h_text[b]);
         if (s->text_ev[b]) cudaEventDestroy(s->text_ev[b]);
     }
+    delete s->widen_pool;
     delete s;
 }
 
@@ -767,10 +782,31 @@ static int host_slots_init(sbwt_gpu_session* s) {
 
 static int slot_finish(HostSlot& h) {
     if (!h.busy) return 0;
-    CU(cudaEventSynchronize(h.done));
+    CU(cudaEventSynchronize(h.done)); // the widening job (if any) was submitted by a callback that precedes this event
+    if (h.widen_job.pool) {
+        h.widen_job.pool->wait(&h.widen_ticket);
+        h.widen_job.pool = nullptr;
+    }
     if (h.out_staged && h.out_bytes) memcpy(h.out_dst, h.h_out, (size_t)h.out_bytes);
     h.busy = false;
     return 0;
+}
+
+static void CUDART_CB widen_callback(void* p) { // stream callback: no CUDA calls in here
+    HostSlot::WidenJob* j = static_cast<HostSlot::WidenJob*>(p);
+    j->pool->submit(j->src, j->dst, j->n, j->ticket);
+}
+
+// How many host threads sign-extend int32 results into the caller's int64 array (0 = none: int64 values cross
+// PCIe). Default: the host's hardware threads divided by the visible GPUs (one process per GPU shares the host),
+// at most 16; fewer than 4 cannot keep up with a PCIe 5 x16 link, so the plain int64 copy is used instead.
+static int widen_thread_count() {
+    if (const char* e = getenv("SBWT_B200_WIDEN_THREADS")) return std::max(0, std::min(64, atoi(e)));
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int t = std::min(16, hw / ndev);
+    return t >= 4 ? t : 0;
 }
 
 static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
@@ -785,6 +821,13 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
     if (host_slots_init(s)) return 1;
     const bool pin_in = is_pinned(ascii), pin_off = is_pinned(off), pin_out = is_pinned(out);
     const int64_t k = ix->k;
+    // int64 results of a narrow index leave the device as int32 and are widened on the host (host_widen.hpp)
+    bool widen = false;
+    if (!out32 && !ix->view.wide && ix->n_nodes < (1ll << 31)) {
+        if (s->widen_threads < 0) s->widen_threads = widen_thread_count();
+        if (s->widen_threads > 0 && !s->widen_pool) s->widen_pool = new WidenPool(s->widen_threads);
+        widen = s->widen_pool != nullptr;
+    }
     int64_t r0 = 0, out_pos = 0;
     int turn = 0;
     while (r0 < n_reads) {
@@ -800,7 +843,7 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
         }
         const int64_t nr = r1 - r0;
         const int64_t n_out = sbwt_gpu_count_outputs(off + r0, nr, k);
-        HostSlot& h = s->slots[turn & 1];
+        HostSlot& h = s->slots[turn % sbwt_gpu_session::kSlots];
         turn++;
         if (slot_finish(h)) return 1;
         const char* src = ascii + off[r0];
@@ -817,7 +860,22 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
         }
         CU(cudaMemcpyAsync(h.d_ascii, src, (size_t)bases, cudaMemcpyHostToDevice, h.stream));
         CU(cudaMemcpyAsync(h.d_offsets, osrc, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, h.stream));
-        if (run_device_batch(s, h.sc, h.d_ascii, h.d_offsets, nr, bases, mode, case_mode, h.d_out, out32, false, h.stream)) return 1;
+        if (run_device_batch(s, h.sc, h.d_ascii, h.d_offsets, nr, bases, mode, case_mode, h.d_out, out32 || widen, false, h.stream)) return 1;
+        if (widen) {
+            if (!h.h_out32) CU(cudaMallocHost(&h.h_out32, std::max<int64_t>(s->max_bases, 1) * 4));
+            h.out_staged = false; h.out_bytes = 0;
+            if (n_out) {
+                CU(cudaMemcpyAsync(h.h_out32, h.d_out, (size_t)n_out * 4, cudaMemcpyDeviceToHost, h.stream));
+                h.widen_job.pool = s->widen_pool; h.widen_job.src = h.h_out32; h.widen_job.dst = (int64_t*)out + out_pos;
+                h.widen_job.n = (size_t)n_out; h.widen_job.ticket = &h.widen_ticket;
+                CU(cudaLaunchHostFunc(h.stream, widen_callback, &h.widen_job));
+            }
+            CU(cudaEventRecord(h.done, h.stream));
+            h.busy = true;
+            out_pos += n_out;
+            r0 = r1;
+            continue;
+        }
         const size_t esz = out32 ? 4 : 8;
         void* dst = (char*)out + (size_t)out_pos * esz;
         h.out_dst = dst; h.out_bytes = n_out * (int64_t)esz; h.out_staged = !pin_out;
@@ -846,6 +904,19 @@ extern "C" int sbwt_gpu_query_host_i32(sbwt_gpu_session* s, const char* ascii, c
         return set_error("int32 results need an index with fewer than 2^31 columns (this one has %lld)", (long long)s->idx->n_nodes);
     return query_host_impl(s, ascii, off, n_reads, mode, case_mode, out, true);
 }
+
+extern "C" int sbwt_gpu_widen_i32(const int32_t* in, int64_t* out, int64_t n, int threads) {
+    if (n < 0 || threads < 1 || threads > 64) return set_error("sbwt_gpu_widen_i32: n >= 0 and 1 <= threads <= 64 expected");
+    if (n == 0) return 0;
+    if (!in || !out) return set_error("null buffer");
+    WidenPool pool(threads);
+    WidenTicket t;
+    pool.submit(in, out, (size_t)n, &t);
+    pool.wait(&t);
+    return 0;
+}
+
+extern "C" int sbwt_gpu_session_widen_threads(const sbwt_gpu_session* s) { return s ? s->widen_threads : -1; }
 
 extern "C" int sbwt_gpu_search_batch(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int64_t* out) {
     return sbwt_gpu_query_host(s, ascii, off, n_reads, SBWT_GPU_MODE_SEARCH, SBWT_GPU_CASE_UPPER, out);

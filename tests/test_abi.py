@@ -71,3 +71,24 @@ def test_product_does_not_import_the_oracle():
                 if re.search(r"(import|from)\s+oracle\b|oracle/|liboracle|sbwt_oracle", txt):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_widen_i32_host_step():
+    """The host half of the 32-bit result wire format: sign extension of every value (incl. -1, the largest
+    column number below 2^31), odd sizes and unaligned destinations, any thread count."""
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 7, 8, 9, 65536, 65537, 1_000_003):
+        v = rng.integers(-1, 2**31 - 1, size=n, dtype=np.int64).astype(np.int32)
+        if n > 2:
+            v[0], v[-1] = -1, 2**31 - 1
+        for threads in (1, 3, 16):
+            assert np.array_equal(sbwt_b200.widen_i32(v, threads), v.astype(np.int64))
+    # destination not 32-byte aligned
+    v = rng.integers(-1, 2**31 - 1, size=100_001, dtype=np.int64).astype(np.int32)
+    buf = np.zeros(v.size + 3, dtype=np.int64)
+    for shift in (1, 2, 3):
+        out = buf[shift:shift + v.size]
+        assert sbwt_b200.lib().sbwt_gpu_widen_i32(v.ctypes.data, out.ctypes.data, v.size, 5) == 0
+        assert np.array_equal(out, v.astype(np.int64))
+    with pytest.raises(sbwt_b200.SbwtGpuError):
+        sbwt_b200.widen_i32(v, 0)

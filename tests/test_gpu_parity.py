@@ -427,3 +427,25 @@ def test_probe_strides_give_identical_results(stride, tmp_path, monkeypatch):
             monkeypatch.setenv("SBWT_B200_WINDOW", window)
         got = run_both(ix, reads, modes=(S.MODE_STREAMING,))[S.MODE_STREAMING]
         np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("threads", ["0", "1", "5"])
+def test_result_wire_formats_of_the_host_pipeline(threads, monkeypatch):
+    """sbwt_gpu_query_host returns int64 either copied as such (SBWT_B200_WIDEN_THREADS=0) or copied as int32 and
+    sign-extended by host threads (host_widen.hpp); same values, pinned or pageable buffers, many chunks in flight."""
+    monkeypatch.setenv("SBWT_B200_WIDEN_THREADS", threads)
+    for name in ("small_k31", "small_k63_rc"):
+        vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+        reads = read_fasta_reads(golden(name, "reads.fna"))
+        a, off = synth.ragged_to_batch(reads)
+        idx = S.Index(golden(name, "index.sbwt"))
+        ses = S.Session(idx, max_bases=3000, max_reads=11)  # dozens of chunks over the three pipeline slots
+        for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+            np.testing.assert_array_equal(ses.query_host(a, off, mode), vals)
+            out = S.pinned_empty(vals.size + 1, np.int64)
+            out[:] = -7
+            got = ses.query_host(a, off, mode, out=out[1:])  # destination off the 32-byte grid
+            np.testing.assert_array_equal(got, vals)
+            assert out[0] == -7
+        ses.close()
+        idx.close()
