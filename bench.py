@@ -179,7 +179,7 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
-    ap.add_argument("--e2e-chunk-bases", type=int, default=96_000_000)
+    ap.add_argument("--e2e-chunk-bases", type=int, default=48_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -319,7 +319,7 @@ def main() -> None:
                "d2h_bytes_per_step": int(n_out * 8), "ms_per_step": sec * 1e3, "steps": n_e2e,
                "api": "sbwt_gpu_query_host (pinned host buffers, int64 results: what SBWT::streaming_search returns)",
                "result_wire_format": ("int32 over PCIe, sign-extended into the caller's int64 array by host threads "
-                                      "(host_widen.hpp; SBWT_B200_WIDEN_THREADS, default = hardware threads / visible GPUs, <= 16)")
+                                      "(host_widen.hpp; SBWT_B200_WIDEN_THREADS, default = hardware threads / visible GPUs, <= 8)")
                if ses_h.widen_threads() > 0 else "int64 over PCIe",
                "widen_threads": ses_h.widen_threads(), "host_threads": os.cpu_count()}
         if ses_h.widen_threads() > 0:

@@ -26,7 +26,7 @@ EXPORTS = [
     "sbwt_gpu_index_create", "sbwt_gpu_index_load", "sbwt_gpu_index_destroy",
     "sbwt_gpu_index_k", "sbwt_gpu_index_n_nodes", "sbwt_gpu_index_n_kmers", "sbwt_gpu_index_precalc_k",
     "sbwt_gpu_index_has_streaming_support", "sbwt_gpu_index_device", "sbwt_gpu_index_C",
-    "sbwt_gpu_index_device_bytes", "sbwt_gpu_index_edges_only_at_group_starts", "sbwt_gpu_rank",
+    "sbwt_gpu_index_device_bytes", "sbwt_gpu_index_edges_only_at_group_starts", "sbwt_gpu_index_compact_layout", "sbwt_gpu_rank",
     "sbwt_gpu_session_create", "sbwt_gpu_session_destroy", "sbwt_gpu_count_outputs",
     "sbwt_gpu_query_host", "sbwt_gpu_query_host_i32", "sbwt_gpu_query_device", "sbwt_gpu_query_device_i32", "sbwt_gpu_search_batch", "sbwt_gpu_streaming_batch",
     "sbwt_gpu_host_alloc", "sbwt_gpu_host_free", "sbwt_gpu_pack_device",
@@ -67,6 +67,7 @@ def lib():
         for name in ("has_streaming_support", "device", "edges_only_at_group_starts"):
             f = getattr(L, "sbwt_gpu_index_" + name)
             f.argtypes, f.restype = [vp], i32
+        L.sbwt_gpu_index_compact_layout.argtypes = [vp, C.POINTER(C.c_double)]
         L.sbwt_gpu_index_C.argtypes = [vp, vp]
         L.sbwt_gpu_index_C.restype = None
         L.sbwt_gpu_rank.argtypes = [vp, vp, vp, i64, vp]
@@ -189,6 +190,13 @@ class Index:
     device = property(lambda s: lib().sbwt_gpu_index_device(s._h))
     device_bytes = property(lambda s: lib().sbwt_gpu_index_device_bytes(s._h))
     edges_only_at_group_starts = property(lambda s: bool(lib().sbwt_gpu_index_edges_only_at_group_starts(s._h)))
+
+    @property
+    def compact_layout(self) -> tuple[bool, float]:
+        """(the one-hot layout is in use, fraction of its blocks answered from the classic sectors; -1 = not built)"""
+        f = C.c_double(-1.0)
+        used = lib().sbwt_gpu_index_compact_layout(self._h, C.byref(f))
+        return bool(used), float(f.value)
 
     @property
     def C_array(self):

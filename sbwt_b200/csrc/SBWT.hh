@@ -263,6 +263,19 @@ public:
         return I;
     }
 
+    // SBWT.hh:369-381: follow the edge labelled c out of `node`; -1 if there is none (or c is not in ACGT).
+    int64_t forward(int64_t node, char c) const {
+        if (!has_streaming_query_support()) throw std::runtime_error("Error: Streaming support required for SBWT::forward");
+        while (!((suffix_group_starts[(size_t)node >> 6] >> (node & 63)) & 1)) node--; // the first node is always marked
+        const int idx = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+        const int64_t pos[2] = {node, node + 1};
+        const char ch[2] = {c, c};
+        int64_t rk[2];
+        gpu_check(sbwt_gpu_rank(dev, pos, ch, 2, rk));
+        if (rk[0] == rk[1]) return -1; // no edge (also every c outside ACGT: its rank is 0 everywhere)
+        return C[idx] + rk[0];
+    }
+
     // SBWT.hh:526-542: longest prefix of input that is found; returns ({l,r}, length matched).
     std::pair<std::pair<int64_t, int64_t>, int64_t> partial_search(const std::string& input) const { return partial_search(input.c_str(), (int64_t)input.size()); }
     std::pair<std::pair<int64_t, int64_t>, int64_t> partial_search(const char* input, int64_t len) const {

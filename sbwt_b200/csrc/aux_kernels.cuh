@@ -266,6 +266,55 @@ __global__ void __launch_bounds__(256) k0_emit_kernel(const uint32_t* __restrict
     sectors[t] = s;
 }
 
+// ones of vector c in [0, pos), from the raw planes and the per-block exclusive prefix
+__device__ __forceinline__ int64_t k0_raw_rank(const uint32_t* __restrict__ raw, int64_t words_per_vec, int64_t n_blocks,
+                                               const int64_t* __restrict__ prefix, int c, int64_t pos) {
+    const int64_t b = pos / kBlockCols;
+    const uint32_t off = (uint32_t)(pos - b * kBlockCols);
+    const uint32_t* w = raw + (int64_t)c * words_per_vec + b * kPayloadWords;
+    int64_t r = prefix[(int64_t)c * n_blocks + b];
+    for (uint32_t i = 0; i < (off >> 5); i++) r += __popc(w[i]);
+    if (off & 31u) r += __popc(w[off >> 5] & ((1u << (off & 31u)) - 1u));
+    return r;
+}
+
+// the compact (one-hot) layout of device_index.cuh: one thread per 96-column block; n_flagged counts the blocks that
+// have a column with no edge or several (columns >= n_nodes are padding and never queried)
+__global__ void __launch_bounds__(256) k0_compact_kernel(const uint32_t* __restrict__ raw, int64_t words_per_vec, int64_t n_blocks,
+                                                         const int64_t* __restrict__ prefix, int64_t C0, int64_t C1, int64_t C2,
+                                                         int64_t C3, int64_t n_nodes, int64_t n_cblocks,
+                                                         Sector* __restrict__ compact, uint32_t* __restrict__ cbase,
+                                                         unsigned long long* __restrict__ n_flagged) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_cblocks) return;
+    const int64_t col0 = b * kCBlockCols, sb = b >> kCSbShift, sbcol = (sb << kCSbShift) * kCBlockCols;
+    const int64_t Cc[4] = {C0, C1, C2, C3};
+    uint32_t rel[4];
+    for (int c = 0; c < 4; c++) {
+        const int64_t at_sb = k0_raw_rank(raw, words_per_vec, n_blocks, prefix, c, sbcol);
+        rel[c] = (uint32_t)(k0_raw_rank(raw, words_per_vec, n_blocks, prefix, c, col0) - at_sb);
+        if ((b & ((1ll << kCSbShift) - 1)) == 0) cbase[sb * 4 + c] = (uint32_t)(Cc[c] + at_sb);
+    }
+    Sector s;
+    uint32_t exc = 0;
+    for (int i = 0; i < 3; i++) {
+        const int64_t wi = 3 * b + i; // 96 = 3 x 32: a block is three whole words of every plane
+        uint32_t a = 0, cc = 0, g = 0, t = 0;
+        if (wi < words_per_vec) { a = raw[wi]; cc = raw[words_per_vec + wi]; g = raw[2 * words_per_vec + wi]; t = raw[3 * words_per_vec + wi]; }
+        const uint32_t two = (a & cc) | (a & g) | (a & t) | (cc & g) | (cc & t) | (g & t);
+        const uint32_t one = (a ^ cc ^ g ^ t) & ~two;
+        const int64_t first = col0 + 32 * i;
+        const uint32_t valid = first >= n_nodes ? 0u : (n_nodes - first >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)(n_nodes - first)) - 1u));
+        exc |= ~one & valid;
+        s.w[2 + i] = cc | t;
+        s.w[5 + i] = g | t;
+    }
+    s.w[0] = rel[0] | (rel[1] << 16) | (exc ? 0x8000u : 0u);
+    s.w[1] = rel[2] | (rel[3] << 16);
+    compact[b] = s;
+    if (exc) atomicAdd(n_flagged, 1ull);
+}
+
 // flag |= 1 if some column that is not a suffix-group start has a non-empty subset
 __global__ void __launch_bounds__(256) k0_check_edges_kernel(const uint32_t* __restrict__ raw, int64_t words_per_vec,
                                                              const uint32_t* __restrict__ sgs, int64_t n_words,

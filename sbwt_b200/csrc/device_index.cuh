@@ -50,7 +50,54 @@ struct DeviceIndexView {
     int sb_shift;
     int wide;                  // 1 if n_nodes >= 2^32 (or forced for tests)
     int edges_at_starts;       // structural invariant (i) of SURVEY.md section 8(a) note 7 holds
+    // compact (one-hot) layout, see below; nullptr when the index is not eligible
+    const Sector* compact;     // [n_cblocks]
+    const uint32_t* cbase;     // [n_csb][4]: C[c] + rank_c(first column of the superblock)
+    int64_t n_cblocks;
 };
+
+// ------------------------------------------------------------------ compact (one-hot) layout
+//
+// In an SBWT of low-repeat sequence almost every column carries exactly ONE outgoing edge (config 2/3 of
+// BASELINE.json: 99.999 % of the columns; E. coli: 99.4 %), so the four bit vectors are one-hot per column and
+// two bits per column say everything. For such indexes a second array is kept next to the sectors above,
+//
+//   csector(block b) = { 4 x u16 rel_c ; 96 bits lo ; 96 bits hi }                32 bytes, ALL FOUR characters
+//     (hi, lo)[j] = the character of the one edge of column 96 b + j  (A=00 C=01 G=10 T=11)
+//     rel_c       = rank_c(96 b) - rank_c(first column of b's superblock)  (< 2^15; superblock = 256 blocks)
+//     bit 15 of rel_A = FLAG: some column of the block has no edge or more than one -> the block is answered from
+//                       the classic sectors instead (rare by the eligibility test at load)
+//   C[c] + rank_c(pos) = cbase[superblock][c] + rel_c + #{ j < pos % 96 : (hi, lo)[j] == c }
+//
+// 0.333 B per column instead of 0.571: a 100 M-column index is 33 MB and stays L2-resident next to the read and
+// result streams (the measured capacity for randomly read data on this chip is ~62 MB: profiles/r01g_l2_capacity.txt),
+// and a rank is 2 LOP3 + 1 POPC per 32 columns over 3 words instead of 7.
+constexpr int kCBlockCols = 96;
+constexpr int kCSbShift = 8; // 256 blocks = 24576 columns per superblock
+
+struct CompactRank {
+    uint32_t value; // C[c] + rank_c(pos)
+    uint32_t bit;   // bit_c(pos): does column pos have an edge labelled c
+};
+
+__device__ __forceinline__ bool csector_flagged(const Sector& s) { return (s.w[0] & 0x8000u) != 0; }
+
+// s = csector of pos's block, off = pos % 96, base = cbase[(pos / 96) >> kCSbShift][c]
+__device__ __forceinline__ CompactRank compact_rank(const Sector& s, uint32_t base, uint32_t off, int c) {
+    const uint32_t cw = (c & 2) ? s.w[1] : s.w[0];
+    const uint32_t rel = ((c & 1) ? (cw >> 16) : cw) & 0x7FFFu;
+    const uint32_t X = (c & 1) ? 0u : 0xFFFFFFFFu, Y = (c & 2) ? 0u : 0xFFFFFFFFu;
+    const uint32_t m0 = (s.w[2] ^ X) & (s.w[5] ^ Y), m1 = (s.w[3] ^ X) & (s.w[6] ^ Y), m2 = (s.w[4] ^ X) & (s.w[7] ^ Y);
+    const uint32_t f = off >> 5, rem = off & 31u;
+    const uint32_t mf = f == 0 ? m0 : (f == 1 ? m1 : m2);
+    uint32_t cnt = __popc(mf & ((1u << rem) - 1u));
+    if (f > 0) cnt += __popc(m0);
+    if (f > 1) cnt += __popc(m1);
+    CompactRank r;
+    r.value = base + rel + cnt;
+    r.bit = (mf >> rem) & 1u;
+    return r;
+}
 
 // 256-bit read-only load of one sector, not allocated in L1 (random access, no reuse there).
 __device__ __forceinline__ Sector ld_sector(const Sector* p) {

@@ -51,6 +51,9 @@ static void apply_l2_fetch_granularity() {
     const char* e = getenv("SBWT_B200_L2_FETCH");
     if (!e) return;
     const int g = atoi(e);
+    static thread_local int applied = 0;
+    if (g == applied) return;
+    applied = g;
     if (g == 32 || g == 64 || g == 128) {
         cudaError_t rc = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
         size_t got = 0;
@@ -82,6 +85,9 @@ struct sbwt_gpu_index {
     int64_t device_bytes = 0;
     DeviceIndexView view{};
     void* d_sectors = nullptr;
+    void* d_compact = nullptr; // one-hot layout (device_index.cuh), nullptr if the index is not eligible
+    void* d_cbase = nullptr;
+    double flagged_fraction = -1.0; // blocks of the compact layout that fall back to the classic sectors (-1: not built)
     void* d_sbbase = nullptr;
     void* d_precalc = nullptr;
     void* d_table = nullptr;
@@ -129,7 +135,9 @@ struct HostSlot {
         int64_t* dst = nullptr;
         size_t n = 0;
         WidenTicket* ticket = nullptr;
-    } widen_job;
+    };
+    std::vector<WidenJob> widen_jobs; // one per D2H piece of the slot's batch; stable until slot_finish
+    WidenPool* widen_pool = nullptr;  // non-null while widening jobs of this slot may be outstanding
     WidenTicket widen_ticket;
 };
 
@@ -272,6 +280,33 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
                                                          sb_shift, n_sb, (Sector*)ix->d_sectors, (int64_t*)ix->d_sbbase); LAUNCHED();
     CUI(cudaGetLastError());
 
+    // one-hot layout: narrow indexes in which (nearly) every column has exactly one outgoing edge.
+    // SBWT_B200_COMPACT = 0 never, 1 (default) when at most 5 % of its blocks need the classic sectors, 2 always (tests)
+    int compact_mode = 1;
+    if (const char* e = getenv("SBWT_B200_COMPACT")) compact_mode = atoi(e);
+    const int64_t n_cblocks = n_nodes / kCBlockCols + 1;
+    if (!wide && compact_mode > 0) {
+        const int64_t n_csb = ((n_cblocks - 1) >> kCSbShift) + 1;
+        unsigned long long* d_nflag = nullptr;
+        CUI(cudaMalloc(&ix->d_compact, (size_t)n_cblocks * sizeof(Sector)));
+        CUI(cudaMalloc(&ix->d_cbase, (size_t)n_csb * 16));
+        CUI(cudaMalloc(&d_nflag, 8));
+        CUI(cudaMemset(d_nflag, 0, 8));
+        k0_compact_kernel<<<grid_for(n_cblocks, 256), 256>>>(d_raw, words_per_vec, n_blocks, d_counts, C[0], C[1], C[2], C[3], n_nodes,
+                                                             n_cblocks, (Sector*)ix->d_compact, (uint32_t*)ix->d_cbase, d_nflag); LAUNCHED();
+        unsigned long long n_flagged = 0;
+        cudaError_t e1 = cudaMemcpy(&n_flagged, d_nflag, 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_nflag);
+        CUI(e1);
+        ix->flagged_fraction = (double)n_flagged / (double)n_cblocks;
+        if (compact_mode == 1 && ix->flagged_fraction > 0.05) {
+            cudaFree(ix->d_compact); cudaFree(ix->d_cbase);
+            ix->d_compact = ix->d_cbase = nullptr;
+        } else {
+            ix->device_bytes += n_cblocks * (int64_t)sizeof(Sector) + n_csb * 16;
+        }
+    }
+
     int edges_at_starts = 0;
     if (sgs) {
         const int64_t sgs_words = words_per_vec + 8;
@@ -289,6 +324,7 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     v.sgs = (const uint32_t*)ix->d_sgs;
     v.n_nodes = n_nodes; v.n_blocks = n_blocks; v.n_sb = n_sb;
     v.k = (int)k; v.p = (int)p; v.sb_shift = sb_shift; v.wide = wide; v.edges_at_starts = edges_at_starts;
+    v.compact = (const Sector*)ix->d_compact; v.cbase = (const uint32_t*)ix->d_cbase; v.n_cblocks = n_cblocks;
     if (p > 0) {
         const size_t bytes = (size_t)16 << (2 * p);
         const int64_t np = 1ll << (2 * p);
@@ -397,6 +433,7 @@ extern "C" void sbwt_gpu_index_destroy(sbwt_gpu_index* ix) {
     if (!ix) return;
     DeviceGuard guard(ix->device);
     cudaFree(ix->d_sectors); cudaFree(ix->d_sbbase); cudaFree(ix->d_precalc); cudaFree(ix->d_sgs); cudaFree(ix->d_table);
+    cudaFree(ix->d_compact); cudaFree(ix->d_cbase);
     delete ix;
 }
 
@@ -408,6 +445,10 @@ extern "C" int sbwt_gpu_index_has_streaming_support(const sbwt_gpu_index* ix) { 
 extern "C" int sbwt_gpu_index_device(const sbwt_gpu_index* ix) { return ix->device; }
 extern "C" void sbwt_gpu_index_C(const sbwt_gpu_index* ix, int64_t C[4]) { for (int c = 0; c < 4; c++) C[c] = ix->C[c]; }
 extern "C" int64_t sbwt_gpu_index_device_bytes(const sbwt_gpu_index* ix) { return ix->device_bytes; }
+extern "C" int sbwt_gpu_index_compact_layout(const sbwt_gpu_index* ix, double* flagged_fraction) {
+    if (flagged_fraction) *flagged_fraction = ix->flagged_fraction;
+    return ix->d_compact ? 1 : 0;
+}
 extern "C" int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index* ix) { return ix->view.edges_at_starts; }
 
 extern "C" int sbwt_gpu_index_get_precalc(const sbwt_gpu_index* ix, int64_t* out_lr) {
@@ -577,24 +618,26 @@ static cudaError_t launch_walk_t(const WalkParams& P, bool count, int sm_count, 
                  : launch_walk_tt<STREAMING, WIDE, false, false>(P, sm_count, blocks_per_sm, st);
 }
 
-template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL>
+template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL, bool COMPACT>
 static cudaError_t launch_walk2_ttt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
     static int occ = 0;
     if (occ == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk2_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL>, kW2Threads, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk2_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, COMPACT>, kW2Threads, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
     }
     const unsigned grid = (unsigned)(sm_count * (blocks_per_sm > 0 ? blocks_per_sm : occ));
-    walk2_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL><<<grid, kW2Threads, 0, st>>>(P);
+    walk2_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, COMPACT><<<grid, kW2Threads, 0, st>>>(P);
     return cudaGetLastError();
 }
 
 template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW>
 static cudaError_t launch_walk2_tt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
     if (STREAMING && !P.ix.edges_at_starts) // the reference's control flow to the letter (hand-made index files)
-        return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, STREAMING>(P, sm_count, blocks_per_sm, st);
-    return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false>(P, sm_count, blocks_per_sm, st);
+        return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, STREAMING, false>(P, sm_count, blocks_per_sm, st);
+    if (!WIDE && P.ix.compact) // one-hot layout (device_index.cuh)
+        return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false, !WIDE>(P, sm_count, blocks_per_sm, st);
+    return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false, false>(P, sm_count, blocks_per_sm, st);
 }
 
 template <bool STREAMING, bool WIDE, int KW>
@@ -617,6 +660,7 @@ static int walk_generation() { // SBWT_B200_WALK=1 selects the lane-state-machin
 static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, bool count, cudaStream_t st) {
     int blocks_per_sm = 0;
     if (const char* e = getenv("SBWT_B200_BLOCKS_PER_SM")) blocks_per_sm = std::max(0, atoi(e));
+    apply_l2_fetch_granularity();
     const char* el = getenv("SBWT_B200_L2_EVICT_LAST");
     P.index_evict_last = el ? atoi(el) : 1;
     const char* fr = getenv("SBWT_B200_L2_FRAC");
@@ -783,9 +827,9 @@ static int host_slots_init(sbwt_gpu_session* s) {
 static int slot_finish(HostSlot& h) {
     if (!h.busy) return 0;
     CU(cudaEventSynchronize(h.done)); // the widening job (if any) was submitted by a callback that precedes this event
-    if (h.widen_job.pool) {
-        h.widen_job.pool->wait(&h.widen_ticket);
-        h.widen_job.pool = nullptr;
+    if (h.widen_pool) {
+        h.widen_pool->wait(&h.widen_ticket);
+        h.widen_pool = nullptr;
     }
     if (h.out_staged && h.out_bytes) memcpy(h.out_dst, h.h_out, (size_t)h.out_bytes);
     h.busy = false;
@@ -799,14 +843,25 @@ static void CUDART_CB widen_callback(void* p) { // stream callback: no CUDA call
 
 // How many host threads sign-extend int32 results into the caller's int64 array (0 = none: int64 values cross
 // PCIe). Default: the host's hardware threads divided by the visible GPUs (one process per GPU shares the host),
-// at most 16; fewer than 4 cannot keep up with a PCIe 5 x16 link, so the plain int64 copy is used instead.
+// at most 8; fewer than 4 cannot keep up with a PCIe 5 x16 link, so the plain int64 copy is used instead.
 static int widen_thread_count() {
     if (const char* e = getenv("SBWT_B200_WIDEN_THREADS")) return std::max(0, std::min(64, atoi(e)));
     int ndev = 1;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
     const int hw = (int)std::thread::hardware_concurrency();
-    const int t = std::min(16, hw / ndev);
+    const int t = std::min(8, hw / ndev); // 8 threads saturate the host's memory system (profiles/r01g_e2e_sweep.txt)
     return t >= 4 ? t : 0;
+}
+
+// values per D2H piece of the 32-bit wire format (SBWT_B200_D2H_PIECE, in values). Default 64 Mi: a chunk of the
+// default size goes in one piece -- smaller pieces only added per-piece overhead on the measured host
+// (profiles/r01g_e2e_sweep.txt)
+static int64_t d2h_piece_values() {
+    if (const char* e = getenv("SBWT_B200_D2H_PIECE")) {
+        const long long v = atoll(e);
+        if (v >= 4096) return (int64_t)v;
+    }
+    return (int64_t)64 << 20;
 }
 
 static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
@@ -865,10 +920,21 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
             if (!h.h_out32) CU(cudaMallocHost(&h.h_out32, std::max<int64_t>(s->max_bases, 1) * 4));
             h.out_staged = false; h.out_bytes = 0;
             if (n_out) {
-                CU(cudaMemcpyAsync(h.h_out32, h.d_out, (size_t)n_out * 4, cudaMemcpyDeviceToHost, h.stream));
-                h.widen_job.pool = s->widen_pool; h.widen_job.src = h.h_out32; h.widen_job.dst = (int64_t*)out + out_pos;
-                h.widen_job.n = (size_t)n_out; h.widen_job.ticket = &h.widen_ticket;
-                CU(cudaLaunchHostFunc(h.stream, widen_callback, &h.widen_job));
+                // the result copy goes piece by piece, each piece handed to the pool as soon as it has landed: the
+                // widening of piece i overlaps the DMA of piece i + 1 and reads it while it is still cache-warm
+                const int64_t piece = d2h_piece_values();
+                const size_t n_pieces = (size_t)((n_out + piece - 1) / piece);
+                h.widen_jobs.assign(n_pieces, HostSlot::WidenJob());
+                h.widen_pool = s->widen_pool;
+                const int32_t* d32 = reinterpret_cast<const int32_t*>(h.d_out);
+                for (size_t pi = 0; pi < n_pieces; pi++) {
+                    const int64_t p0 = (int64_t)pi * piece, pn = std::min(piece, n_out - p0);
+                    CU(cudaMemcpyAsync(h.h_out32 + p0, d32 + p0, (size_t)pn * 4, cudaMemcpyDeviceToHost, h.stream));
+                    HostSlot::WidenJob& j = h.widen_jobs[pi];
+                    j.pool = s->widen_pool; j.src = h.h_out32 + p0; j.dst = (int64_t*)out + out_pos + p0;
+                    j.n = (size_t)pn; j.ticket = &h.widen_ticket;
+                    CU(cudaLaunchHostFunc(h.stream, widen_callback, &j));
+                }
             }
             CU(cudaEventRecord(h.done, h.stream));
             h.busy = true;

@@ -155,9 +155,13 @@ struct OutStage {
 // hand-made file): streaming answers may then differ from search() answers, so the reference's
 // control flow is followed to the letter -- after a miss the k-mers are searched one at a time and
 // streaming resumes from the first one found (SBWT.hh:556-576); invalid bases are met by the chain.
-template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL>
+// COMPACT: rank steps are answered from the one-hot layout (device_index.cuh: one 32-byte csector holds all four
+// characters of 96 columns); a block flagged there (some column with no edge or several) is answered from the classic
+// sectors on a rare divergent path. Narrow, non-LITERAL kernels only; the host picks it when the index is eligible.
+template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL, bool COMPACT>
 __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS) walk2_kernel(const WalkParams P) {
     static_assert(STREAMING || !LITERAL, "LITERAL is a streaming-mode variant");
+    static_assert(!COMPACT || (!WIDE && !LITERAL), "the compact layout serves narrow indexes that keep the edge invariant");
     typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
     __shared__ W2Queues<WIDE> queues[kW2Warps];
     W2Queues<WIDE>& Q = queues[threadIdx.x >> 5];
@@ -178,6 +182,9 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
     const uint64_t pol_t = pol; // table rows
     if (P.index_evict_last == 2) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(P.l2_frac));
     if (P.index_evict_last == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(pol) : "f"(P.l2_frac));
+    const Sector* const cmp_base = ix.compact;
+    const uint32_t* const cbase = ix.cbase;
+    const uint64_t pol_cl = COMPACT ? make_l2_policy(false) : pol; // classic sectors are the cold structure of a compact index
     const pos_t last_col = (pos_t)(ix.n_nodes - 1);
     constexpr uint32_t kGrab = STREAMING ? 32u : 8u; // items (streaming) or chunks (search) per cursor bump
 
@@ -295,14 +302,30 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                 bool miss = false;
                 if (act) {
                     const int c = (int)((cw >> ((pos & 15u) * 2u)) & 3u);
-                    const BlockPos bp = split_pos<WIDE>((int64_t)col);
-                    const Sector s = ld_sector(sector_ptr<WIDE>(sec_base, bp.blk, c), pol);
-                    const SectorPrefix pf = sector_prefix(s);
-                    const uint32_t f = bp.off >> 5, rm = bp.off & 31u;
-                    const uint32_t w = sector_word(s, f);
-                    pos_t ncol = (pos_t)(s.w[0] + __byte_perm(pf.X, pf.Y, f) + __popc(w & ((1u << rm) - 1u)));
-                    if (WIDE) ncol += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (bp.blk >> ix.sb_shift));
-                    miss = ((w >> rm) & 1u) == 0; // [col, col] -> empty interval (SBWT.hh:433) / l != r (SBWT.hh:574)
+                    pos_t ncol = 0;
+                    int64_t cblk = -1; // classic block of col, when it was read
+                    bool classic = true;
+                    if (COMPACT) {
+                        const uint32_t cb = (uint32_t)col / (uint32_t)kCBlockCols, coff = (uint32_t)col - cb * (uint32_t)kCBlockCols;
+                        const Sector s = ld_sector(cmp_base + cb, pol);
+                        if (!csector_flagged(s)) {
+                            const CompactRank cr = compact_rank(s, __ldg(cbase + ((cb >> kCSbShift) << 2) + c), coff, c);
+                            ncol = (pos_t)cr.value;
+                            miss = cr.bit == 0;
+                            classic = false;
+                        }
+                    }
+                    if (classic) {
+                        const BlockPos bp = split_pos<WIDE>((int64_t)col);
+                        cblk = bp.blk;
+                        const Sector s = ld_sector(sector_ptr<WIDE>(sec_base, bp.blk, c), pol_cl);
+                        const SectorPrefix pf = sector_prefix(s);
+                        const uint32_t f = bp.off >> 5, rm = bp.off & 31u;
+                        const uint32_t w = sector_word(s, f);
+                        ncol = (pos_t)(s.w[0] + __byte_perm(pf.X, pf.Y, f) + __popc(w & ((1u << rm) - 1u)));
+                        if (WIDE) ncol += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (bp.blk >> ix.sb_shift));
+                        miss = ((w >> rm) & 1u) == 0; // [col, col] -> empty interval (SBWT.hh:433) / l != r (SBWT.hh:574)
+                    }
                     if (COUNT) { st_ranks += 2; st_sectors += 1; }
                     bool bad = false; // LITERAL: the chain can run into a base outside ACGT (SBWT.hh:565-568)
                     if (LITERAL && fs) bad = ((__ldg(P.invalid + (pos >> 5)) >> (pos & 31u)) & 1u) != 0;
@@ -317,8 +340,8 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                         if (COUNT) st_sectors++;
                         if (g != (int64_t)col) {
                             const BlockPos bs = split_pos<WIDE>(g);
-                            const Sector ss = ld_sector(sector_ptr<WIDE>(sec_base, bs.blk, c), pol);
-                            if (COUNT) st_sectors += bs.blk != bp.blk;
+                            const Sector ss = ld_sector(sector_ptr<WIDE>(sec_base, bs.blk, c), pol_cl);
+                            if (COUNT) st_sectors += bs.blk != cblk;
                             miss = sector_bit(ss, bs.off) == 0;
                             ncol = (pos_t)lf_value<WIDE>(ix, ss, bs.blk, bs.off, c);
                         }
@@ -472,23 +495,41 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
             if (!__any_sync(FULL, go)) break;
             if (go) {
                 const int c = (int)win_char<KW>(win, jl);
-                const BlockPos b0 = split_pos<WIDE>((int64_t)l), b1 = split_pos<WIDE>((int64_t)r + 1);
-                const bool two = b1.blk != b0.blk;
-                const Sector s0 = ld_sector(sector_ptr<WIDE>(sec_base, b0.blk, c), pol);
-                Sector s1;
-                if (two) s1 = ld_sector(sector_ptr<WIDE>(sec_base, b1.blk, c), pol);
-                const SectorPrefix pf0 = sector_prefix(s0);
-                pos_t nl = (pos_t)sector_rank_fast(s0, pf0, b0.off);
-                pos_t nr;
-                if (two) {
-                    const SectorPrefix pf1 = sector_prefix(s1);
-                    nr = (pos_t)sector_rank_fast(s1, pf1, b1.off);
-                } else {
-                    nr = (pos_t)sector_rank_fast(s0, pf0, b1.off);
+                pos_t nl = 0, nr = 0;
+                bool two = false, classic = true;
+                if (COMPACT) {
+                    const uint32_t p0 = (uint32_t)l, p1 = (uint32_t)r + 1u;
+                    const uint32_t cb0 = p0 / (uint32_t)kCBlockCols, cb1 = p1 / (uint32_t)kCBlockCols;
+                    two = cb1 != cb0;
+                    const Sector s0 = ld_sector(cmp_base + cb0, pol);
+                    Sector s1 = s0;
+                    if (two) s1 = ld_sector(cmp_base + cb1, pol);
+                    if (!csector_flagged(s0) && !csector_flagged(s1)) {
+                        const uint32_t base0 = __ldg(cbase + ((cb0 >> kCSbShift) << 2) + c);
+                        const uint32_t base1 = __ldg(cbase + ((cb1 >> kCSbShift) << 2) + c);
+                        nl = (pos_t)compact_rank(s0, base0, p0 - cb0 * (uint32_t)kCBlockCols, c).value;
+                        nr = (pos_t)compact_rank(s1, base1, p1 - cb1 * (uint32_t)kCBlockCols, c).value;
+                        classic = false;
+                    }
                 }
-                if (WIDE) {
-                    nl += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b0.blk >> ix.sb_shift));
-                    nr += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b1.blk >> ix.sb_shift));
+                if (classic) {
+                    const BlockPos b0 = split_pos<WIDE>((int64_t)l), b1 = split_pos<WIDE>((int64_t)r + 1);
+                    two = b1.blk != b0.blk;
+                    const Sector s0 = ld_sector(sector_ptr<WIDE>(sec_base, b0.blk, c), pol_cl);
+                    Sector s1;
+                    if (two) s1 = ld_sector(sector_ptr<WIDE>(sec_base, b1.blk, c), pol_cl);
+                    const SectorPrefix pf0 = sector_prefix(s0);
+                    nl = (pos_t)sector_rank_fast(s0, pf0, b0.off);
+                    if (two) {
+                        const SectorPrefix pf1 = sector_prefix(s1);
+                        nr = (pos_t)sector_rank_fast(s1, pf1, b1.off);
+                    } else {
+                        nr = (pos_t)sector_rank_fast(s0, pf0, b1.off);
+                    }
+                    if (WIDE) {
+                        nl += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b0.blk >> ix.sb_shift));
+                        nr += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b1.blk >> ix.sb_shift));
+                    }
                 }
                 nr -= 1;
                 if (COUNT) { st_ranks += 2; st_sectors += two ? 2 : 1; }

@@ -36,6 +36,13 @@ int main(int argc, char** argv) {
         std::cout << "interval " << I.first << " " << I.second << "\n";
         auto P = idx.partial_search(read);
         std::cout << "partial " << P.first.first << " " << P.first.second << " " << P.second << "\n";
+        // forward (SBWT.hh:369-381) along the read reproduces the streaming answers: ans[i+1] == forward(ans[i], read[i+k])
+        {
+            const std::vector<int64_t> ans = idx.streaming_search(read);
+            std::cout << "forward";
+            for (size_t i = 0; i + 1 < ans.size() && i < 40; i++) std::cout << " " << (ans[i] >= 0 ? idx.forward(ans[i], read[i + k]) : -2);
+            std::cout << " " << idx.forward(ans[0], 'N') << "\n";
+        }
         std::cout << "rank " << idx.get_subset_rank_structure().rank(idx.number_of_subsets(), 'A') << " "
                   << idx.get_subset_rank_structure().rank(idx.number_of_subsets() / 2, 'G') << " "
                   << idx.get_subset_rank_structure().rank(5, 'N') << "\n";

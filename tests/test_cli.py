@@ -148,6 +148,8 @@ def test_cpp_mirror_surface(tmp_path):
     assert lines["interval"].split() == [str(want[0]), str(want[0])] and want[0] >= 0
     pl, pr, plen = (int(x) for x in lines["partial"].split())
     assert plen == 100 and pl <= pr  # the walk from the full interval stops at the N
+    fw = [int(x) for x in lines["forward"].split()]
+    assert fw[-1] == -1 and fw[:-1] == [int(want[i + 1]) if want[i] >= 0 else -2 for i in range(len(fw) - 1)]
     assert [int(x) for x in lines["rank"].split()] == [orc.rank(orc.n_nodes, "A"), orc.rank(orc.n_nodes // 2, "G"), 0]
     assert lines["rebuilt_same_C"] == "1" and lines["rebuilt_same_precalc"] == "1"
     assert "incompatible version of SBWT" in lines["version_error"]

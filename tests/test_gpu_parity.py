@@ -449,3 +449,69 @@ def test_result_wire_formats_of_the_host_pipeline(threads, monkeypatch):
             assert out[0] == -7
         ses.close()
         idx.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_compact_one_hot_layout_gives_identical_results(mode, tmp_path, monkeypatch):
+    """The compact layout (two bits per column, device_index.cuh) is a pure representation choice: off (0), automatic
+    (1) and forced (2, every index, so that indexes with many flagged blocks such as config 1 mix csector answers and
+    classic-sector fallbacks inside one warp) must all reproduce the reference's output; int32 results and the
+    counted instantiation included."""
+    monkeypatch.setenv("SBWT_B200_COMPACT", mode)
+    for name in ("small_k31", "small_k63_rc", "cli_k6", "small_k8_p0"):
+        expected = open(golden(name, "known_answer.txt" if name == "cli_k6" else "expected.txt"), "rb").read()
+        reads = read_fasta_reads(golden(name, "queries.fna" if name == "cli_k6" else "reads.fna"))
+        vals, _ = parse_expected(expected)
+        res = run_both(golden(name, "index.sbwt"), reads)
+        np.testing.assert_array_equal(res[S.MODE_STREAMING], vals)
+        np.testing.assert_array_equal(res[S.MODE_SEARCH], vals)
+    idx = S.Index(golden("small_k31", "index.sbwt"))
+    used, flagged = idx.compact_layout
+    assert used == (mode != "0") and (flagged < 0 if mode == "0" else 0 <= flagged < 0.05)
+    idx.close()
+    idx = S.Index(golden("c1", "index.sbwt"))
+    used, flagged = idx.compact_layout
+    assert used == (mode == "2") and (mode == "0" or 0.2 < flagged < 0.6)  # 39 % of coli3's blocks hold a branching or dead-end column
+    reads = c1_reads()
+    a, off = synth.ragged_to_batch(reads)
+    vals, _ = parse_expected(c1_expected())
+    ses = S.Session(idx, a.size, len(reads))
+    for m in (S.MODE_STREAMING, S.MODE_SEARCH):
+        np.testing.assert_array_equal(ses.query_host(a, off, m), vals)
+        np.testing.assert_array_equal(ses.query_host_i32(a, off, m).astype(np.int64), vals)
+    import torch
+    d_a, d_off = torch.from_numpy(a).cuda(), torch.from_numpy(off).cuda()
+    d_out = torch.empty(vals.size, dtype=torch.int64, device="cuda")
+    st = ses.query_device_counted(d_a.data_ptr(), d_off.data_ptr(), len(reads), a.size, S.MODE_STREAMING, d_out.data_ptr(), vals.size)
+    np.testing.assert_array_equal(d_out.cpu().numpy(), vals)
+    assert st.lookups == vals.size and st.hits == int((vals >= 0).sum())
+    ses.close()
+    idx.close()
+    # long reads with planted stretches, substitutions and Ns on a +RC index (restarts, walk-backs, TODO ranges)
+    ref = synth.random_contigs(2, 50_000, seed=7)
+    fa = str(tmp_path / "r.fna")
+    synth.write_fasta(fa, [ref[i] for i in range(2)])
+    ix = str(tmp_path / "i.sbwt")
+    build_index(fa, ix, k=31, precalc=8, add_rc=True)
+    rng = np.random.default_rng(12)
+    reads = []
+    for i in range(60):
+        parts = []
+        for _ in range(int(rng.integers(1, 10))):
+            L = int(rng.integers(1, 900))
+            if rng.random() < 0.6:
+                o = int(rng.integers(0, 50_000 - L))
+                seg = ref[int(rng.integers(0, 2)), o:o + L].copy()
+                for _ in range(int(rng.integers(0, 3))):
+                    seg[int(rng.integers(0, L))] = synth.LUT[int(rng.integers(0, 4))]
+            else:
+                seg = synth.LUT[rng.integers(0, 4, size=L, dtype=np.uint8)]
+            if rng.random() < 0.2:
+                seg[int(rng.integers(0, L))] = ord("N")
+            parts.append(seg)
+        reads.append(bytes(np.concatenate(parts)))
+    a, off = synth.ragged_to_batch(reads)
+    want = oracle.OracleIndex(ix).query_batch(a, off, streaming=True)
+    res = run_both(ix, reads)
+    np.testing.assert_array_equal(res[S.MODE_STREAMING], want)
+    np.testing.assert_array_equal(res[S.MODE_SEARCH], want)
