@@ -394,10 +394,16 @@ def main() -> None:
         try:
             dram = S.sector_probe(local_rank, 8 << 30, 1 << 28, 32)
             l2 = S.sector_probe(local_rank, 48 << 20, 1 << 28, 32)
-            same = S.sector_probe(local_rank, max(1 << 20, idx.device_bytes), 1 << 28, 32)
+            # the structures the walk touches at random: the rank sectors in use + the search table
+            hot = (32 * (idx.n_nodes // 96 + 1) if idx.compact_layout[0] else 128 * (idx.n_nodes // 224 + 1)) + (8 << (2 * idx.table_length))
+            same = S.sector_probe(local_rank, max(1 << 20, hot), 1 << 28, 32)
             roofline["random_sector_ceiling"] = {"dram_sectors_per_s": dram, "l2_sectors_per_s": l2, "index_sized_buffer_sectors_per_s": same,
                                                  "frac_of_index_sized_ceiling": roofline["sectors_per_s"] / same,
-                                                 "how": "sbwt_gpu_sector_probe: 2^28 independent uniformly random 32-byte loads over 8 GiB / 48 MiB / an index-sized buffer"}
+                                                 "index_sized_buffer_bytes": int(hot),
+                                                 "how": "sbwt_gpu_sector_probe: 2^28 independent uniformly random 32-byte loads over 8 GiB / 48 MiB / a buffer the size of the rank sectors in use + the search table",
+                                                 "note": "an L2 miss moves a whole 128-byte line (4 sectors) from HBM whatever cudaLimitMaxL2FetchGranularity says, so "
+                                                         "the DRAM figure x 128 B is ~94 % of the HBM copy peak; ~62 MB of L2 are usable for randomly read data "
+                                                         "(profiles/r01g_l2_capacity.txt)"}
         except Exception as e:  # the probe is informational
             roofline["random_sector_ceiling"] = {"error": str(e)}
 
@@ -411,7 +417,12 @@ def main() -> None:
             "dtype": "int64", "data": "synthetic", "config": config, "clocks": clk.summary(), "e2e": e2e,
             "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step), "roofline": roofline, "cpu_baseline": cpu,
             "lookups_per_step_per_gpu": int(n_out), "hit_rate": hits_gpu / n_out, "index_device_bytes": int(idx.device_bytes),
-            "n_nodes": int(idx.n_nodes)}
+            "n_nodes": int(idx.n_nodes),
+            "index_layout": ({"kind": "compact one-hot csectors (96 columns x 4 characters per 32-byte sector) + classic sectors for flagged blocks",
+                              "flagged_block_fraction": idx.compact_layout[1], "hot_bytes": int(32 * (idx.n_nodes // 96 + 1))}
+                             if idx.compact_layout[0] else
+                             {"kind": "classic sectors (224 columns x 1 character per 32-byte sector)",
+                              "flagged_block_fraction": idx.compact_layout[1], "hot_bytes": int(128 * (idx.n_nodes // 224 + 1))})}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

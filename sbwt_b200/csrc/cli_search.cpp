@@ -24,6 +24,8 @@
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <exception>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -158,27 +160,43 @@ struct Options {
 // run_file (sbwt_search.cpp:93-105): streaming search when the index supports it, else search() per k-mer.
 static int64_t run_file(const string& infile, const string& outfile, const sbwt::plain_matrix_sbwt_t& index, bool gzip_output,
                         const Options& opt, long long& query_micros) {
-    sbwt_b200::FastxReader reader(infile);
+    sbwt_b200::ParallelFastxReader reader(infile, opt.threads); // same batches and errors as the serial FastxReader
     Writer writer(outfile, gzip_output, opt.threads);
     SinkState sink{&writer, ""};
     const bool streaming = index.has_streaming_query_support();
     write_log(string(streaming ? "Running streaming queries from input file " : "Running non-streaming queries from input file ") + infile +
               " to output file " + outfile);
-    vector<char> ascii;
-    vector<int64_t> offsets;
+    // two batch buffers: batch i + 1 is parsed by a helper thread while the device answers batch i. A parse error
+    // surfaces when its batch is due, after the output of everything before it has been written (as in the reference,
+    // which parses and queries read by read)
+    struct Batch {
+        vector<char> ascii;
+        vector<int64_t> offsets;
+        int64_t n = 0;
+        std::exception_ptr error;
+    } batches[2];
+    auto parse = [&](Batch& b) {
+        try { b.n = reader.next_batch(opt.batch_bases, opt.batch_reads, b.ascii, b.offsets); }
+        catch (...) { b.error = std::current_exception(); b.n = 0; }
+    };
     int64_t n_queries = 0;
-    while (true) {
-        const int64_t n = reader.next_batch(opt.batch_bases, opt.batch_reads, ascii, offsets);
-        if (n == 0) break;
+    parse(batches[0]);
+    for (int turn = 0;; turn ^= 1) {
+        Batch& b = batches[turn];
+        if (b.error) std::rethrow_exception(b.error);
+        if (b.n == 0) break;
+        std::thread ahead(parse, std::ref(batches[turn ^ 1]));
         const long long t0 = cur_time_micros();
         try {
-            n_queries += index.query_batch_text(ascii.data(), offsets.data(), n, streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH,
+            n_queries += index.query_batch_text(b.ascii.data(), b.offsets.data(), b.n, streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH,
                                                 SBWT_GPU_CASE_UPPER, text_sink, &sink);
         } catch (const std::runtime_error&) {
+            ahead.join();
             if (!sink.error.empty()) throw std::runtime_error(sink.error);
             throw;
         }
         query_micros += cur_time_micros() - t0;
+        ahead.join();
     }
     writer.finish();
     write_log("us/query: " + std::to_string((double)query_micros / std::max<int64_t>(n_queries, 1)) + " (excluding I/O etc)");
@@ -197,7 +215,7 @@ static void print_help(const char* prog) {
               << "                         magnitude.\n"
               << "      --device arg       CUDA device (default 0)\n"
               << "      --batch-bases arg  Read bases per GPU batch (default 67108864)\n"
-              << "      --threads arg      Host threads for gzip output (default 8)\n"
+              << "      --threads arg      Host threads for parsing the query file and for gzip output (default 8)\n"
               << "  -h, --help             Print usage\n" << std::endl;
 }
 

@@ -82,21 +82,47 @@ struct CompactRank {
 
 __device__ __forceinline__ bool csector_flagged(const Sector& s) { return (s.w[0] & 0x8000u) != 0; }
 
-// s = csector of pos's block, off = pos % 96, base = cbase[(pos / 96) >> kCSbShift][c]
-__device__ __forceinline__ CompactRank compact_rank(const Sector& s, uint32_t base, uint32_t off, int c) {
+// the columns of a csector whose edge is c, 32 per word, and the block's relative count for c
+struct CompactMatch {
+    uint32_t m0, m1, m2, rel;
+};
+
+__device__ __forceinline__ CompactMatch compact_match(const Sector& s, int c) {
     const uint32_t cw = (c & 2) ? s.w[1] : s.w[0];
-    const uint32_t rel = ((c & 1) ? (cw >> 16) : cw) & 0x7FFFu;
     const uint32_t X = (c & 1) ? 0u : 0xFFFFFFFFu, Y = (c & 2) ? 0u : 0xFFFFFFFFu;
-    const uint32_t m0 = (s.w[2] ^ X) & (s.w[5] ^ Y), m1 = (s.w[3] ^ X) & (s.w[6] ^ Y), m2 = (s.w[4] ^ X) & (s.w[7] ^ Y);
-    const uint32_t f = off >> 5, rem = off & 31u;
-    const uint32_t mf = f == 0 ? m0 : (f == 1 ? m1 : m2);
-    uint32_t cnt = __popc(mf & ((1u << rem) - 1u));
-    if (f > 0) cnt += __popc(m0);
-    if (f > 1) cnt += __popc(m1);
-    CompactRank r;
-    r.value = base + rel + cnt;
-    r.bit = (mf >> rem) & 1u;
+    CompactMatch m;
+    m.rel = ((c & 1) ? (cw >> 16) : cw) & 0x7FFFu;
+    m.m0 = (s.w[2] ^ X) & (s.w[5] ^ Y);
+    m.m1 = (s.w[3] ^ X) & (s.w[6] ^ Y);
+    m.m2 = (s.w[4] ^ X) & (s.w[7] ^ Y);
+    return m;
+}
+
+// 0xFFFFFFFF << n with PTX semantics (n >= 32 gives 0), so ~shl_clamp(n) is the mask of the n lowest bits for 0 <= n <= 32+
+__device__ __forceinline__ uint32_t shl_ones_clamp(uint32_t n) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(0xFFFFFFFFu), "r"(n));
     return r;
+}
+
+// off = pos % 96, base = cbase[(pos / 96) >> kCSbShift][c]. Straight-line: three masked popcounts.
+__device__ __forceinline__ CompactRank compact_rank(const CompactMatch& m, uint32_t base, uint32_t off) {
+    const uint32_t n1 = (uint32_t)max((int)off - 32, 0), n2 = (uint32_t)max((int)off - 64, 0);
+    const uint32_t c0 = __popc(m.m0 & ~shl_ones_clamp(off)), c1 = __popc(m.m1 & ~shl_ones_clamp(n1)), c2 = __popc(m.m2 & ~shl_ones_clamp(n2));
+    const uint32_t f = off >> 5;
+    const uint32_t mf = f == 0 ? m.m0 : (f == 1 ? m.m1 : m.m2);
+    CompactRank r;
+    r.value = base + m.rel + c0 + c1 + c2;
+    r.bit = (mf >> (off & 31u)) & 1u;
+    return r;
+}
+
+// cbase entry of (csector block cb, character c); volatile so that it is issued where it is written -- ahead of the
+// csector load it travels with -- instead of being sunk behind the branch on the csector's flag
+__device__ __forceinline__ uint32_t ld_cbase(const uint32_t* __restrict__ cbase, uint32_t cb, int c) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(cbase + ((cb >> kCSbShift) << 2) + c));
+    return v;
 }
 
 // 256-bit read-only load of one sector, not allocated in L1 (random access, no reuse there).

@@ -11,11 +11,20 @@
 // C ABI takes.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <zlib.h>
 
@@ -54,11 +63,19 @@ class FastxReader {
     FILE* fp = nullptr;
     gzFile gzf = nullptr;
     std::vector<char> buf;
+    const char* mem = nullptr; // memory source (ParallelFastxReader's fallback): [mem, mem + mem_len)
+    size_t mem_len = 0, mem_pos = 0;
     size_t pos = 0, size = 0;
+    size_t taken = 0;    // bytes handed out by get() before the current buffer
     bool is_eof = false; // true once a get() ran past the end (Buffered_ifstream::eof)
 
     bool refill() {
-        if (gz) {
+        taken += size;
+        if (mem) {
+            size = std::min(buf.size(), mem_len - mem_pos);
+            memcpy(buf.data(), mem + mem_pos, size);
+            mem_pos += size;
+        } else if (gz) {
             int n = gzread(gzf, buf.data(), (unsigned)buf.size());
             if (n < 0) throw std::runtime_error("Error reading gzip file " + filename);
             size = (size_t)n;
@@ -102,6 +119,15 @@ public:
         if (format == SeqFormat::FASTA && c != '>') throw std::runtime_error("ERROR: FASTA file " + filename + " does not start with '>'");
         if (format == SeqFormat::FASTQ && c != '@') throw std::runtime_error("ERROR: FASTQ file " + filename + " does not start with '@'");
     }
+    // Serial parser over a memory range that starts at a record (whose first byte is consumed here, like the
+    // look-ahead get() at the end of next_read does); `filename` only feeds the error messages.
+    FastxReader(const std::string& filename, SeqFormat format, const char* mem, size_t len)
+        : filename(filename), format(format), gz(false), buf(1 << 20), mem(mem), mem_len(len) {
+        char c = 0;
+        get(c);
+    }
+    // bytes consumed so far, not counting the look-ahead byte of the next record
+    size_t consumed() const { return is_eof ? taken + pos : taken + pos - 1; }
     FastxReader(const FastxReader&) = delete;
     FastxReader& operator=(const FastxReader&) = delete;
     ~FastxReader() {
@@ -155,6 +181,200 @@ public:
             offsets.push_back((int64_t)ascii.size());
         }
         return (int64_t)offsets.size() - 1;
+    }
+};
+
+// Parallel batch reader for uncompressed FASTA / FASTQ files: the same batches, byte for byte, as
+// FastxReader::next_batch (and the same exceptions), produced by `threads` host threads.
+//
+// The file is mapped; for every batch a window of it is cut into lines by a parallel newline scan.
+// Line structure alone fixes the records -- FASTQ is strictly four lines per record (SeqIO.hh:316-343: no
+// '@' test after the first record), a FASTA header is any line that starts with '>' after a sequence line
+// (SeqIO.hh:262-312) -- so record boundaries need no guessing, and the sequence lines are copied into the
+// batch in parallel at prefix-summed offsets. Anything the reference treats specially (empty lines, empty
+// sequences, a last line without '\n', a FASTQ record whose header line is empty) is not reasoned about
+// here: the first batch that meets such a line is handed, from its first record on, to the serial parser
+// above, which raises the reference's error or carries on exactly as the reference would.
+class ParallelFastxReader {
+    std::string filename;
+    SeqFormat format;
+    int threads;
+    int fd = -1;
+    const char* data = nullptr;
+    size_t size = 0, cur = 0; // cur: first byte of the next record
+    std::unique_ptr<FastxReader> serial; // gzip input, or the fallback after an anomaly
+    size_t serial_origin = 0;
+
+    struct Line {
+        size_t start, end; // [start, end): without the '\n'
+    };
+
+    template <typename F>
+    void parallel_for(size_t n, F f) const {
+        const size_t T = std::max<size_t>(1, std::min<size_t>((size_t)threads, n));
+        if (T == 1) { f(0, n, 0); return; }
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < T; t++) th.emplace_back([=] { f(n * t / T, n * (t + 1) / T, t); });
+        f(0, n / T, 0);
+        for (auto& x : th) x.join();
+    }
+
+    // complete lines of [from, to): every '\n' found ends one
+    void scan_lines(size_t from, size_t to, std::vector<Line>& lines) const {
+        const size_t T = (size_t)std::max(1, threads);
+        std::vector<std::vector<size_t>> nl(T);
+        parallel_for(to - from, [&](size_t a, size_t b, size_t t) {
+            const char* p = data + from + a;
+            const char* e = data + from + b;
+            while (p < e) {
+                const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
+                if (!q) break;
+                nl[t].push_back((size_t)(q - data));
+                p = q + 1;
+            }
+        });
+        lines.clear();
+        size_t start = from;
+        for (const auto& v : nl)
+            for (size_t x : v) {
+                lines.push_back(Line{start, x});
+                start = x + 1;
+            }
+    }
+
+    int64_t from_serial(int64_t max_bases, int64_t max_reads, std::vector<char>& ascii, std::vector<int64_t>& offsets) {
+        return serial->next_batch(max_bases, max_reads, ascii, offsets);
+    }
+
+public:
+    ParallelFastxReader(const std::string& filename, int threads) : filename(filename), threads(std::max(1, threads)) {
+        const FileFormat ff = figure_out_file_format(filename);
+        format = ff.format;
+        if (ff.gzipped) { // a gzip stream is sequential
+            serial.reset(new FastxReader(filename));
+            return;
+        }
+        fd = open(filename.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("Error opening file " + filename);
+        struct stat st;
+        if (fstat(fd, &st) != 0) throw std::runtime_error("Error opening file " + filename);
+        size = (size_t)st.st_size;
+        if (size > 0) {
+            void* p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p == MAP_FAILED) { // e.g. a pipe: read it serially
+                close(fd);
+                fd = -1;
+                serial.reset(new FastxReader(filename));
+                return;
+            }
+            data = (const char*)p;
+            madvise((void*)data, size, MADV_SEQUENTIAL);
+        }
+        // read_first_char_and_sanity_check, SeqIO.hh:178-189 (an empty file reads a 0 byte there)
+        const char c = size ? data[0] : 0;
+        if (format == SeqFormat::FASTA && c != '>') throw std::runtime_error("ERROR: FASTA file " + filename + " does not start with '>'");
+        if (format == SeqFormat::FASTQ && c != '@') throw std::runtime_error("ERROR: FASTQ file " + filename + " does not start with '@'");
+    }
+    ParallelFastxReader(const ParallelFastxReader&) = delete;
+    ParallelFastxReader& operator=(const ParallelFastxReader&) = delete;
+    ~ParallelFastxReader() {
+        serial.reset();
+        if (data) munmap((void*)data, size);
+        if (fd >= 0) close(fd);
+    }
+
+    // Same contract as FastxReader::next_batch.
+    int64_t next_batch(int64_t max_bases, int64_t max_reads, std::vector<char>& ascii, std::vector<int64_t>& offsets) {
+        if (serial) return from_serial(max_bases, max_reads, ascii, offsets);
+        ascii.clear();
+        offsets.clear();
+        offsets.push_back(0);
+        if (cur >= size || max_reads <= 0 || max_bases <= 0) return 0;
+        struct Rec {
+            size_t first_line, n_lines; // sequence lines
+            int64_t len;
+        };
+        std::vector<Line> lines;
+        std::vector<Rec> recs;
+        size_t window = (size_t)max_bases + (size_t)max_bases / 2 + ((size_t)1 << 20);
+        bool anomaly = false;
+        size_t next_cur = cur;
+        for (;;) {
+            const size_t wend = std::min(size, cur + window);
+            const bool at_eof = wend == size;
+            scan_lines(cur, wend, lines);
+            recs.clear();
+            anomaly = false;
+            int64_t bases = 0;
+            bool full = false; // the batch reached max_reads / max_bases
+            next_cur = cur;
+            size_t i = 0;
+            const size_t nl = lines.size();
+            if (format == SeqFormat::FASTQ) {
+                while (i + 4 <= nl) {
+                    if (lines[i].end == lines[i].start || lines[i + 1].end == lines[i + 1].start) { anomaly = true; break; }
+                    recs.push_back(Rec{i + 1, 1, (int64_t)(lines[i + 1].end - lines[i + 1].start)});
+                    bases += recs.back().len;
+                    i += 4;
+                    next_cur = i < nl ? lines[i].start : lines[i - 1].end + 1;
+                    if ((int64_t)recs.size() >= max_reads || bases >= max_bases) { full = true; break; }
+                }
+                // a tail that is not a whole record (or lacks its last '\n') is the serial parser's business
+                if (!full && !anomaly && at_eof && next_cur < size) anomaly = true;
+            } else {
+                while (i < nl) {
+                    // line i is a header (the first byte of a record is '>' by construction)
+                    size_t j = i + 1;
+                    int64_t len = 0;
+                    bool bad = lines[i].end == lines[i].start; // cannot happen ('>' is there), kept for symmetry
+                    while (j < nl && data[lines[j].start] != '>') {
+                        if (lines[j].end == lines[j].start) { bad = true; break; }
+                        len += (int64_t)(lines[j].end - lines[j].start);
+                        j++;
+                    }
+                    if (bad || (j < nl && j == i + 1)) { anomaly = true; break; } // empty line / empty sequence
+                    const size_t after = j < nl ? lines[j].start : lines[j - 1].end + 1;
+                    if (j == nl && !(at_eof && after == size)) {
+                        // the record may go on beyond the window; at the end of the file: unterminated last line
+                        if (at_eof) anomaly = true;
+                        break;
+                    }
+                    if (j == i + 1) { anomaly = true; break; } // a header at the very end of the file
+                    recs.push_back(Rec{i + 1, j - (i + 1), len});
+                    bases += len;
+                    i = j;
+                    next_cur = after;
+                    if ((int64_t)recs.size() >= max_reads || bases >= max_bases) { full = true; break; }
+                }
+                if (!full && !anomaly && at_eof && next_cur < size) anomaly = true; // bytes after the last '\n'
+            }
+            if (anomaly || full || at_eof) break;
+            window *= 2; // the window ended before the batch was full
+        }
+        if (anomaly) {
+            serial.reset(new FastxReader(filename, format, data + cur, size - cur));
+            return from_serial(max_bases, max_reads, ascii, offsets);
+        }
+        const size_t n = recs.size();
+        offsets.resize(n + 1);
+        for (size_t r = 0; r < n; r++) offsets[r + 1] = offsets[r] + recs[r].len;
+        ascii.resize((size_t)offsets[n]);
+        char* out = ascii.data();
+        const int64_t* off = offsets.data();
+        const Line* L = lines.data();
+        const Rec* R = recs.data();
+        const char* d = data;
+        parallel_for(n, [=](size_t a, size_t b, size_t) {
+            for (size_t r = a; r < b; r++) {
+                char* o = out + off[r];
+                for (size_t l = R[r].first_line; l < R[r].first_line + R[r].n_lines; l++) {
+                    memcpy(o, d + L[l].start, L[l].end - L[l].start);
+                    o += L[l].end - L[l].start;
+                }
+            }
+        });
+        cur = next_cur;
+        return (int64_t)n;
     }
 };
 

@@ -661,6 +661,15 @@ static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, 
     int blocks_per_sm = 0;
     if (const char* e = getenv("SBWT_B200_BLOCKS_PER_SM")) blocks_per_sm = std::max(0, atoi(e));
     apply_l2_fetch_granularity();
+    // The compact layout pays in streaming mode, whose 8 B-per-k-mer result stream competes with the index for L2.
+    // The per-k-mer search path re-reads the wide top of the tree, is bound by L2 sector throughput and issue slots,
+    // and is faster on the 224-column classic sectors (fewer two-sector steps): profiles/r01h_compact_ab.txt.
+    // SBWT_B200_COMPACT_SEARCH=1 (or SBWT_B200_COMPACT=2) uses it there as well.
+    if (!streaming && P.ix.compact) {
+        const char* cs = getenv("SBWT_B200_COMPACT_SEARCH");
+        const char* cm = getenv("SBWT_B200_COMPACT");
+        if (!((cs && atoi(cs) > 0) || (cm && atoi(cm) >= 2))) P.ix.compact = nullptr;
+    }
     const char* el = getenv("SBWT_B200_L2_EVICT_LAST");
     P.index_evict_last = el ? atoi(el) : 1;
     const char* fr = getenv("SBWT_B200_L2_FRAC");

@@ -58,6 +58,13 @@ constexpr int kQCap = 64; // entries per queue: at most 32 are waiting when up t
 #ifndef SBWT_B200_SINGLE_HOLD
 #define SBWT_B200_SINGLE_HOLD 2
 #endif
+// SBWT_B200_DEBUG_NOSTORE (measurement knob) costs a uniform load and a branch at every store of the hot loop, so it
+// only exists in builds made with -DSBWT_B200_DEBUG_KNOBS (tools/gpu_variants.sh)
+#ifdef SBWT_B200_DEBUG_KNOBS
+constexpr bool kDebugKnobs = true;
+#else
+constexpr bool kDebugKnobs = false;
+#endif
 constexpr uint32_t kSingleHold = SBWT_B200_SINGLE_HOLD; // extra NARROW steps on a singleton interval before it is queued (drops most chance survivors)
 
 template <bool WIDE>
@@ -120,7 +127,7 @@ __device__ __forceinline__ bool kmer_invalid(const uint32_t* __restrict__ inv, u
 
 template <bool OUT32>
 __device__ __forceinline__ void store_result(const WalkParams& P, uint32_t o, int64_t v) {
-    if (P.debug_no_store) { // measurement only: 1 = no store, 2 = plain write-back store instead of the streaming one
+    if (kDebugKnobs && P.debug_no_store) { // measurement only: 1 = no store, 2 = plain write-back store instead of the streaming one
         if (P.debug_no_store == 2) {
             if (OUT32) P.out32[o] = (int32_t)v;
             else P.out[o] = v;
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                 OS.v[sl][lane] = (typename OutStage<OUT32>::val_t)v;
                 if (sl == OR - 1u) {
                     if (x - gs == OR - 1u) {
-                        if (!P.debug_no_store) {
+                        if (!(kDebugKnobs && P.debug_no_store)) {
                             uint32_t wv[8];
                             if (OUT32) {
 #pragma unroll
@@ -307,9 +314,12 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                     bool classic = true;
                     if (COMPACT) {
                         const uint32_t cb = (uint32_t)col / (uint32_t)kCBlockCols, coff = (uint32_t)col - cb * (uint32_t)kCBlockCols;
+                        const uint32_t base = ld_cbase(cbase, cb, c); // in flight together with the csector
                         const Sector s = ld_sector(cmp_base + cb, pol);
-                        if (!csector_flagged(s)) {
-                            const CompactRank cr = compact_rank(s, __ldg(cbase + ((cb >> kCSbShift) << 2) + c), coff, c);
+                        // (base is never all ones; testing it here makes the branch wait for it, so ptxas cannot sink its load
+                        // behind the branch, where it would add a second dependent memory latency to every step)
+                        if (!(csector_flagged(s) | (base == 0xFFFFFFFFu))) {
+                            const CompactRank cr = compact_rank(compact_match(s, c), base, coff);
                             ncol = (pos_t)cr.value;
                             miss = cr.bit == 0;
                             classic = false;
@@ -501,14 +511,17 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                     const uint32_t p0 = (uint32_t)l, p1 = (uint32_t)r + 1u;
                     const uint32_t cb0 = p0 / (uint32_t)kCBlockCols, cb1 = p1 / (uint32_t)kCBlockCols;
                     two = cb1 != cb0;
+                    const uint32_t base0 = ld_cbase(cbase, cb0, c); // in flight together with the csectors
+                    uint32_t base1 = base0;
+                    if ((cb1 >> kCSbShift) != (cb0 >> kCSbShift)) base1 = ld_cbase(cbase, cb1, c);
                     const Sector s0 = ld_sector(cmp_base + cb0, pol);
-                    Sector s1 = s0;
+                    Sector s1;
                     if (two) s1 = ld_sector(cmp_base + cb1, pol);
-                    if (!csector_flagged(s0) && !csector_flagged(s1)) {
-                        const uint32_t base0 = __ldg(cbase + ((cb0 >> kCSbShift) << 2) + c);
-                        const uint32_t base1 = __ldg(cbase + ((cb1 >> kCSbShift) << 2) + c);
-                        nl = (pos_t)compact_rank(s0, base0, p0 - cb0 * (uint32_t)kCBlockCols, c).value;
-                        nr = (pos_t)compact_rank(s1, base1, p1 - cb1 * (uint32_t)kCBlockCols, c).value;
+                    if (!(csector_flagged(s0) | (two && csector_flagged(s1)) | ((base0 & base1) == 0xFFFFFFFFu))) { // (bases: see CHAIN)
+                        const CompactMatch m0 = compact_match(s0, c);
+                        nl = (pos_t)compact_rank(m0, base0, p0 - cb0 * (uint32_t)kCBlockCols).value;
+                        if (two) nr = (pos_t)compact_rank(compact_match(s1, c), base1, p1 - cb1 * (uint32_t)kCBlockCols).value;
+                        else nr = (pos_t)compact_rank(m0, base0, p1 - cb0 * (uint32_t)kCBlockCols).value;
                         classic = false;
                     }
                 }

@@ -1,0 +1,129 @@
+"""ParallelFastxReader (sbwt_b200/csrc/fastx.hpp) against the serial FastxReader, which restates
+seq_io::Reader::get_next_read_to_buffer (SeqIO/include/SeqIO/SeqIO.hh:255-360): same batches byte for byte, same
+exceptions, over well-formed files (single- and multi-line FASTA, FASTQ, CRLF, long reads, tiny batches) and over
+every malformation the reference singles out (empty lines, empty sequences, a last line without a newline, truncated
+FASTQ records, an empty FASTQ header). CPU only."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("fx") / "test_fastx")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-o", out, os.path.join(ROOT, "tests", "cpp", "test_fastx.cpp"), "-lz", "-lpthread"], check=True)
+    return out
+
+
+def both(exe, path, max_bases, max_reads, threads):
+    r = subprocess.run([exe, path, str(max_bases), str(max_reads), str(threads)], capture_output=True, text=True, check=True)
+    a, b = r.stdout.strip().split("\n")
+    return a, b
+
+
+def rand_seq(rng, n):
+    return bytes(np.frombuffer(b"ACGTNacgt", dtype=np.uint8)[rng.integers(0, 9, size=n)])
+
+
+def fasta(rng, n, multi_line, crlf=False, max_len=400):
+    nl = b"\r\n" if crlf else b"\n"
+    out = []
+    for i in range(n):
+        s = rand_seq(rng, int(rng.integers(1, max_len)))
+        out.append(b">r%d some header > with @ signs" % i + nl)
+        if multi_line:
+            w = int(rng.integers(1, 90))
+            out += [s[j:j + w] + nl for j in range(0, len(s), w)]
+        else:
+            out.append(s + nl)
+    return b"".join(out)
+
+
+def fastq(rng, n, crlf=False, max_len=400):
+    nl = b"\r\n" if crlf else b"\n"
+    out = []
+    for i in range(n):
+        s = rand_seq(rng, int(rng.integers(1, max_len)))
+        q = bytes(rng.integers(33, 74, size=len(s), dtype=np.uint8))  # '@' and '+' occur as quality values
+        if i % 7 == 0:
+            q = b"@" + q[1:]
+        out += [b"@r%d" % i + nl, s + nl, b"+" + nl, q + nl]
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("kind", ["fa1", "fam", "fq", "fa_crlf", "fq_crlf"])
+def test_wellformed_files_give_identical_batches(exe, tmp_path, kind):
+    rng = np.random.default_rng(hash(kind) % 1000)
+    data = {"fa1": lambda: fasta(rng, 3000, False), "fam": lambda: fasta(rng, 3000, True), "fq": lambda: fastq(rng, 3000),
+            "fa_crlf": lambda: fasta(rng, 500, True, crlf=True), "fq_crlf": lambda: fastq(rng, 500, crlf=True)}[kind]()
+    path = str(tmp_path / ("x.fq" if kind.startswith("fq") else "x.fna"))
+    open(path, "wb").write(data)
+    for max_bases, max_reads, threads in [(1 << 30, 1 << 30, 4), (5000, 1 << 30, 3), (1, 1 << 30, 2), (1 << 30, 7, 8), (100_000, 100, 1), (333, 5, 5)]:
+        a, b = both(exe, path, max_bases, max_reads, threads)
+        assert not a.startswith("ERROR"), a
+        assert a == b, (kind, max_bases, max_reads, threads)
+
+
+def test_long_reads_exceed_the_scan_window(exe, tmp_path):
+    rng = np.random.default_rng(5)
+    path = str(tmp_path / "long.fna")
+    with open(path, "wb") as f:
+        for i in range(6):
+            s = rand_seq(rng, 3_000_000 + i)
+            f.write(b">c%d\n" % i)
+            for j in range(0, len(s), 70):
+                f.write(s[j:j + 70] + b"\n")
+    for mb in (10, 1_000_000, 1 << 30):
+        a, b = both(exe, path, mb, 1 << 30, 4)
+        assert not a.startswith("ERROR") and a == b
+
+
+BAD = {
+    "fa_empty_line_after_header.fna": b">a\nACGT\n>b\n\nACGT\n>c\nAC\n",
+    "fa_empty_line_in_sequence.fna": b">a\nACGT\n>b\nAC\n\nGT\n",
+    "fa_empty_sequence.fna": b">a\nACGT\n>b\n>c\nACGT\n",
+    "fa_header_at_end.fna": b">a\nACGT\n>b\n",
+    "fa_no_final_newline.fna": b">a\nACGT\n>b\nACGTT",
+    "fa_trailing_empty_line.fna": b">a\nACGT\n>b\nACGTT\n\n",
+    "fa_wrong_start.fna": b"ACGT\n>b\nACGTT\n",
+    "fq_truncated.fq": b"@a\nACGT\n+\nIIII\n@b\nAC\n+\n",
+    "fq_no_final_newline.fq": b"@a\nACGT\n+\nIIII\n@b\nAC\n+\nII",
+    "fq_empty_sequence.fq": b"@a\nACGT\n+\nIIII\n@b\n\n+\n\n@c\nAC\n+\nII\n",
+    "fq_empty_header.fq": b"@a\nACGT\n+\nIIII\n\nAC\n+\nII\n@c\nAC\n+\nII\n",
+    "fq_wrong_start.fq": b"a\nACGT\n+\nIIII\n",
+    "fq_extra_blank_lines.fq": b"@a\nACGT\n+\nIIII\n\n\n",
+    "empty.fna": b"",
+    "empty.fq": b"",
+}
+
+
+@pytest.mark.parametrize("name", sorted(BAD))
+def test_malformed_files_fail_or_parse_exactly_like_the_serial_reader(exe, tmp_path, name):
+    path = str(tmp_path / name)
+    # a few good records in front, so that the anomaly is met in a later batch as well as in the first
+    rng = np.random.default_rng(3)
+    for prefix in (b"", (fastq(rng, 40) if name.endswith(".fq") else fasta(rng, 40, True))):
+        if name.startswith("fa_wrong") or name.startswith("fq_wrong") or name.startswith("empty"):
+            prefix = b""
+        open(path, "wb").write(prefix + BAD[name])
+        for max_bases, max_reads, threads in [(1 << 30, 1 << 30, 4), (50, 1 << 30, 2), (1 << 30, 1, 3)]:
+            a, b = both(exe, path, max_bases, max_reads, threads)
+            assert a == b, (name, a, b)
+
+
+def test_gzip_input_goes_through_the_serial_reader(exe, tmp_path):
+    rng = np.random.default_rng(9)
+    data = fastq(rng, 500)
+    path = str(tmp_path / "x.fastq.gz")
+    with gzip.open(path, "wb") as f:
+        f.write(data)
+    plain = str(tmp_path / "x.fastq")
+    open(plain, "wb").write(data)
+    a, b = both(exe, path, 10_000, 1 << 30, 4)
+    a2, b2 = both(exe, plain, 10_000, 1 << 30, 4)
+    assert not a.startswith("ERROR") and a == b == a2 == b2
