@@ -385,6 +385,8 @@ def main() -> None:
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                # DRAM bytes actually moved per launch (ncu) / this run's kernel time / peak: how much of HBM the kernel uses
+                "traffic_frac": (traffic / (w_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel": "walk2_kernel",
                 "kernel_ms": w_ms, "kernel_share_of_step": w_ms / ms_per_step, "prep_ms": float(np.mean(prep_ms)),
                 "algorithmic_sectors_per_step": stats.index_sectors, "sectors_per_s": stats.index_sectors / (w_ms * 1e-3),
@@ -395,7 +397,7 @@ def main() -> None:
             dram = S.sector_probe(local_rank, 8 << 30, 1 << 28, 32)
             l2 = S.sector_probe(local_rank, 48 << 20, 1 << 28, 32)
             # the structures the walk touches at random: the rank sectors in use + the search table
-            hot = (32 * (idx.n_nodes // 96 + 1) if idx.compact_layout[0] else 128 * (idx.n_nodes // 224 + 1)) + (8 << (2 * idx.table_length))
+            hot = (32 * (idx.n_nodes // 96 + 1) if (idx.compact_layout[0] and w["streaming"]) else 128 * (idx.n_nodes // 224 + 1)) + (8 << (2 * idx.table_length))
             same = S.sector_probe(local_rank, max(1 << 20, hot), 1 << 28, 32)
             roofline["random_sector_ceiling"] = {"dram_sectors_per_s": dram, "l2_sectors_per_s": l2, "index_sized_buffer_sectors_per_s": same,
                                                  "frac_of_index_sized_ceiling": roofline["sectors_per_s"] / same,
@@ -420,7 +422,7 @@ def main() -> None:
             "n_nodes": int(idx.n_nodes),
             "index_layout": ({"kind": "compact one-hot csectors (96 columns x 4 characters per 32-byte sector) + classic sectors for flagged blocks",
                               "flagged_block_fraction": idx.compact_layout[1], "hot_bytes": int(32 * (idx.n_nodes // 96 + 1))}
-                             if idx.compact_layout[0] else
+                             if (idx.compact_layout[0] and w["streaming"]) else
                              {"kind": "classic sectors (224 columns x 1 character per 32-byte sector)",
                               "flagged_block_fraction": idx.compact_layout[1], "hot_bytes": int(128 * (idx.n_nodes // 224 + 1))})}
     print(json.dumps(line), flush=True)

@@ -65,6 +65,10 @@ constexpr bool kDebugKnobs = true;
 #else
 constexpr bool kDebugKnobs = false;
 #endif
+#ifndef SBWT_B200_FAST_CHAIN
+#define SBWT_B200_FAST_CHAIN 1
+#endif
+constexpr bool kFastChain = SBWT_B200_FAST_CHAIN != 0; // the steady-state loop of CHAIN (A/B: -DSBWT_B200_FAST_CHAIN=0)
 constexpr uint32_t kSingleHold = SBWT_B200_SINGLE_HOLD; // extra NARROW steps on a singleton interval before it is queued (drops most chance survivors)
 
 template <bool WIDE>
@@ -306,6 +310,52 @@ __global__ void __launch_bounds__(kW2Threads, WIDE ? 3 : SBWT_B200_W2_MINBLOCKS)
                     else { j = k - 1; fs = true; }
                 }
                 if (!__any_sync(FULL, act)) break;
+                // ---- steady state of a streaming chain: every active lane sits on a found k-mer (SBWT.hh:561-575 with
+                // l == r) and the next one is found as well. Those iterations need none of the bookkeeping below (pending
+                // results, misses, queue pushes, walk-backs), so they run in a loop of their own: step, and if EVERY active
+                // lane found its next k-mer, commit and emit at once. The first iteration in which some lane misses, meets a
+                // flagged csector or needs anything else is left untouched (nothing committed) to the general code below.
+                // (COMPACT kernels only: an index on classic sectors is HBM-bound, not issue-bound, and measured 7 % slower
+                // with the extra loop: profiles/r01k_fast_chain.txt)
+                if (STREAMING && !LITERAL && COMPACT && kFastChain && sb && __all_sync(FULL, !act || (fs && j == k - 1u))) {
+                    while (true) {
+                        bool ok = true;
+                        pos_t ncol = 0;
+                        if (act) {
+                            const int c = (int)((cw >> ((pos & 15u) * 2u)) & 3u);
+                            if (COMPACT) {
+                                const uint32_t cb = (uint32_t)col / (uint32_t)kCBlockCols, coff = (uint32_t)col - cb * (uint32_t)kCBlockCols;
+                                const uint32_t base = ld_cbase(cbase, cb, c);
+                                const Sector s = ld_sector(cmp_base + cb, pol);
+                                const CompactRank cr = compact_rank(compact_match(s, c), base, coff);
+                                ncol = (pos_t)cr.value;
+                                ok = cr.bit != 0 && !(csector_flagged(s) | (base == 0xFFFFFFFFu)); // (base: see below)
+                            } else {
+                                const BlockPos bp = split_pos<WIDE>((int64_t)col);
+                                const Sector s = ld_sector(sector_ptr<WIDE>(sec_base, bp.blk, c), pol_cl);
+                                const SectorPrefix pf = sector_prefix(s);
+                                const uint32_t f = bp.off >> 5, rm = bp.off & 31u;
+                                const uint32_t w = sector_word(s, f);
+                                ncol = (pos_t)(s.w[0] + __byte_perm(pf.X, pf.Y, f) + __popc(w & ((1u << rm) - 1u)));
+                                if (WIDE) ncol += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (bp.blk >> ix.sb_shift));
+                                ok = ((w >> rm) & 1u) != 0;
+                            }
+                        }
+                        if (!__all_sync(FULL, ok)) break;
+                        if (act) {
+                            if (COUNT) { st_ranks += 2; st_sectors += 1; st_lookups++; st_hits++; }
+                            col = ncol;
+                            pos++;
+                            if ((pos & 15u) == 0) { cw = nx; nx = __ldg(P.codes + (pos >> 4) + 1); }
+                            emit(o, (int64_t)col);
+                            o++;
+                            rem--;
+                            if (rem == 0) { act = false; drain(o); }
+                        }
+                        if (!__any_sync(FULL, act)) break;
+                    }
+                    if (!__any_sync(FULL, act)) break;
+                }
                 bool miss = false;
                 if (act) {
                     const int c = (int)((cw >> ((pos & 15u) * 2u)) & 3u);
