@@ -384,6 +384,54 @@ __global__ void __launch_bounds__(256) rank_kernel(const DeviceIndexView ix, con
     out[t] = lf_value<WIDE>(ix, s, bp.blk, bp.off, c) - Cc;
 }
 
+// ------------------------------------------------------------------ sparse result wire format
+//
+// A batch of int32 results (colex rank or -1) leaves the device as
+//   masks[g]       bit i = result 32 g + i is a hit                       (n / 8 bytes)
+//   packed[...]    the hits only, in result order within every 4096-result block
+//   block_base[b]  where block b's hits start in `packed` (blocks claim their space with one atomicAdd, so their
+//                  order in `packed` is arbitrary; inside a block the order is the result order)
+// so that the PCIe copy and the host-side read of it shrink with the miss rate (SBWT.hh:390/:545 return one int64 per
+// k-mer; a miss is always -1). The host rebuilds the caller's array from the three pieces (host_widen.cpp).
+constexpr int kSparseBlock = 4096; // results per thread block: 8 warps x 16 groups of 32
+
+__global__ void __launch_bounds__(256) sparse_pack_kernel(const int32_t* __restrict__ vals, int64_t n, uint32_t* __restrict__ masks,
+                                                          int32_t* __restrict__ packed, uint32_t* __restrict__ block_base,
+                                                          unsigned long long* __restrict__ total) {
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ uint32_t base_sh;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t g0 = (int64_t)blockIdx.x * (kSparseBlock / 32) + w * 16; // first group of this warp
+    int32_t v[16];
+    uint32_t m[16];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int64_t idx = (g0 + i) * 32 + lane;
+        v[i] = idx < n ? vals[idx] : -1;
+        m[i] = __ballot_sync(0xFFFFFFFFu, v[i] >= 0);
+        cnt += __popc(m[i]);
+        if (lane == 0 && (g0 + i) * 32 < n) masks[g0 + i] = m[i];
+    }
+    if (lane == 0) warp_cnt[w] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) { const uint32_t c = warp_cnt[i]; warp_cnt[i] = t; t += c; }
+        const uint32_t b = (uint32_t)atomicAdd(total, (unsigned long long)t);
+        base_sh = b;
+        block_base[blockIdx.x] = b;
+    }
+    __syncthreads();
+    uint32_t pos = base_sh + warp_cnt[w];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (v[i] >= 0) packed[pos + __popc(m[i] & lt)] = v[i];
+        pos += __popc(m[i]);
+    }
+}
+
 // ------------------------------------------------------------------ random-sector probe
 
 // Each thread issues `per_thread` independent random aligned loads of BYTES (32 or 64) and xors them.

@@ -1,0 +1,19 @@
+#!/bin/bash
+# r01m: final-binary validation of the round: smoke, parity, c2 bench line + reference arm, ncu launch list + full capture,
+# knob sweep on the compact kernel.
+set -u
+TAG=${1:-r01m}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+T0=$(date +%s)
+python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $OUT/smoke.log
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 $OUT/pytest_gpu.log
+echo "t=$(( $(date +%s) - T0 ))s"
+timeout 900 python bench.py > $OUT/bench_c2.json 2> $OUT/bench_c2.log; echo "bench c2 rc=$?"; cat $OUT/bench_c2.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_c2.json 2> $OUT/bench_ref_c2.log; echo "bench ref rc=$?"; cat $OUT/bench_ref_c2.json
+echo "t=$(( $(date +%s) - T0 ))s"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c2.csv \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-probe > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:walk -s 4 -c 1 -f -o $OUT/walk2_c2_full \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-probe > $OUT/ncu_full_c2.log 2>&1; echo "ncu full c2 rc=$?"
+echo "t=$(( $(date +%s) - T0 ))s"
+timeout 600 python tools/exp_knobs.py c2 10000000 compact 2>&1 | grep -v "^\[bench\]" | tee $OUT/knobs_compact.txt
+echo "t=$(( $(date +%s) - T0 ))s"
