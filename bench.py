@@ -318,12 +318,19 @@ def main() -> None:
         e2e = {"value": world * n_out / sec, "unit": "lookups/s", "h2d_bytes_per_step": int(a.nbytes + off.nbytes),
                "d2h_bytes_per_step": int(n_out * 8), "ms_per_step": sec * 1e3, "steps": n_e2e,
                "api": "sbwt_gpu_query_host (pinned host buffers, int64 results: what SBWT::streaming_search returns)",
-               "result_wire_format": ("int32 over PCIe, sign-extended into the caller's int64 array by host threads "
-                                      "(host_widen.hpp; SBWT_B200_WIDEN_THREADS, default = hardware threads / visible GPUs, <= 8)")
-               if ses_h.widen_threads() > 0 else "int64 over PCIe",
                "widen_threads": ses_h.widen_threads(), "host_threads": os.cpu_count()}
-        if ses_h.widen_threads() > 0:
+        sparse_wire = ses_h.widen_threads() > 0 and os.environ.get("SBWT_B200_WIRE", "sparse") != "dense"
+        sparse_bytes = int(n_out // 8 + 4 * hits_gpu + n_out // 1024)  # hit masks + the hits + block bases
+        if sparse_wire:
+            e2e["result_wire_format"] = ("sparse: one hit bit per result + the hits only (int32) cross PCIe; host threads rebuild the caller's "
+                                         "int64 array (host_widen.hpp; SBWT_B200_WIRE=dense sends every result as int32 instead)")
+            e2e["d2h_bytes_per_step"] = sparse_bytes
+        elif ses_h.widen_threads() > 0:
+            e2e["result_wire_format"] = ("dense: int32 over PCIe, sign-extended into the caller's int64 array by host threads "
+                                         "(host_widen.hpp; SBWT_B200_WIDEN_THREADS, default = hardware threads / visible GPUs, <= 8)")
             e2e["d2h_bytes_per_step"] = int(n_out * 4)
+        else:
+            e2e["result_wire_format"] = "int64 over PCIe"
 
         def timed_leg(session, fn_name, out_buf):
             getattr(session, fn_name)(h_a, h_off, mode, out=out_buf)
@@ -366,7 +373,7 @@ def main() -> None:
                 t = torch.tensor([sec32], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 sec32 = float(t.item())
-            e2e["int32_results"] = {"value": world * n_out / sec32, "unit": "lookups/s", "d2h_bytes_per_step": int(n_out * 4),
+            e2e["int32_results"] = {"value": world * n_out / sec32, "unit": "lookups/s", "d2h_bytes_per_step": sparse_bytes if sparse_wire else int(n_out * 4),
                                     "ms_per_step": sec32 * 1e3, "api": "sbwt_gpu_query_host_i32"}
             del h_out32
         ses_h.close()

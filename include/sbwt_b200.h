@@ -218,9 +218,18 @@ int sbwt_gpu_sector_probe(int device, int64_t buffer_bytes, int64_t n_loads, int
 /* Host half of the 32-bit result wire format (no device work): sbwt_gpu_query_host on an index with fewer
  * than 2^31 columns lets the kernel write int32, copies those over PCIe and sign-extends them into the
  * caller's int64 array with `threads` host threads (SBWT_B200_WIDEN_THREADS; default = hardware threads /
- * visible GPUs, at most 16; below 4 the int64 values are copied directly). This entry runs that widening
+ * visible GPUs, at most 8; below 4 the int64 values are copied directly). This entry runs that widening
  * step alone: out[i] = in[i] for i < n. Values are what SBWT::search returns (SBWT.hh:390-415). */
 int sbwt_gpu_widen_i32(const int32_t *in, int64_t *out, int64_t n, int threads);
+/* Host half of the SPARSE result wire format (the default of sbwt_gpu_query_host / _i32 when host threads are
+ * available; SBWT_B200_WIRE=dense selects the format above): the device sends, per chunk, one hit bit per
+ * result (masks[g] bit i = result 32 g + i is >= 0), the hits only (packed, int32, result order inside every
+ * 4096-result block) and where each block's hits start in `packed` (block_base[b]); a miss is always -1
+ * (SBWT.hh:390-415, :545-581), so nothing is lost. This entry rebuilds n results into out (int64 if out_is_i64,
+ * else int32) with `threads` host threads; no device work. `packed` must be readable for 32 bytes past its last
+ * value (hits are moved eight at a time). */
+int sbwt_gpu_expand_sparse(const uint32_t *masks, const uint32_t *block_base, const int32_t *packed, int64_t n,
+                           void *out, int out_is_i64, int threads);
 /* Host threads this session's sbwt_gpu_query_host calls widen with: 0 = int64 values cross PCIe, -1 = not
  * decided yet (decided by the first sbwt_gpu_query_host call). */
 int sbwt_gpu_session_widen_threads(const sbwt_gpu_session *s);

@@ -33,7 +33,7 @@ EXPORTS = [
     "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
     "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
     "sbwt_gpu_index_set_table_length", "sbwt_gpu_index_table_length",
-    "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text", "sbwt_gpu_widen_i32", "sbwt_gpu_session_widen_threads",
+    "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text", "sbwt_gpu_widen_i32", "sbwt_gpu_expand_sparse", "sbwt_gpu_session_widen_threads",
 ]
 
 TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
@@ -96,6 +96,7 @@ def lib():
         L.sbwt_gpu_launch_count.restype = i64
         L.sbwt_gpu_sector_probe.argtypes = [i32, i64, i64, i32, i32, C.POINTER(C.c_double)]
         L.sbwt_gpu_widen_i32.argtypes = [vp, vp, i64, i32]
+        L.sbwt_gpu_expand_sparse.argtypes = [vp, vp, vp, i64, vp, i32, i32]
         L.sbwt_gpu_session_widen_threads.argtypes = [vp]
         L.sbwt_gpu_text_capacity.argtypes = [vp, i64, i64]
         L.sbwt_gpu_text_capacity.restype = i64
@@ -336,6 +337,21 @@ def widen_i32(values: np.ndarray, threads: int = 4) -> np.ndarray:
     out = np.empty(values.size, dtype=np.int64)
     _check(lib().sbwt_gpu_widen_i32(values.ctypes.data, out.ctypes.data, values.size, threads))
     return out
+
+
+def expand_sparse(masks: np.ndarray, block_base: np.ndarray, packed: np.ndarray, n: int, dtype=np.int64, threads: int = 4,
+                  out: np.ndarray | None = None) -> np.ndarray:
+    """Host half of the sparse result wire format (sbwt_gpu_expand_sparse; no device needed)."""
+    masks = np.ascontiguousarray(masks, dtype=np.uint32)
+    block_base = np.ascontiguousarray(block_base, dtype=np.uint32)
+    packed = np.ascontiguousarray(packed, dtype=np.int32)
+    packed = np.concatenate([packed, np.zeros(8, dtype=np.int32)])  # the entry reads 8 values at a time
+    if out is None:
+        out = np.empty(n, dtype=dtype)
+    assert out.size >= n and out.dtype in (np.int64, np.int32)
+    _check(lib().sbwt_gpu_expand_sparse(masks.ctypes.data, block_base.ctypes.data, packed.ctypes.data, n, out.ctypes.data,
+                                       1 if out.dtype == np.int64 else 0, threads))
+    return out[:n]
 
 
 def sector_probe(device: int, buffer_bytes: int, n_loads: int, bytes_per_load: int = 32, iters: int = 3) -> float:

@@ -139,6 +139,26 @@ struct HostSlot {
     std::vector<WidenJob> widen_jobs; // one per D2H piece of the slot's batch; stable until slot_finish
     WidenPool* widen_pool = nullptr;  // non-null while widening jobs of this slot may be outstanding
     WidenTicket widen_ticket;
+    // sparse wire format (aux_kernels.cuh sparse_pack_kernel, host_widen.hpp): masks + block bases + hit count come
+    // back first (ev_small); the hits follow once the host knows how many there are (slot_back)
+    uint32_t* d_masks = nullptr;
+    uint32_t* d_bbase = nullptr;
+    unsigned long long* d_total = nullptr;
+    uint32_t* h_masks = nullptr;
+    uint32_t* h_bbase = nullptr;
+    unsigned long long* h_total = nullptr;
+    cudaEvent_t ev_small = nullptr;
+    bool back_pending = false;
+    struct SparseJob {
+        WidenPool* pool = nullptr;
+        const uint32_t* masks = nullptr;
+        const uint32_t* bbase = nullptr;
+        const int32_t* packed = nullptr;
+        size_t n = 0;
+        void* dst = nullptr;
+        bool dst64 = true;
+        WidenTicket* ticket = nullptr;
+    } sparse_job;
 };
 
 struct sbwt_gpu_session {
@@ -362,9 +382,12 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
         const char* e = getenv("SBWT_B200_TABLE_P");
         if (e) tp = atoi(e);
         else {
-            // longest table that stays below half the size of the sector array (it shares L2 / HBM with it)
-            tp = (int)std::min<int64_t>(std::max<int64_t>(p, 12), k);
-            while (tp > p && ((int64_t)(wide ? 16 : 8) << (2 * tp)) > std::max<int64_t>(4 * n_blocks * (int64_t)sizeof(Sector) / 2, 1 << 20)) tp--;
+            // longest table (<= 13 characters: 537 MB of 8-byte rows) with at most 2 rows per column of the index. A row
+            // is read once per from-scratch search and replaces one dependent interval step per extra character; every
+            // workload measured faster with each character up to 13 although the table then dwarfs the sector array and
+            // lives in HBM (profiles/r01n_table_length.txt: c2 10.86 -> 9.81 ms, c3 71.0 -> 65.7, c4s 20.4 -> 18.7, c5s 17.9 -> 16.3)
+            tp = (int)std::min<int64_t>(std::max<int64_t>(p, 13), k);
+            while (tp > p && (1ll << (2 * tp)) > std::max<int64_t>(2 * n_nodes, 1 << 16)) tp--;
         }
     }
     if (int rc = sbwt_gpu_index_set_table_length(ix, tp)) { sbwt_gpu_index_destroy(ix); return rc; }
@@ -376,7 +399,7 @@ extern "C" int sbwt_gpu_index_set_table_length(sbwt_gpu_index* ix, int tp) {
     if (!ix) return set_error("null index");
     if (tp < 0) return set_error("negative table length");
     if (tp > ix->k) tp = (int)ix->k;
-    if (tp > 13) tp = 13;
+    if (tp > 14) tp = 14;
     if (!ix->table_from_bits && tp != ix->precalc_k)
         return set_error("the file's precalc table does not follow from its bit vectors; only its own length (%lld) can be used", (long long)ix->precalc_k);
     DeviceGuard guard(ix->device);
@@ -551,6 +574,9 @@ extern "C" void sbwt_gpu_session_destroy(sbwt_gpu_session* s) {
         scratch_free(h.sc);
         cudaFree(h.d_ascii); cudaFree(h.d_offsets); cudaFree(h.d_out); cudaFree(h.d_text);
         cudaFreeHost(h.h_ascii); cudaFreeHost(h.h_offsets); cudaFreeHost(h.h_out); cudaFreeHost(h.h_totals); cudaFreeHost(h.h_out32);
+        cudaFree(h.d_masks); cudaFree(h.d_bbase); cudaFree(h.d_total);
+        cudaFreeHost(h.h_masks); cudaFreeHost(h.h_bbase); cudaFreeHost(h.h_total);
+        if (h.ev_small) cudaEventDestroy(h.ev_small);
         if (h.stream) cudaStreamDestroy(h.stream);
         if (h.done) cudaEventDestroy(h.done);
     }
@@ -833,8 +859,30 @@ static int host_slots_init(sbwt_gpu_session* s) {
     return 0;
 }
 
+static void CUDART_CB sparse_callback(void* p) { // stream callback: no CUDA calls in here
+    HostSlot::SparseJob* j = static_cast<HostSlot::SparseJob*>(p);
+    j->pool->submit_sparse(j->masks, j->bbase, j->packed, j->n, j->dst, j->dst64, j->ticket);
+}
+
+// second half of a sparse-format chunk: the hit count has arrived, fetch exactly that many hits and hand the three
+// pieces to the pool. Called one chunk late, so that the device already has the next chunk's work queued.
+static int slot_back(HostSlot& h) {
+    if (!h.back_pending) return 0;
+    h.back_pending = false;
+    CU(cudaEventSynchronize(h.ev_small));
+    const unsigned long long total = *h.h_total;
+    if (total > h.sparse_job.n) return set_error("sparse result format: %llu hits reported for %zu results", total, h.sparse_job.n);
+    const int32_t* d_packed = reinterpret_cast<const int32_t*>(h.d_out) + h.sc.max_bases;
+    if (total) CU(cudaMemcpyAsync(h.h_out32, d_packed, (size_t)total * 4, cudaMemcpyDeviceToHost, h.stream));
+    h.widen_pool = h.sparse_job.pool;
+    CU(cudaLaunchHostFunc(h.stream, sparse_callback, &h.sparse_job));
+    CU(cudaEventRecord(h.done, h.stream));
+    return 0;
+}
+
 static int slot_finish(HostSlot& h) {
     if (!h.busy) return 0;
+    if (slot_back(h)) return 1;
     CU(cudaEventSynchronize(h.done)); // the widening job (if any) was submitted by a callback that precedes this event
     if (h.widen_pool) {
         h.widen_pool->wait(&h.widen_ticket);
@@ -887,13 +935,17 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
     const int64_t k = ix->k;
     // int64 results of a narrow index leave the device as int32 and are widened on the host (host_widen.hpp)
     bool widen = false;
-    if (!out32 && !ix->view.wide && ix->n_nodes < (1ll << 31)) {
+    bool sparse = false; // sparse wire format: hit masks + hits only (SBWT_B200_WIRE=dense turns it off)
+    if (!ix->view.wide && ix->n_nodes < (1ll << 31)) {
         if (s->widen_threads < 0) s->widen_threads = widen_thread_count();
         if (s->widen_threads > 0 && !s->widen_pool) s->widen_pool = new WidenPool(s->widen_threads);
-        widen = s->widen_pool != nullptr;
+        widen = !out32 && s->widen_pool != nullptr;
+        const char* we = getenv("SBWT_B200_WIRE");
+        sparse = s->widen_pool != nullptr && !(we && strcmp(we, "dense") == 0);
     }
     int64_t r0 = 0, out_pos = 0;
     int turn = 0;
+    HostSlot* prev = nullptr; // the slot of the previous chunk, whose second half (sparse format) is still to be issued
     while (r0 < n_reads) {
         // largest chunk [r0, r1) that fits the session capacity
         int64_t r1 = r0, bases = 0;
@@ -924,9 +976,48 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
         }
         CU(cudaMemcpyAsync(h.d_ascii, src, (size_t)bases, cudaMemcpyHostToDevice, h.stream));
         CU(cudaMemcpyAsync(h.d_offsets, osrc, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, h.stream));
-        if (run_device_batch(s, h.sc, h.d_ascii, h.d_offsets, nr, bases, mode, case_mode, h.d_out, out32 || widen, false, h.stream)) return 1;
+        if (run_device_batch(s, h.sc, h.d_ascii, h.d_offsets, nr, bases, mode, case_mode, h.d_out, out32 || widen || sparse, false, h.stream)) return 1;
+        if (sparse) {
+            h.out_staged = false; h.out_bytes = 0;
+            if (n_out) {
+                const int64_t cap = std::max<int64_t>(s->max_bases, 1);
+                const int64_t n_groups = (n_out + 31) / 32, n_sblocks = (n_out + kSparseBlock - 1) / kSparseBlock;
+                if (!h.d_masks) {
+                    CU(cudaMalloc(&h.d_masks, (size_t)(cap / 32 + 2) * 4));
+                    CU(cudaMalloc(&h.d_bbase, (size_t)(cap / kSparseBlock + 2) * 4));
+                    CU(cudaMalloc(&h.d_total, 8));
+                    CU(cudaMallocHost(&h.h_masks, (size_t)(cap / 32 + 2) * 4));
+                    CU(cudaMallocHost(&h.h_bbase, (size_t)(cap / kSparseBlock + 2) * 4));
+                    CU(cudaMallocHost(&h.h_total, 8));
+                    CU(cudaEventCreateWithFlags(&h.ev_small, cudaEventDisableTiming));
+                }
+                if (!h.h_out32) CU(cudaMallocHost(&h.h_out32, (size_t)cap * 4 + 64)); // (+64: the mixed-group expansion reads 8 values at a time)
+                int32_t* d32 = reinterpret_cast<int32_t*>(h.d_out);
+                CU(cudaMemsetAsync(h.d_total, 0, 8, h.stream));
+                sparse_pack_kernel<<<(unsigned)n_sblocks, 256, 0, h.stream>>>(d32, n_out, h.d_masks, d32 + cap, h.d_bbase, h.d_total); LAUNCHED();
+                CU(cudaGetLastError());
+                CU(cudaMemcpyAsync(h.h_masks, h.d_masks, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, h.stream));
+                CU(cudaMemcpyAsync(h.h_bbase, h.d_bbase, (size_t)n_sblocks * 4, cudaMemcpyDeviceToHost, h.stream));
+                CU(cudaMemcpyAsync(h.h_total, h.d_total, 8, cudaMemcpyDeviceToHost, h.stream));
+                CU(cudaEventRecord(h.ev_small, h.stream));
+                HostSlot::SparseJob& j = h.sparse_job;
+                j.pool = s->widen_pool; j.masks = h.h_masks; j.bbase = h.h_bbase; j.packed = h.h_out32; j.n = (size_t)n_out;
+                j.dst = out32 ? (void*)((int32_t*)out + out_pos) : (void*)((int64_t*)out + out_pos);
+                j.dst64 = !out32; j.ticket = &h.widen_ticket;
+                h.back_pending = true;
+            } else {
+                CU(cudaEventRecord(h.done, h.stream));
+            }
+            h.busy = true;
+            // the previous chunk's hits are fetched now that this chunk's kernels are queued behind them
+            if (prev && prev != &h && slot_back(*prev)) return 1;
+            prev = &h;
+            out_pos += n_out;
+            r0 = r1;
+            continue;
+        }
         if (widen) {
-            if (!h.h_out32) CU(cudaMallocHost(&h.h_out32, std::max<int64_t>(s->max_bases, 1) * 4));
+            if (!h.h_out32) CU(cudaMallocHost(&h.h_out32, std::max<int64_t>(s->max_bases, 1) * 4 + 64));
             h.out_staged = false; h.out_bytes = 0;
             if (n_out) {
                 // the result copy goes piece by piece, each piece handed to the pool as soon as it has landed: the
@@ -987,6 +1078,18 @@ extern "C" int sbwt_gpu_widen_i32(const int32_t* in, int64_t* out, int64_t n, in
     WidenPool pool(threads);
     WidenTicket t;
     pool.submit(in, out, (size_t)n, &t);
+    pool.wait(&t);
+    return 0;
+}
+
+extern "C" int sbwt_gpu_expand_sparse(const uint32_t* masks, const uint32_t* block_base, const int32_t* packed, int64_t n, void* out,
+                                      int out_is_i64, int threads) {
+    if (n < 0 || threads < 1 || threads > 64) return set_error("sbwt_gpu_expand_sparse: n >= 0 and 1 <= threads <= 64 expected");
+    if (n == 0) return 0;
+    if (!masks || !block_base || !out || !packed) return set_error("null buffer");
+    WidenPool pool(threads);
+    WidenTicket t;
+    pool.submit_sparse(masks, block_base, packed, (size_t)n, out, out_is_i64 != 0, &t);
     pool.wait(&t);
     return 0;
 }

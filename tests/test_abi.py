@@ -92,3 +92,52 @@ def test_widen_i32_host_step():
         assert np.array_equal(out, v.astype(np.int64))
     with pytest.raises(sbwt_b200.SbwtGpuError):
         sbwt_b200.widen_i32(v, 0)
+
+
+def _sparse_pack_reference(v: np.ndarray, rng) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """What sparse_pack_kernel (aux_kernels.cuh) produces for the int32 results v, with the 4096-result blocks placed in
+    `packed` in a shuffled order (on the device the order is whatever the atomicAdd gives)."""
+    n = v.size
+    n_groups, n_blocks = (n + 31) // 32, (n + 4095) // 4096
+    hit = np.zeros(n_groups * 32, dtype=bool)
+    hit[:n] = v >= 0
+    masks = (hit.reshape(n_groups, 32).astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+    counts = [int((v[b * 4096:(b + 1) * 4096] >= 0).sum()) for b in range(n_blocks)]
+    order = rng.permutation(n_blocks)
+    base = np.zeros(n_blocks, dtype=np.uint32)
+    packed = np.zeros(max(1, sum(counts)), dtype=np.int32)
+    pos = 0
+    for b in order:
+        base[b] = pos
+        blk = v[b * 4096:(b + 1) * 4096]
+        packed[pos:pos + counts[b]] = blk[blk >= 0]
+        pos += counts[b]
+    return masks, base, packed
+
+
+def test_expand_sparse_host_step():
+    """The host half of the sparse result wire format rebuilds exactly the device's int32 results, as int64 or int32:
+    mixed groups, long runs of hits and of misses (the run primitives), ragged tails, unaligned destinations."""
+    rng = np.random.default_rng(11)
+    for n in (1, 31, 32, 33, 4095, 4096, 4097, 70_000, 300_007):
+        for style in ("mixed", "runs", "all_hit", "all_miss"):
+            v = rng.integers(0, 2**31 - 1, size=n, dtype=np.int64).astype(np.int32)
+            if style == "mixed":
+                v[rng.random(n) < 0.5] = -1
+            elif style == "runs":  # reads of 120 results, found or absent as a whole
+                for s0 in range(0, n, 120):
+                    if rng.random() < 0.5:
+                        v[s0:s0 + 120] = -1
+            elif style == "all_miss":
+                v[:] = -1
+            masks, base, packed = _sparse_pack_reference(v, rng)
+            for threads in (1, 5):
+                assert np.array_equal(sbwt_b200.expand_sparse(masks, base, packed, n, np.int64, threads), v.astype(np.int64)), (n, style)
+                assert np.array_equal(sbwt_b200.expand_sparse(masks, base, packed, n, np.int32, threads), v), (n, style)
+            for shift in (1, 3):
+                buf = np.full(n + 4, -7, dtype=np.int64)
+                sbwt_b200.expand_sparse(masks, base, packed, n, threads=3, out=buf[shift:shift + n])
+                assert np.array_equal(buf[shift:shift + n], v.astype(np.int64)) and buf[shift - 1] == -7 and buf[shift + n] == -7
+                buf32 = np.full(n + 4, -7, dtype=np.int32)
+                sbwt_b200.expand_sparse(masks, base, packed, n, threads=3, out=buf32[shift:shift + n])
+                assert np.array_equal(buf32[shift:shift + n], v) and buf32[shift - 1] == -7 and buf32[shift + n] == -7

@@ -249,7 +249,7 @@ def test_search_table_lengths(tmp_path):
         assert idx.table_length >= file_p
         np.testing.assert_array_equal(idx.precalc().reshape(-1), read_sbwt(golden(name, "index.sbwt"))["precalc"].reshape(-1))
         ses = S.Session(idx, a.size, len(reads))
-        for tp in (0, 1, file_p, 5, 8, 9, 11, 12):
+        for tp in (0, 1, file_p, 5, 8, 9, 11, 12) + ((13, 14) if name == "small_k31" else ()):
             idx.set_table_length(tp)
             assert idx.table_length == min(tp, idx.k)
             for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
@@ -429,11 +429,15 @@ def test_probe_strides_give_identical_results(stride, tmp_path, monkeypatch):
         np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("wire", ["dense", "sparse"])
 @pytest.mark.parametrize("threads", ["0", "1", "5"])
-def test_result_wire_formats_of_the_host_pipeline(threads, monkeypatch):
-    """sbwt_gpu_query_host returns int64 either copied as such (SBWT_B200_WIDEN_THREADS=0) or copied as int32 and
-    sign-extended by host threads (host_widen.hpp); same values, pinned or pageable buffers, many chunks in flight."""
+def test_result_wire_formats_of_the_host_pipeline(threads, wire, monkeypatch):
+    """sbwt_gpu_query_host returns int64 either copied as such (SBWT_B200_WIDEN_THREADS=0), or copied as int32 and
+    sign-extended by host threads (dense), or as hit masks + hits only, rebuilt by host threads (sparse; host_widen.hpp).
+    Same values every way, int64 and int32 API, pinned or pageable buffers, many chunks in flight, chunks that are all
+    hits, all misses, empty, and destinations off the 32-byte grid."""
     monkeypatch.setenv("SBWT_B200_WIDEN_THREADS", threads)
+    monkeypatch.setenv("SBWT_B200_WIRE", wire)
     for name in ("small_k31", "small_k63_rc"):
         vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
         reads = read_fasta_reads(golden(name, "reads.fna"))
@@ -442,11 +446,31 @@ def test_result_wire_formats_of_the_host_pipeline(threads, monkeypatch):
         ses = S.Session(idx, max_bases=3000, max_reads=11)  # dozens of chunks over the three pipeline slots
         for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
             np.testing.assert_array_equal(ses.query_host(a, off, mode), vals)
+            np.testing.assert_array_equal(ses.query_host_i32(a, off, mode).astype(np.int64), vals)
             out = S.pinned_empty(vals.size + 1, np.int64)
             out[:] = -7
             got = ses.query_host(a, off, mode, out=out[1:])  # destination off the 32-byte grid
             np.testing.assert_array_equal(got, vals)
             assert out[0] == -7
+            out32 = S.pinned_empty(vals.size + 3, np.int32)
+            out32[:] = -7
+            got = ses.query_host_i32(a, off, mode, out=out32[3:])
+            np.testing.assert_array_equal(got.astype(np.int64), vals)
+            assert (out32[:3] == -7).all()
+        ses.close()
+        # larger chunks: several 4096-result blocks per chunk, runs of found reads, absent reads and reads too short for a k-mer
+        rng = np.random.default_rng(21)
+        big = []
+        for i in range(600):
+            r = reads[int(rng.integers(0, len(reads)))]
+            kind = rng.random()
+            big.append(r if kind < 0.5 else (bytes(synth.LUT[rng.integers(0, 4, size=len(r), dtype=np.uint8)]) if kind < 0.9 else r[:5]))
+        a2, off2 = synth.ragged_to_batch(big)
+        want = oracle.OracleIndex(golden(name, "index.sbwt")).query_batch(a2, off2, streaming=True)
+        ses = S.Session(idx, max_bases=40_000, max_reads=1000)
+        for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+            np.testing.assert_array_equal(ses.query_host(a2, off2, mode), want)
+            np.testing.assert_array_equal(ses.query_host_i32(a2, off2, mode).astype(np.int64), want)
         ses.close()
         idx.close()
 

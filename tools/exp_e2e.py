@@ -32,8 +32,14 @@ ref_out = None
 SETS = {
     "main": [(t, c, p) for t in (16, 12, 8, 6) for c in (96, 48, 24) for p in (4, 1, 64)],
     "quick": [(16, 96, 4), (12, 96, 4), (8, 96, 4), (12, 48, 4), (12, 96, 1), (12, 96, 64), (0, 96, 4)],
+    # (threads, chunk, piece, wire)
+    "wire": [(8, 48, 64, "dense"), (8, 48, 64, "sparse"), (12, 48, 64, "sparse"), (16, 48, 64, "sparse"), (6, 48, 64, "sparse"),
+             (8, 96, 64, "sparse"), (8, 24, 64, "sparse"), (8, 12, 64, "sparse")],
 }
-for threads, chunk_m, piece_m in SETS[which]:
+for cfg in SETS[which]:
+    threads, chunk_m, piece_m = cfg[:3]
+    wire = cfg[3] if len(cfg) > 3 else os.environ.get("SBWT_B200_WIRE", "sparse")
+    os.environ["SBWT_B200_WIRE"] = wire
     os.environ["SBWT_B200_WIDEN_THREADS"] = str(threads)
     os.environ["SBWT_B200_D2H_PIECE"] = str(piece_m << 20)
     chunk = chunk_m * 1_000_000
@@ -53,6 +59,6 @@ for threads, chunk_m, piece_m in SETS[which]:
         t0 = time.perf_counter()
         ses.query_host_i32(h_a, h_off, mode, out=h_out32)
         t32.append(time.perf_counter() - t0)
-    print(f"{name} widen_threads={threads:2d} chunk_Mbases={chunk_m:3d} piece_Mvalues={piece_m:3d} int64_ms={min(ts) * 1e3:8.2f} "
+    print(f"{name} wire={wire:6s} widen_threads={threads:2d} chunk_Mbases={chunk_m:3d} piece_Mvalues={piece_m:3d} int64_ms={min(ts) * 1e3:8.2f} "
           f"({' '.join('%.1f' % (t * 1e3) for t in ts)}) -> {n_out / min(ts) / 1e9:6.2f} G lookups/s ; i32_ms={min(t32) * 1e3:8.2f}", flush=True)
     ses.close()

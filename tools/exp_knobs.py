@@ -40,6 +40,7 @@ SETS = {
            dict(SBWT_B200_DEBUG_NOSTORE=2)],
     "base": [dict()],
     "tp": [dict(), dict(tp=11), dict(tp=12), dict(tp=13)],
+    "tp14": [dict(), dict(tp=12), dict(tp=14)],
     "compact": [dict(), dict(tp=9), dict(tp=11), dict(tp=12), dict(SBWT_B200_BLOCKS_PER_SM=3), dict(out32=1), dict(SBWT_B200_PROBE=14), dict(SBWT_B200_PROBE=20)],
     "frac": [dict()] + [dict(SBWT_B200_L2_EVICT_LAST=m, SBWT_B200_L2_FRAC=f) for m in (2, 3) for f in (0.9, 0.75, 0.6, 0.45)]
             + [dict(SBWT_B200_L2_EVICT_LAST=2, SBWT_B200_L2_FRAC=f, SBWT_B200_DEBUG_NOSTORE=1) for f in (1.0, 0.75, 0.5)],
