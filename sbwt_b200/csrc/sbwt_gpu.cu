@@ -382,12 +382,13 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
         const char* e = getenv("SBWT_B200_TABLE_P");
         if (e) tp = atoi(e);
         else {
-            // longest table (<= 13 characters: 537 MB of 8-byte rows) with at most 2 rows per column of the index. A row
+            // longest table (<= 14 characters: 2.1 GB of 8-byte rows) with at most 4 rows per column of the index. A row
             // is read once per from-scratch search and replaces one dependent interval step per extra character; every
-            // workload measured faster with each character up to 13 although the table then dwarfs the sector array and
-            // lives in HBM (profiles/r01n_table_length.txt: c2 10.86 -> 9.81 ms, c3 71.0 -> 65.7, c4s 20.4 -> 18.7, c5s 17.9 -> 16.3)
-            tp = (int)std::min<int64_t>(std::max<int64_t>(p, 13), k);
-            while (tp > p && (1ll << (2 * tp)) > std::max<int64_t>(2 * n_nodes, 1 << 16)) tp--;
+            // workload measured faster with each character up to 14 although the table then dwarfs the sector array and
+            // lives in HBM (profiles/r01n_table_length.txt: c2 10.86 -> 9.73 -> 8.86 ms for 10 / 13 / 14 characters,
+            // c4s 20.4 -> 18.8 -> 17.8 ms)
+            tp = (int)std::min<int64_t>(std::max<int64_t>(p, 14), k);
+            while (tp > p && (1ll << (2 * tp)) > std::max<int64_t>(4 * n_nodes, 1 << 16)) tp--;
         }
     }
     if (int rc = sbwt_gpu_index_set_table_length(ix, tp)) { sbwt_gpu_index_destroy(ix); return rc; }
