@@ -194,6 +194,9 @@ static int64_t run_file(const string& infile, const string& outfile, const sbwt:
             ahead.join();
             if (!sink.error.empty()) throw std::runtime_error(sink.error);
             throw;
+        } catch (...) {
+            ahead.join();
+            throw;
         }
         query_micros += cur_time_micros() - t0;
         ahead.join();
