@@ -215,6 +215,15 @@ int64_t sbwt_gpu_launch_count(int reset);
 int sbwt_gpu_sector_probe(int device, int64_t buffer_bytes, int64_t n_loads, int bytes_per_load,
                           int iters, double *best_ms);
 
+/* Multi-GPU inside one process (the reference is single-threaded; this is the batched form of running
+ * run_queries_streaming / run_queries_not_streaming, sbwt_search.cpp:45-91, over several devices): `sessions`
+ * are sessions on replicas of ONE index, normally one per device (sbwt_gpu_index_load(path, device = d)). The
+ * reads are cut into n_sessions contiguous ranges of (almost) equal total bases, one host thread per session
+ * answers its range with sbwt_gpu_query_host, and the results land in order in `out` -- exactly what one
+ * sbwt_gpu_query_host call over the whole batch returns. No collective, nothing is exchanged between devices. */
+int sbwt_gpu_query_host_sharded(sbwt_gpu_session *const *sessions, int n_sessions, const char *ascii,
+                                const int64_t *read_offsets, int64_t n_reads, int mode, int case_mode, int64_t *out);
+
 /* Host half of the 32-bit result wire format (no device work): sbwt_gpu_query_host on an index with fewer
  * than 2^31 columns lets the kernel write int32, copies those over PCIe and sign-extends them into the
  * caller's int64 array with `threads` host threads (SBWT_B200_WIDEN_THREADS; default = hardware threads /

@@ -33,7 +33,7 @@ EXPORTS = [
     "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
     "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
     "sbwt_gpu_index_set_table_length", "sbwt_gpu_index_table_length",
-    "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text", "sbwt_gpu_widen_i32", "sbwt_gpu_expand_sparse", "sbwt_gpu_session_widen_threads",
+    "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text", "sbwt_gpu_widen_i32", "sbwt_gpu_expand_sparse", "sbwt_gpu_session_widen_threads", "sbwt_gpu_query_host_sharded",
 ]
 
 TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
@@ -96,6 +96,7 @@ def lib():
         L.sbwt_gpu_launch_count.restype = i64
         L.sbwt_gpu_sector_probe.argtypes = [i32, i64, i64, i32, i32, C.POINTER(C.c_double)]
         L.sbwt_gpu_widen_i32.argtypes = [vp, vp, i64, i32]
+        L.sbwt_gpu_query_host_sharded.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp]
         L.sbwt_gpu_expand_sparse.argtypes = [vp, vp, vp, i64, vp, i32, i32]
         L.sbwt_gpu_session_widen_threads.argtypes = [vp]
         L.sbwt_gpu_text_capacity.argtypes = [vp, i64, i64]
@@ -337,6 +338,21 @@ def widen_i32(values: np.ndarray, threads: int = 4) -> np.ndarray:
     out = np.empty(values.size, dtype=np.int64)
     _check(lib().sbwt_gpu_widen_i32(values.ctypes.data, out.ctypes.data, values.size, threads))
     return out
+
+
+def query_host_sharded(sessions: list, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER,
+                       out: np.ndarray | None = None) -> np.ndarray:
+    """One batch over several sessions (replicas of one index, normally one per GPU): sbwt_gpu_query_host_sharded."""
+    ascii_ = np.ascontiguousarray(ascii_, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n_out = lib().sbwt_gpu_count_outputs(offsets.ctypes.data, offsets.size - 1, sessions[0].index.k)
+    if out is None:
+        out = np.empty(n_out, dtype=np.int64)
+    assert out.dtype == np.int64 and out.size >= n_out
+    handles = (C.c_void_p * len(sessions))(*[s._h for s in sessions])
+    _check(lib().sbwt_gpu_query_host_sharded(handles, len(sessions), ascii_.ctypes.data, offsets.ctypes.data, offsets.size - 1, mode,
+                                            case_mode, out.ctypes.data))
+    return out[:n_out]
 
 
 def expand_sparse(masks: np.ndarray, block_base: np.ndarray, packed: np.ndarray, n: int, dtype=np.int64, threads: int = 4,

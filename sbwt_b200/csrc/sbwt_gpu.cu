@@ -7,6 +7,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -1070,6 +1071,56 @@ extern "C" int sbwt_gpu_query_host_i32(sbwt_gpu_session* s, const char* ascii, c
     if (s && (s->idx->n_nodes >= (1ll << 31) || s->idx->view.wide))
         return set_error("int32 results need an index with fewer than 2^31 columns (this one has %lld)", (long long)s->idx->n_nodes);
     return query_host_impl(s, ascii, off, n_reads, mode, case_mode, out, true);
+}
+
+// Multi-GPU in one process: the index is replicated (one session per device, made by the caller),
+// the reads are cut into contiguous ranges of (almost) equal total bases -- the split of sbwt_b200/sharding.py --
+// and one host thread per session answers its range into its own slice of `out`. No collective, nothing is exchanged.
+extern "C" int sbwt_gpu_query_host_sharded(sbwt_gpu_session* const* sessions, int n_sessions, const char* ascii, const int64_t* off,
+                                           int64_t n_reads, int mode, int case_mode, int64_t* out) {
+    if (!sessions || n_sessions < 1 || n_sessions > 64) return set_error("sbwt_gpu_query_host_sharded: 1 <= n_sessions <= 64 expected");
+    for (int i = 0; i < n_sessions; i++) {
+        if (!sessions[i]) return set_error("null session");
+        if (sessions[i]->idx->k != sessions[0]->idx->k || sessions[i]->idx->n_nodes != sessions[0]->idx->n_nodes)
+            return set_error("sbwt_gpu_query_host_sharded: the sessions must hold replicas of one index");
+        for (int j = 0; j < i; j++)
+            if (sessions[j] == sessions[i]) return set_error("sbwt_gpu_query_host_sharded: a session is listed twice");
+    }
+    if (n_reads < 0) return set_error("negative batch size");
+    if (n_reads == 0) return 0;
+    if (!ascii || !off || !out) return set_error("null buffer");
+    const int64_t k = sessions[0]->idx->k;
+    // cuts[i] = first read of shard i: the first read starting at or after the i-th equal share of the bases
+    std::vector<int64_t> cuts((size_t)n_sessions + 1, n_reads);
+    cuts[0] = 0;
+    const int64_t total = off[n_reads] - off[0];
+    for (int i = 1; i < n_sessions; i++) {
+        const int64_t target = off[0] + (int64_t)((__int128)total * i / n_sessions);
+        cuts[(size_t)i] = std::max<int64_t>(cuts[(size_t)i - 1], std::lower_bound(off, off + n_reads + 1, target) - off);
+        cuts[(size_t)i] = std::min(cuts[(size_t)i], n_reads);
+    }
+    std::vector<int64_t> out_pos((size_t)n_sessions + 1, 0);
+    for (int i = 0; i < n_sessions; i++)
+        out_pos[(size_t)i + 1] = out_pos[(size_t)i] + sbwt_gpu_count_outputs(off + cuts[(size_t)i], cuts[(size_t)i + 1] - cuts[(size_t)i], k);
+    std::vector<int> rc((size_t)n_sessions, 0);
+    std::vector<std::string> err((size_t)n_sessions);
+    std::vector<int64_t> launches((size_t)n_sessions, 0);
+    std::vector<std::thread> th;
+    auto work = [&](int i) {
+        const int64_t r0 = cuts[(size_t)i], nr = cuts[(size_t)i + 1] - r0;
+        if (nr == 0) return;
+        const int64_t before = g_launches; // (thread-local, like the error text)
+        rc[(size_t)i] = query_host_impl(sessions[i], ascii, off + r0, nr, mode, case_mode, out + out_pos[(size_t)i], false);
+        if (rc[(size_t)i]) err[(size_t)i] = g_last_error;
+        launches[(size_t)i] = g_launches - before;
+    };
+    for (int i = 1; i < n_sessions; i++) th.emplace_back(work, i);
+    work(0);
+    for (std::thread& t : th) t.join();
+    for (int i = 1; i < n_sessions; i++) g_launches += launches[(size_t)i];
+    for (int i = 0; i < n_sessions; i++)
+        if (rc[(size_t)i]) return set_error("shard %d (device %d): %s", i, sessions[i]->idx->device, err[(size_t)i].c_str());
+    return 0;
 }
 
 extern "C" int sbwt_gpu_widen_i32(const int32_t* in, int64_t* out, int64_t n, int threads) {

@@ -157,3 +157,9 @@ def test_cpp_mirror_header_compiles_and_links(tmp_path):
         run = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "small_k31", "index.sbwt"), str(tmp_path / "o.sbwt"), "ACGT" * 20],
                              capture_output=True, text=True)
         assert run.returncode != 0 and "no CUDA device" in (run.stdout + run.stderr)
+
+
+def test_sharded_entry_rejects_bad_arguments_without_a_device():
+    L = sbwt_b200.lib()
+    assert L.sbwt_gpu_query_host_sharded(None, 0, None, None, 0, 0, 0, None) != 0
+    assert b"n_sessions" in L.sbwt_gpu_last_error()

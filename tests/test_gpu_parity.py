@@ -539,3 +539,35 @@ def test_compact_one_hot_layout_gives_identical_results(mode, tmp_path, monkeypa
     res = run_both(ix, reads)
     np.testing.assert_array_equal(res[S.MODE_STREAMING], want)
     np.testing.assert_array_equal(res[S.MODE_SEARCH], want)
+
+
+def test_sharded_query_over_several_sessions():
+    """sbwt_gpu_query_host_sharded: one batch cut into contiguous ranges of equal base count, one host thread per session
+    (on a multi-GPU box one session per device; here replicas on whatever devices exist, several per device if need be),
+    results in order in the caller's array -- equal to one sbwt_gpu_query_host call, empty shards and tiny batches included."""
+    n_dev = S.device_count()
+    for name in ("small_k31", "small_k63_rc"):
+        vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+        reads = read_fasta_reads(golden(name, "reads.fna"))
+        a, off = synth.ragged_to_batch(reads)
+        for n_ses in (1, 2, 3, 5):
+            idxs = [S.Index(golden(name, "index.sbwt"), device=i % n_dev) for i in range(n_ses)]
+            sess = [S.Session(ix, max_bases=20_000, max_reads=500) for ix in idxs]
+            for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+                np.testing.assert_array_equal(S.query_host_sharded(sess, a, off, mode), vals)
+            # fewer reads than sessions: some shards are empty
+            a1, off1 = synth.ragged_to_batch(reads[:2])
+            want1 = sess[0].query_host(a1, off1, S.MODE_STREAMING).copy()
+            np.testing.assert_array_equal(S.query_host_sharded(sess, a1, off1, S.MODE_STREAMING), want1)
+            for s_ in sess:
+                s_.close()
+            for ix in idxs:
+                ix.close()
+    idx = S.Index(golden("small_k31", "index.sbwt"))
+    ses = S.Session(idx, 1000, 10)
+    with pytest.raises(S.SbwtGpuError, match="listed twice"):
+        S.query_host_sharded([ses, ses], a, off, S.MODE_STREAMING)
+    other = S.Index(golden("small_k63_rc", "index.sbwt"))
+    ses2 = S.Session(other, 1000, 10)
+    with pytest.raises(S.SbwtGpuError, match="replicas of one index"):
+        S.query_host_sharded([ses, ses2], a, off, S.MODE_STREAMING)
