@@ -5,12 +5,16 @@ A "step" is one pass of the hot path (pack -> plan -> walk) over one batch of sy
 Default workload = BASELINE.json configs[1] ("c2"): 100 Mbp random-DNA reference, k=31
 plain-matrix index with streaming support (p=8), 10 M x 150 bp reads at 50 % hit rate,
 streaming_search. `--workload c3` is the same index without streaming support (per-k-mer
-search), `--workload c4s` a scaled pangenome-like index (+RC) that exceeds L2.
+search), `--workload c4s` / `c5s` a scaled pangenome-like index (+RC, k = 31 / 63) that exceeds L2.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4s] [--reads R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4s|c5s|tiny] [--reads R]
 
 Prints ONE JSON line (rank 0). `value` is measured with inputs resident in HBM, `e2e` through
-sbwt_gpu_query_host with pinned HOST buffers (H2D + D2H inside the timed region).
+sbwt_gpu_query_host with pinned HOST buffers (H2D + D2H inside the timed region). `roofline` carries the
+counted algorithmic sector bytes of the walk kernel against the measured HBM copy peak, the DRAM bytes one
+launch really moves (profiles/traffic.json, from ncu), the measured random-sector ceilings and the same kernel
+timed with the shorter search table; `cpu_baseline` is the reference's own query code on the host cores.
+`--impl reference` runs only that (the reference arm of the contract).
 Multi-GPU (torchrun, one rank per GPU): the index is replicated, every rank answers its own
 shard of reads, no collective on the data path (weak scaling); NCCL is used only for the
 barrier and the max-over-ranks of the timing the contract asks for.
