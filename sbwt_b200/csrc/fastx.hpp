@@ -63,18 +63,26 @@ class FastxReader {
     FILE* fp = nullptr;
     gzFile gzf = nullptr;
     std::vector<char> buf;
-    const char* mem = nullptr; // memory source (ParallelFastxReader's fallback): [mem, mem + mem_len)
+    const char* mem = nullptr; // memory source (ParallelFastxReader's fallback): [mem, mem + mem_len) ...
     size_t mem_len = 0, mem_pos = 0;
+    gzFile cont = nullptr;     // ... continued, when it is used up, by the rest of this gzip stream (not owned)
     size_t pos = 0, size = 0;
     size_t taken = 0;    // bytes handed out by get() before the current buffer
     bool is_eof = false; // true once a get() ran past the end (Buffered_ifstream::eof)
 
     bool refill() {
         taken += size;
-        if (mem) {
+        if (mem && mem_pos < mem_len) {
             size = std::min(buf.size(), mem_len - mem_pos);
             memcpy(buf.data(), mem + mem_pos, size);
             mem_pos += size;
+        } else if (mem) {
+            size = 0;
+            if (cont) {
+                int n = gzread(cont, buf.data(), (unsigned)buf.size());
+                if (n < 0) throw std::runtime_error("Error reading gzip file " + filename);
+                size = (size_t)n;
+            }
         } else if (gz) {
             int n = gzread(gzf, buf.data(), (unsigned)buf.size());
             if (n < 0) throw std::runtime_error("Error reading gzip file " + filename);
@@ -121,8 +129,8 @@ public:
     }
     // Serial parser over a memory range that starts at a record (whose first byte is consumed here, like the
     // look-ahead get() at the end of next_read does); `filename` only feeds the error messages.
-    FastxReader(const std::string& filename, SeqFormat format, const char* mem, size_t len)
-        : filename(filename), format(format), gz(false), buf(1 << 20), mem(mem), mem_len(len) {
+    FastxReader(const std::string& filename, SeqFormat format, const char* mem, size_t len, gzFile cont = nullptr)
+        : filename(filename), format(format), gz(false), buf(1 << 20), mem(mem ? mem : ""), mem_len(len), cont(cont) {
         char c = 0;
         get(c);
     }
@@ -202,8 +210,34 @@ class ParallelFastxReader {
     int fd = -1;
     const char* data = nullptr;
     size_t size = 0, cur = 0; // cur: first byte of the next record
-    std::unique_ptr<FastxReader> serial; // gzip input, or the fallback after an anomaly
-    size_t serial_origin = 0;
+    std::unique_ptr<FastxReader> serial; // the fallback after an anomaly (or for inputs that cannot be mapped)
+    // gzip input: the stream is inflated (sequentially: a deflate stream cannot be entered in the middle) into a sliding
+    // buffer; data / size / cur then refer to that buffer and the parsing is the same parallel code
+    gzFile gzf = nullptr;
+    std::vector<char> zbuf;
+    bool z_eof = false;
+    bool all_here = true; // everything up to the end of the input is in [data, data + size)
+
+    // make at least `want` bytes after `cur` available (or reach the end of the stream)
+    void z_fill(size_t want) {
+        if (!gzf) return;
+        if (cur > 0 && cur == size) { size = 0; cur = 0; }
+        if (cur > ((size_t)64 << 20)) { // drop what has been consumed
+            memmove(zbuf.data(), zbuf.data() + cur, size - cur);
+            size -= cur;
+            cur = 0;
+        }
+        while (!z_eof && size - cur < want) {
+            const size_t step = (size_t)16 << 20;
+            if (zbuf.size() < size + step) zbuf.resize(std::max(zbuf.size() * 2, size + step));
+            const int n = gzread(gzf, zbuf.data() + size, (unsigned)step);
+            if (n < 0) throw std::runtime_error("Error reading gzip file " + filename);
+            if (n == 0) z_eof = true;
+            size += (size_t)n;
+        }
+        data = zbuf.data();
+        all_here = z_eof;
+    }
 
     struct Line {
         size_t start, end; // [start, end): without the '\n'
@@ -250,8 +284,14 @@ public:
     ParallelFastxReader(const std::string& filename, int threads) : filename(filename), threads(std::max(1, threads)) {
         const FileFormat ff = figure_out_file_format(filename);
         format = ff.format;
-        if (ff.gzipped) { // a gzip stream is sequential
-            serial.reset(new FastxReader(filename));
+        if (ff.gzipped) {
+            gzf = gzopen(filename.c_str(), "rb");
+            if (!gzf) throw std::runtime_error("Error opening file " + filename);
+            gzbuffer(gzf, 1 << 20);
+            z_fill(1);
+            const char c = size ? data[0] : 0; // read_first_char_and_sanity_check, SeqIO.hh:178-189
+            if (format == SeqFormat::FASTA && c != '>') throw std::runtime_error("ERROR: FASTA file " + filename + " does not start with '>'");
+            if (format == SeqFormat::FASTQ && c != '@') throw std::runtime_error("ERROR: FASTQ file " + filename + " does not start with '@'");
             return;
         }
         fd = open(filename.c_str(), O_RDONLY);
@@ -279,7 +319,8 @@ public:
     ParallelFastxReader& operator=(const ParallelFastxReader&) = delete;
     ~ParallelFastxReader() {
         serial.reset();
-        if (data) munmap((void*)data, size);
+        if (gzf) gzclose(gzf);
+        else if (data) munmap((void*)data, size);
         if (fd >= 0) close(fd);
     }
 
@@ -289,7 +330,9 @@ public:
         ascii.clear();
         offsets.clear();
         offsets.push_back(0);
-        if (cur >= size || max_reads <= 0 || max_bases <= 0) return 0;
+        if (max_reads <= 0 || max_bases <= 0) return 0;
+        z_fill(1);
+        if (cur >= size) return 0;
         struct Rec {
             size_t first_line, n_lines; // sequence lines
             int64_t len;
@@ -300,8 +343,9 @@ public:
         bool anomaly = false;
         size_t next_cur = cur;
         for (;;) {
+            z_fill(window);
             const size_t wend = std::min(size, cur + window);
-            const bool at_eof = wend == size;
+            const bool at_eof = wend == size && all_here;
             scan_lines(cur, wend, lines);
             recs.clear();
             anomaly = false;
@@ -352,7 +396,7 @@ public:
             window *= 2; // the window ended before the batch was full
         }
         if (anomaly) {
-            serial.reset(new FastxReader(filename, format, data + cur, size - cur));
+            serial.reset(new FastxReader(filename, format, data + cur, size - cur, gzf)); // (gzip: continues with the rest of the stream)
             return from_serial(max_bases, max_reads, ascii, offsets);
         }
         const size_t n = recs.size();

@@ -63,10 +63,14 @@ def test_wellformed_files_give_identical_batches(exe, tmp_path, kind):
             "fa_crlf": lambda: fasta(rng, 500, True, crlf=True), "fq_crlf": lambda: fastq(rng, 500, crlf=True)}[kind]()
     path = str(tmp_path / ("x.fq" if kind.startswith("fq") else "x.fna"))
     open(path, "wb").write(data)
+    with gzip.open(path + ".gz", "wb", compresslevel=1) as f:  # the same bytes through the inflate-ahead path
+        f.write(data)
     for max_bases, max_reads, threads in [(1 << 30, 1 << 30, 4), (5000, 1 << 30, 3), (1, 1 << 30, 2), (1 << 30, 7, 8), (100_000, 100, 1), (333, 5, 5)]:
         a, b = both(exe, path, max_bases, max_reads, threads)
         assert not a.startswith("ERROR"), a
         assert a == b, (kind, max_bases, max_reads, threads)
+        az, bz = both(exe, path + ".gz", max_bases, max_reads, threads)
+        assert az == a and bz == a, (kind, "gz", max_bases, max_reads, threads)
 
 
 def test_long_reads_exceed_the_scan_window(exe, tmp_path):
@@ -78,9 +82,13 @@ def test_long_reads_exceed_the_scan_window(exe, tmp_path):
             f.write(b">c%d\n" % i)
             for j in range(0, len(s), 70):
                 f.write(s[j:j + 70] + b"\n")
+    with open(path, "rb") as f, gzip.open(path + ".gz", "wb", compresslevel=1) as g:
+        g.write(f.read())
     for mb in (10, 1_000_000, 1 << 30):
         a, b = both(exe, path, mb, 1 << 30, 4)
         assert not a.startswith("ERROR") and a == b
+        az, bz = both(exe, path + ".gz", mb, 1 << 30, 4)
+        assert az == a and bz == a
 
 
 BAD = {
@@ -111,12 +119,31 @@ def test_malformed_files_fail_or_parse_exactly_like_the_serial_reader(exe, tmp_p
         if name.startswith("fa_wrong") or name.startswith("fq_wrong") or name.startswith("empty"):
             prefix = b""
         open(path, "wb").write(prefix + BAD[name])
+        with gzip.open(path + ".gz", "wb") as f:
+            f.write(prefix + BAD[name])
         for max_bases, max_reads, threads in [(1 << 30, 1 << 30, 4), (50, 1 << 30, 2), (1 << 30, 1, 3)]:
             a, b = both(exe, path, max_bases, max_reads, threads)
             assert a == b, (name, a, b)
+            az, bz = both(exe, path + ".gz", max_bases, max_reads, threads)
+            assert az == bz == a.replace(name, name + ".gz"), (name, "gz", az, bz, a)
 
 
-def test_gzip_input_goes_through_the_serial_reader(exe, tmp_path):
+def test_gzip_input_large_enough_to_slide_the_buffer(exe, tmp_path):
+    """more than the 64 MB after which the inflate buffer drops what was consumed, multi-line FASTA and FASTQ"""
+    rng = np.random.default_rng(10)
+    seq = rand_seq(rng, 5_000_000)
+    path = str(tmp_path / "big.fna.gz")
+    with gzip.open(path, "wb", compresslevel=1) as f:
+        for i in range(40):
+            f.write(b">c%d\n" % i)
+            s_ = seq[i * 1000:i * 1000 + 4_000_000]
+            f.write(b"\n".join(s_[j:j + 80] for j in range(0, len(s_), 80)) + b"\n")
+    for mb, mr in ((1 << 30, 1 << 30), (3_000_000, 1 << 30), (20_000_000, 3)):
+        a, b = both(exe, path, mb, mr, 4)
+        assert not a.startswith("ERROR") and a == b and a.split()[1] == "40"
+
+
+def test_gzip_input_small(exe, tmp_path):
     rng = np.random.default_rng(9)
     data = fastq(rng, 500)
     path = str(tmp_path / "x.fastq.gz")
