@@ -253,13 +253,15 @@ class ParallelFastxReader {
         for (auto& x : th) x.join();
     }
 
-    // complete lines of [from, to): every '\n' found ends one
+    // complete lines of [from, to): every '\n' found ends one. Two parallel passes: collect the newline positions of every
+    // slice, then write the lines of every slice at its prefix-summed place.
     void scan_lines(size_t from, size_t to, std::vector<Line>& lines) const {
         const size_t T = (size_t)std::max(1, threads);
         std::vector<std::vector<size_t>> nl(T);
         parallel_for(to - from, [&](size_t a, size_t b, size_t t) {
             const char* p = data + from + a;
             const char* e = data + from + b;
+            nl[t].reserve((size_t)(e - p) / 64 + 16);
             while (p < e) {
                 const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
                 if (!q) break;
@@ -267,13 +269,28 @@ class ParallelFastxReader {
                 p = q + 1;
             }
         });
-        lines.clear();
-        size_t start = from;
-        for (const auto& v : nl)
-            for (size_t x : v) {
-                lines.push_back(Line{start, x});
-                start = x + 1;
+        std::vector<size_t> first(T + 1, 0), start(T, from); // first line index of slice t; start of its first line
+        size_t prev_start = from;
+        for (size_t t = 0; t < T; t++) {
+            first[t + 1] = first[t] + nl[t].size();
+            start[t] = prev_start;
+            if (!nl[t].empty()) prev_start = nl[t].back() + 1;
+        }
+        lines.resize(first[T]);
+        Line* out = lines.data();
+        const std::vector<size_t>* nlp = nl.data();
+        const size_t* firstp = first.data();
+        const size_t* startp = start.data();
+        parallel_for(T, [=](size_t a, size_t b, size_t) {
+            for (size_t t = a; t < b; t++) {
+                size_t st = startp[t];
+                Line* o = out + firstp[t];
+                for (size_t x : nlp[t]) {
+                    *o++ = Line{st, x};
+                    st = x + 1;
+                }
             }
+        });
     }
 
     int64_t from_serial(int64_t max_bases, int64_t max_reads, std::vector<char>& ascii, std::vector<int64_t>& offsets) {
@@ -327,12 +344,11 @@ public:
     // Same contract as FastxReader::next_batch.
     int64_t next_batch(int64_t max_bases, int64_t max_reads, std::vector<char>& ascii, std::vector<int64_t>& offsets) {
         if (serial) return from_serial(max_bases, max_reads, ascii, offsets);
-        ascii.clear();
         offsets.clear();
         offsets.push_back(0);
-        if (max_reads <= 0 || max_bases <= 0) return 0;
+        if (max_reads <= 0 || max_bases <= 0) { ascii.clear(); return 0; }
         z_fill(1);
-        if (cur >= size) return 0;
+        if (cur >= size) { ascii.clear(); return 0; }
         struct Rec {
             size_t first_line, n_lines; // sequence lines
             int64_t len;
@@ -402,7 +418,7 @@ public:
         const size_t n = recs.size();
         offsets.resize(n + 1);
         for (size_t r = 0; r < n; r++) offsets[r + 1] = offsets[r] + recs[r].len;
-        ascii.resize((size_t)offsets[n]);
+        ascii.resize((size_t)offsets[n]); // (not cleared first: only growth beyond the previous batch is zero-filled)
         char* out = ascii.data();
         const int64_t* off = offsets.data();
         const Line* L = lines.data();
