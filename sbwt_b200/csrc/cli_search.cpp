@@ -26,6 +26,7 @@
 #include <string>
 #include <exception>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -158,8 +159,51 @@ struct Options {
 };
 
 // run_file (sbwt_search.cpp:93-105): streaming search when the index supports it, else search() per k-mer.
-static int64_t run_file(const string& infile, const string& outfile, const sbwt::plain_matrix_sbwt_t& index, bool gzip_output,
+static int string_sink(void* user, const char* text, int64_t n_bytes) {
+    static_cast<string*>(user)->append(text, (size_t)n_bytes);
+    return 0;
+}
+
+// One batch over several devices (--devices): the reads are cut into contiguous ranges of (almost) equal total bases,
+// one host thread per replica produces the text of its range, and the ranges are written in order. Nothing is exchanged
+// between the devices.
+static int64_t query_batch_multi(const vector<const sbwt::plain_matrix_sbwt_t*>& replicas, const vector<char>& ascii,
+                                 const vector<int64_t>& offsets, int64_t n, int mode, Writer& writer) {
+    const size_t D = replicas.size();
+    vector<int64_t> cuts(D + 1, n);
+    cuts[0] = 0;
+    const int64_t total = offsets[(size_t)n] - offsets[0];
+    for (size_t d = 1; d < D; d++) {
+        const int64_t target = offsets[0] + total * (int64_t)d / (int64_t)D;
+        const int64_t c = std::lower_bound(offsets.begin(), offsets.begin() + n + 1, target) - offsets.begin();
+        cuts[d] = std::min<int64_t>(n, std::max<int64_t>(cuts[d - 1], c));
+    }
+    vector<string> text(D);
+    vector<int64_t> lookups(D, 0);
+    vector<std::exception_ptr> errors(D);
+    auto work = [&](size_t d) {
+        try {
+            const int64_t r0 = cuts[d], nr = cuts[d + 1] - r0;
+            if (nr > 0)
+                lookups[d] = replicas[d]->query_batch_text(ascii.data(), offsets.data() + r0, nr, mode, SBWT_GPU_CASE_UPPER, string_sink, &text[d]);
+        } catch (...) { errors[d] = std::current_exception(); }
+    };
+    vector<std::thread> th;
+    for (size_t d = 1; d < D; d++) th.emplace_back(work, d);
+    work(0);
+    for (auto& t : th) t.join();
+    int64_t n_lookups = 0;
+    for (size_t d = 0; d < D; d++) {
+        if (errors[d]) std::rethrow_exception(errors[d]);
+        writer.write(text[d].data(), text[d].size());
+        n_lookups += lookups[d];
+    }
+    return n_lookups;
+}
+
+static int64_t run_file(const string& infile, const string& outfile, const vector<const sbwt::plain_matrix_sbwt_t*>& replicas, bool gzip_output,
                         const Options& opt, long long& query_micros) {
+    const sbwt::plain_matrix_sbwt_t& index = *replicas[0];
     sbwt_b200::ParallelFastxReader reader(infile, opt.threads); // same batches and errors as the serial FastxReader
     Writer writer(outfile, gzip_output, opt.threads);
     SinkState sink{&writer, ""};
@@ -188,8 +232,9 @@ static int64_t run_file(const string& infile, const string& outfile, const sbwt:
         std::thread ahead(parse, std::ref(batches[turn ^ 1]));
         const long long t0 = cur_time_micros();
         try {
-            n_queries += index.query_batch_text(b.ascii.data(), b.offsets.data(), b.n, streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH,
-                                                SBWT_GPU_CASE_UPPER, text_sink, &sink);
+            const int mode = streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH;
+            if (replicas.size() > 1) n_queries += query_batch_multi(replicas, b.ascii, b.offsets, b.n, mode, writer);
+            else n_queries += index.query_batch_text(b.ascii.data(), b.offsets.data(), b.n, mode, SBWT_GPU_CASE_UPPER, text_sink, &sink);
         } catch (const std::runtime_error&) {
             ahead.join();
             if (!sink.error.empty()) throw std::runtime_error(sink.error);
@@ -217,6 +262,8 @@ static void print_help(const char* prog) {
               << "  -z, --gzip-output      Writes output in gzipped form. This can shrink the output files by an order of\n"
               << "                         magnitude.\n"
               << "      --device arg       CUDA device (default 0)\n"
+              << "      --devices arg      Comma-separated CUDA devices: the index is replicated on each of them and every\n"
+              << "                         batch of reads is split over them (no data is exchanged between devices)\n"
               << "      --batch-bases arg  Read bases per GPU batch (default 67108864)\n"
               << "      --threads arg      Host threads for parsing the query file and for gzip output (default 8)\n"
               << "  -h, --help             Print usage\n" << std::endl;
@@ -227,6 +274,7 @@ static int search_main(int argc, char** argv) {
     string out_file, index_file, query_file;
     bool gzip_output = false, have_o = false, have_i = false, have_q = false;
     int device = 0;
+    vector<int> devices; // --devices a,b,...: one replica of the index per listed device, every batch split over them
     Options opt;
     if (argc == 1) { print_help(argv[0]); return 1; }
     for (int i = 1; i < argc; i++) {
@@ -241,6 +289,10 @@ static int search_main(int argc, char** argv) {
         else if (a == "-q" || a == "--query-file") { query_file = value("query-file"); have_q = true; }
         else if (a == "-z" || a == "--gzip-output") gzip_output = true;
         else if (a == "--device") device = std::stoi(value("device"));
+        else if (a == "--devices") {
+            std::stringstream ss(value("devices"));
+            for (string tok; std::getline(ss, tok, ',');) devices.push_back(std::stoi(tok));
+        }
         else if (a == "--batch-bases") opt.batch_bases = std::stoll(value("batch-bases"));
         else if (a == "--threads") opt.threads = std::stoi(value("threads"));
         else throw std::runtime_error("Option '" + a + "' does not exist");
@@ -272,8 +324,20 @@ static int search_main(int argc, char** argv) {
         std::cerr << "Error: the GPU query path serves the plain-matrix variant only (index is " << variant << ")" << std::endl;
         return 1;
     }
-    sbwt::plain_matrix_sbwt_t index(device);
-    index.load(in);
+    if (devices.empty()) devices.push_back(device);
+    vector<std::unique_ptr<sbwt::plain_matrix_sbwt_t>> owned;
+    vector<const sbwt::plain_matrix_sbwt_t*> replicas;
+    for (size_t d = 0; d < devices.size(); d++) {
+        owned.emplace_back(new sbwt::plain_matrix_sbwt_t(devices[d]));
+        if (d == 0) owned.back()->load(in);
+        else { // every replica reads the file itself (the variant string first, sbwt_search.cpp:194)
+            std::ifstream again(index_file, std::ios::binary);
+            if (!again.good()) throw std::runtime_error("Error opening file: " + index_file);
+            sbwt_b200::load_variant_string(again);
+            owned.back()->load(again);
+        }
+        replicas.push_back(owned.back().get());
+    }
 
     if (input_files.size() != output_files.size())
         throw std::runtime_error("Number of input and output files does not match (" + std::to_string(input_files.size()) + " vs " +
@@ -281,7 +345,7 @@ static int search_main(int argc, char** argv) {
     int64_t number_of_queries = 0;
     for (size_t i = 0; i < input_files.size(); i++) {
         long long micros = 0;
-        number_of_queries += run_file(input_files[i], output_files[i], index, gzip_output, opt, micros);
+        number_of_queries += run_file(input_files[i], output_files[i], replicas, gzip_output, opt, micros);
     }
     const long long total_micros = cur_time_micros() - micros_start;
     write_log("us/query end-to-end: " + std::to_string((double)total_micros / std::max<int64_t>(number_of_queries, 1)));
