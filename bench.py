@@ -48,6 +48,10 @@ WORKLOADS = {
                 ref=("pangenome", 40, 5_000_000, 44), k=31, streaming=True, rc=True, reads=10_000_000),
     "c5s": dict(desc="configs[4] scaled: the same pangenome-like reference, k=63 (+RC), index > L2, streaming_search, 88 lookups per 150-bp read",
                 ref=("pangenome", 40, 5_000_000, 44), k=63, streaming=True, rc=True, reads=10_000_000),
+    "c4": dict(desc="configs[3] at full size: pangenome-like 400 x 5 Mbp mutated copies (5% subst.) = 2 Gbp, k=31 +RC (~3.2 G columns: narrow layout with values >= 2^31), streaming_search",
+               ref=("pangenome", 400, 5_000_000, 44), k=31, streaming=True, rc=True, reads=10_000_000),
+    "c5": dict(desc="configs[4] at full size: the same 2 Gbp pangenome-like reference, k=63 (+RC), streaming_search, 88 lookups per 150-bp read",
+               ref=("pangenome", 400, 5_000_000, 44), k=63, streaming=True, rc=True, reads=10_000_000),
     "tiny": dict(desc="smoke-sized: 2 Mbp random DNA, k=31, streaming", ref=("contigs", 2, 1_000_000, 42), k=31, streaming=True,
                  rc=False, reads=200_000),
 }
@@ -80,7 +84,8 @@ def ensure_index(name: str, w: dict) -> tuple[str, np.ndarray]:
         info = build_index(raw, path + ".tmp", k=w["k"], precalc=8, streaming=w["streaming"], add_rc=w["rc"], raw=True)
         os.replace(path + ".tmp", path)
         os.remove(raw)
-        log(f"built {path}: {info} in {time.time() - t0:.1f}s")
+        import resource
+        log(f"built {path}: {info} in {time.time() - t0:.1f}s (builder peak RSS {resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss / 1e6:.1f} GB)")
     return path, ref
 
 

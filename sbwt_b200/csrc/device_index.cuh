@@ -51,10 +51,15 @@ struct DeviceIndexView {
     int wide;                  // 1 if n_nodes >= 2^32 (or forced for tests)
     int edges_at_starts;       // structural invariant (i) of SURVEY.md section 8(a) note 7 holds
     // compact (one-hot) layout, see below; nullptr when the index is not eligible
-    const Sector* compact;     // [n_cblocks]
-    const uint32_t* cbase;     // [n_csb][4]: C[c] + rank_c(first column of the superblock)
+    const Sector* compact;     // [n_cblocks]: csectors of `layout` (96 or 64 columns each)
+    const uint32_t* cbase;     // LAY_C96 only: [n_csb][4]: C[c] + rank_c(first column of the superblock)
     int64_t n_cblocks;
+    int layout;                // LAY_CLASSIC / LAY_C96 / LAY_C64: what `compact` holds (LAY_CLASSIC: nothing)
 };
+
+constexpr int LAY_CLASSIC = 0; // 224 columns x 1 character per sector
+constexpr int LAY_C96 = 1;     // 96 columns x 4 characters, 15-bit relative counts + cbase[]
+constexpr int LAY_C64 = 2;     // 64 columns x 4 characters, absolute counts inline
 
 // ------------------------------------------------------------------ compact (one-hot) layout
 //
