@@ -164,37 +164,9 @@ __global__ void __launch_bounds__(256) plan_count_kernel(const int64_t* __restri
     n_win[r] = (nk + window - 1) / window;
 }
 
-// per read: emit its work items. out_off / win_off are the exclusive scans of the counts.
+// per read: emit its work items. out_off / win_off are the exclusive scans of the counts. item.vfrom holds `nvalid`,
+// the number of leading k-mers of the item that cover no invalid base (0 = already the first k-mer does).
 __global__ void __launch_bounds__(256) plan_emit_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k,
-                                                        int window, const int64_t* __restrict__ out_off,
-                                                        const int64_t* __restrict__ win_off,
-                                                        const uint32_t* __restrict__ invalid, WalkItem* __restrict__ items) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const int64_t start = offsets[r] - offsets[0];
-    const int64_t len = offsets[r + 1] - offsets[r];
-    const int64_t nk = len >= k ? len - k + 1 : 0;
-    int64_t it = win_off[r];
-    for (int64_t done = 0; done < nk; done += window, it++) {
-        WalkItem w;
-        const int64_t lo = start + done, hi = lo + k - 1; // the first k-mer's bases but the last: [lo, hi)
-        w.base = (uint32_t)lo;
-        w.out = (uint32_t)(out_off[r] + done);
-        w.cnt = (uint32_t)(nk - done < window ? nk - done : window);
-        w.vfrom = (uint32_t)lo;
-        for (int64_t wi = (hi - 1) >> 5; hi > lo && wi >= (lo >> 5); wi--) {
-            uint32_t bits = invalid[wi];
-            if (wi == ((hi - 1) >> 5) && (hi & 31)) bits &= (1u << (hi & 31)) - 1u;
-            if (wi == (lo >> 5)) bits &= 0xFFFFFFFFu << (lo & 31);
-            if (bits) { w.vfrom = (uint32_t)(wi * 32 + 32 - __clz(bits)); break; }
-        }
-        items[it] = w;
-    }
-}
-
-// The same, for walk2_kernel: item.vfrom holds `nvalid`, the number of leading k-mers of the item that
-// cover no invalid base (0 = already the first k-mer does).
-__global__ void __launch_bounds__(256) plan_emit2_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k,
                                                          int window, const int64_t* __restrict__ out_off,
                                                          const int64_t* __restrict__ win_off,
                                                          const uint32_t* __restrict__ invalid, WalkItem* __restrict__ items) {
@@ -311,6 +283,35 @@ __global__ void __launch_bounds__(256) k0_compact_kernel(const uint32_t* __restr
     }
     s.w[0] = rel[0] | (rel[1] << 16) | (exc ? 0x8000u : 0u);
     s.w[1] = rel[2] | (rel[3] << 16);
+    compact[b] = s;
+    if (exc) atomicAdd(n_flagged, 1ull);
+}
+
+// the self-contained one-hot layout (LAY_C64, device_index.cuh): one thread per 64-column block
+__global__ void __launch_bounds__(256) k0_compact64_kernel(const uint32_t* __restrict__ raw, int64_t words_per_vec, int64_t n_blocks,
+                                                           const int64_t* __restrict__ prefix, int64_t C0, int64_t C1, int64_t C2,
+                                                           int64_t C3, int64_t n_nodes, int64_t n_cblocks,
+                                                           Sector* __restrict__ compact, unsigned long long* __restrict__ n_flagged) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_cblocks) return;
+    const int64_t col0 = b * kC64Cols;
+    const int64_t Cc[4] = {C0, C1, C2, C3};
+    Sector s;
+    for (int c = 0; c < 4; c++) s.w[c] = (uint32_t)(Cc[c] + k0_raw_rank(raw, words_per_vec, n_blocks, prefix, c, col0));
+    uint32_t exc = 0;
+    for (int i = 0; i < 2; i++) {
+        const int64_t wi = 2 * b + i; // 64 = 2 x 32: a block is two whole words of every plane
+        uint32_t a = 0, cc = 0, g = 0, t = 0;
+        if (wi < words_per_vec) { a = raw[wi]; cc = raw[words_per_vec + wi]; g = raw[2 * words_per_vec + wi]; t = raw[3 * words_per_vec + wi]; }
+        const uint32_t two = (a & cc) | (a & g) | (a & t) | (cc & g) | (cc & t) | (g & t);
+        const uint32_t one = (a ^ cc ^ g ^ t) & ~two;
+        const int64_t first = col0 + 32 * i;
+        const uint32_t valid = first >= n_nodes ? 0u : (n_nodes - first >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)(n_nodes - first)) - 1u));
+        exc |= ~one & valid;
+        s.w[4 + i] = cc | t;
+        s.w[6 + i] = g | t;
+    }
+    if (exc) s.w[0] = 0xFFFFFFFFu;
     compact[b] = s;
     if (exc) atomicAdd(n_flagged, 1ull);
 }

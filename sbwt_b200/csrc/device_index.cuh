@@ -122,6 +122,32 @@ __device__ __forceinline__ CompactRank compact_rank(const CompactMatch& m, uint3
     return r;
 }
 
+// ------------------------------------------------------------------ LAY_C64: self-contained one-hot csectors
+//
+//   csector64(block b) = { 4 x u32 cnt_c ; 64 bits lo ; 64 bits hi }              32 bytes, ALL FOUR characters of 64 columns
+//     cnt_c       = C[c] + rank_c(64 b), absolute: one rank is exactly ONE memory request (no cbase[] word, no
+//                   division: block = pos >> 6), two masked popcounts
+//     (hi, lo)[j] = the character of the one edge of column 64 b + j
+//     cnt_A == 0xFFFFFFFF: some column of the block has no edge or several -> answered from the classic sectors
+//                   (cnt_A <= C[1] <= n_nodes < 2^32 - 256 otherwise, so the marker cannot be a count)
+// 0.5 B per column (LAY_C96: 0.333): which of the two a narrow one-hot index gets is a measured choice of the loader.
+constexpr int kC64Cols = 64;
+
+__device__ __forceinline__ bool c64_flagged(const Sector& s) { return s.w[0] == 0xFFFFFFFFu; }
+
+// value = C[c] + rank_c(pos), bit = bit_c(pos) for in-block offset off = pos & 63 (0 <= off < 64)
+__device__ __forceinline__ CompactRank c64_rank(const Sector& s, int c, uint32_t off) {
+    const bool c0 = (c & 1) != 0, c1 = (c & 2) != 0;
+    const uint32_t X = c0 ? 0u : 0xFFFFFFFFu, Y = c1 ? 0u : 0xFFFFFFFFu;
+    const uint32_t ca = c0 ? s.w[1] : s.w[0], cb = c0 ? s.w[3] : s.w[2];
+    const uint32_t m0 = (s.w[4] ^ X) & (s.w[6] ^ Y), m1 = (s.w[5] ^ X) & (s.w[7] ^ Y);
+    const uint32_t n1 = (uint32_t)max((int)off - 32, 0);
+    CompactRank r;
+    r.value = (c1 ? cb : ca) + __popc(m0 & ~shl_ones_clamp(off)) + __popc(m1 & ~shl_ones_clamp(n1));
+    r.bit = (((off & 32u) ? m1 : m0) >> (off & 31u)) & 1u;
+    return r;
+}
+
 // cbase entry of (csector block cb, character c); volatile so that it is issued where it is written -- ahead of the
 // csector load it travels with -- instead of being sunk behind the branch on the csector's flag
 __device__ __forceinline__ uint32_t ld_cbase(const uint32_t* __restrict__ cbase, uint32_t cb, int c) {

@@ -19,9 +19,13 @@
 #include "host_widen.hpp"
 #include "sbwt_file.hpp"
 #include "walk_kernel.cuh"
-#include "walk2_kernel.cuh"
 
 using namespace sbwt_b200;
+
+#ifndef SBWT_B200_DEFAULT_LAYOUT
+#define SBWT_B200_DEFAULT_LAYOUT LAY_C64
+#endif
+static constexpr int kDefaultCompactLayout = SBWT_B200_DEFAULT_LAYOUT; // csector format of eligible (one-hot, narrow) indexes
 
 // ------------------------------------------------------------------ errors
 
@@ -45,23 +49,6 @@ static int set_error(const char* fmt, ...) {
     } while (0)
 
 #define LAUNCHED() (g_launches++)
-
-// SBWT_B200_L2_FETCH=32|64|128: cudaLimitMaxL2FetchGranularity (how many bytes an L2 miss brings in from
-// HBM; a random 32-byte sector read costs 128 bytes of DRAM traffic at the default setting, ncu exp2)
-static void apply_l2_fetch_granularity() {
-    const char* e = getenv("SBWT_B200_L2_FETCH");
-    if (!e) return;
-    const int g = atoi(e);
-    static thread_local int applied = 0;
-    if (g == applied) return;
-    applied = g;
-    if (g == 32 || g == 64 || g == 128) {
-        cudaError_t rc = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
-        size_t got = 0;
-        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-        fprintf(stderr, "[sbwt_b200] cudaLimitMaxL2FetchGranularity <- %d: %s, now %zu\n", g, cudaGetErrorName(rc), got);
-    }
-}
 
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -94,6 +81,8 @@ struct sbwt_gpu_index {
     void* d_table = nullptr;
     int64_t table_bytes = 0;
     bool table_from_bits = true; // the file's table equals what the bit vectors imply, so any table length is admissible
+    bool compact_in_search = false; // the per-k-mer search path also walks the compact layout (default: classic sectors)
+    uint32_t probe_stride = 0;      // streaming walk: distance between the probes of a range of presumed misses (0 = none)
     void* d_sgs = nullptr;
 };
 
@@ -239,7 +228,6 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     if (k > 64) return set_error("k = %lld is not supported by this build (k <= 64)", (long long)k);
     if (p < 0 || p > k || p > 14) return set_error("precalc length %lld is not supported (0 <= p <= min(k,14))", (long long)p);
     DeviceGuard guard(device);
-    apply_l2_fetch_granularity();
     sbwt_gpu_index* ix = new sbwt_gpu_index();
     auto fail = [&](int rc) { sbwt_gpu_index_destroy(ix); return rc; };
     ix->device = device;
@@ -301,20 +289,32 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
                                                          sb_shift, n_sb, (Sector*)ix->d_sectors, (int64_t*)ix->d_sbbase); LAUNCHED();
     CUI(cudaGetLastError());
 
-    // one-hot layout: narrow indexes in which (nearly) every column has exactly one outgoing edge.
-    // SBWT_B200_COMPACT = 0 never, 1 (default) when at most 5 % of its blocks need the classic sectors, 2 always (tests)
+    // one-hot layouts: narrow indexes in which (nearly) every column has exactly one outgoing edge.
+    // SBWT_B200_COMPACT = 0 never, 1 (default) when at most 5 % of its blocks need the classic sectors, 2 always (tests);
+    // SBWT_B200_LAYOUT = c96 | c64 picks the csector format (device_index.cuh). Read here, once per index.
     int compact_mode = 1;
     if (const char* e = getenv("SBWT_B200_COMPACT")) compact_mode = atoi(e);
-    const int64_t n_cblocks = n_nodes / kCBlockCols + 1;
+    int layout = kDefaultCompactLayout;
+    if (const char* e = getenv("SBWT_B200_LAYOUT")) layout = strcmp(e, "c64") == 0 ? LAY_C64 : (strcmp(e, "c96") == 0 ? LAY_C96 : layout);
+    if (const char* e = getenv("SBWT_B200_COMPACT_SEARCH")) ix->compact_in_search = atoi(e) > 0;
+    if (compact_mode >= 2) ix->compact_in_search = true;
+    const int ccols = layout == LAY_C64 ? kC64Cols : kCBlockCols;
+    const int64_t n_cblocks = n_nodes / ccols + 1;
+    int built_layout = LAY_CLASSIC;
     if (!wide && compact_mode > 0) {
         const int64_t n_csb = ((n_cblocks - 1) >> kCSbShift) + 1;
         unsigned long long* d_nflag = nullptr;
         CUI(cudaMalloc(&ix->d_compact, (size_t)n_cblocks * sizeof(Sector)));
-        CUI(cudaMalloc(&ix->d_cbase, (size_t)n_csb * 16));
+        if (layout == LAY_C96) CUI(cudaMalloc(&ix->d_cbase, (size_t)n_csb * 16));
         CUI(cudaMalloc(&d_nflag, 8));
         CUI(cudaMemset(d_nflag, 0, 8));
-        k0_compact_kernel<<<grid_for(n_cblocks, 256), 256>>>(d_raw, words_per_vec, n_blocks, d_counts, C[0], C[1], C[2], C[3], n_nodes,
-                                                             n_cblocks, (Sector*)ix->d_compact, (uint32_t*)ix->d_cbase, d_nflag); LAUNCHED();
+        if (layout == LAY_C64)
+            k0_compact64_kernel<<<grid_for(n_cblocks, 256), 256>>>(d_raw, words_per_vec, n_blocks, d_counts, C[0], C[1], C[2], C[3], n_nodes,
+                                                                   n_cblocks, (Sector*)ix->d_compact, d_nflag);
+        else
+            k0_compact_kernel<<<grid_for(n_cblocks, 256), 256>>>(d_raw, words_per_vec, n_blocks, d_counts, C[0], C[1], C[2], C[3], n_nodes,
+                                                                 n_cblocks, (Sector*)ix->d_compact, (uint32_t*)ix->d_cbase, d_nflag);
+        LAUNCHED();
         unsigned long long n_flagged = 0;
         cudaError_t e1 = cudaMemcpy(&n_flagged, d_nflag, 8, cudaMemcpyDeviceToHost);
         cudaFree(d_nflag);
@@ -324,7 +324,8 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
             cudaFree(ix->d_compact); cudaFree(ix->d_cbase);
             ix->d_compact = ix->d_cbase = nullptr;
         } else {
-            ix->device_bytes += n_cblocks * (int64_t)sizeof(Sector) + n_csb * 16;
+            built_layout = layout;
+            ix->device_bytes += n_cblocks * (int64_t)sizeof(Sector) + (layout == LAY_C96 ? n_csb * 16 : 0);
         }
     }
 
@@ -345,7 +346,7 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     v.sgs = (const uint32_t*)ix->d_sgs;
     v.n_nodes = n_nodes; v.n_blocks = n_blocks; v.n_sb = n_sb;
     v.k = (int)k; v.p = (int)p; v.sb_shift = sb_shift; v.wide = wide; v.edges_at_starts = edges_at_starts;
-    v.compact = (const Sector*)ix->d_compact; v.cbase = (const uint32_t*)ix->d_cbase; v.n_cblocks = n_cblocks;
+    v.compact = (const Sector*)ix->d_compact; v.cbase = (const uint32_t*)ix->d_cbase; v.n_cblocks = n_cblocks; v.layout = built_layout;
     if (p > 0) {
         const size_t bytes = (size_t)16 << (2 * p);
         const int64_t np = 1ll << (2 * p);
@@ -393,6 +394,13 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
         }
     }
     if (int rc = sbwt_gpu_index_set_table_length(ix, tp)) { sbwt_gpu_index_destroy(ix); return rc; }
+    if (ix->table_from_bits) { // (see launch_walk)
+        int log4n = 0;
+        while (log4n < 32 && (1ll << (2 * log4n)) < ix->n_nodes) log4n++;
+        const int64_t d = ix->k - log4n - 2;
+        ix->probe_stride = d >= 8 ? (uint32_t)d : 0u;
+        if (const char* pe = getenv("SBWT_B200_PROBE")) ix->probe_stride = (uint32_t)std::max(0, atoi(pe));
+    }
     *out = ix;
     return 0;
 }
@@ -603,150 +611,55 @@ static int launch_pack(const char* d_ascii, int64_t n_bases, int case_mode, uint
     return 0;
 }
 
-// L2 persistence (SBWT_B200_L2_PERSIST=1): bytes set aside for persisting lines and the largest window
-static size_t g_persist_bytes = 0, g_persist_window_max = 0;
-
-template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32>
-static cudaError_t launch_walk_tt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
-    static int occ = 0; // resident 256-thread blocks per SM of this instantiation
+template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL, int LAY>
+static cudaError_t launch_walk_ttt(const WalkParams& P, int sm_count, cudaStream_t st) {
+    static int occ = 0; // resident blocks per SM of this instantiation
     if (occ == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<STREAMING, WIDE, COUNT, OUT32>, 256, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, LAY>, kWalkThreads, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
     }
-    const unsigned grid = (unsigned)(sm_count * (blocks_per_sm > 0 ? blocks_per_sm : occ));
-    if (g_persist_bytes > 0) {
-        // L2 persistence window over the sector array (per launch): lines of the index are kept
-        // as "persisting", everything else streams through the rest of L2.
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeAccessPolicyWindow;
-        const size_t bytes = (size_t)P.ix.n_blocks * 4 * sizeof(Sector);
-        const size_t win = std::min(bytes, g_persist_window_max);
-        attr.val.accessPolicyWindow.base_ptr = const_cast<Sector*>(P.ix.sectors);
-        attr.val.accessPolicyWindow.num_bytes = win;
-        attr.val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)g_persist_bytes / (double)std::max<size_t>(win, 1));
-        attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, walk_kernel<STREAMING, WIDE, COUNT, OUT32>, P);
-    }
-    walk_kernel<STREAMING, WIDE, COUNT, OUT32><<<grid, 256, 0, st>>>(P);
-    return cudaGetLastError();
-}
-
-template <bool STREAMING, bool WIDE>
-static cudaError_t launch_walk_t(const WalkParams& P, bool count, int sm_count, int blocks_per_sm, cudaStream_t st) {
-    if (P.out32) {
-        if (WIDE || count) return cudaErrorInvalidValue; // int32 results exist only for narrow, uncounted batches
-        return launch_walk_tt<STREAMING, false, false, true>(P, sm_count, blocks_per_sm, st);
-    }
-    return count ? launch_walk_tt<STREAMING, WIDE, true, false>(P, sm_count, blocks_per_sm, st)
-                 : launch_walk_tt<STREAMING, WIDE, false, false>(P, sm_count, blocks_per_sm, st);
-}
-
-template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL, bool COMPACT>
-static cudaError_t launch_walk2_ttt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
-    static int occ = 0;
-    if (occ == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk2_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, COMPACT>, kW2Threads, 0);
-        if (e != cudaSuccess) return e;
-        if (occ < 1) occ = 1;
-    }
-    const unsigned grid = (unsigned)(sm_count * (blocks_per_sm > 0 ? blocks_per_sm : occ));
-    walk2_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, COMPACT><<<grid, kW2Threads, 0, st>>>(P);
+    walk_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, LAY><<<(unsigned)(sm_count * occ), kWalkThreads, 0, st>>>(P);
     return cudaGetLastError();
 }
 
 template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW>
-static cudaError_t launch_walk2_tt(const WalkParams& P, int sm_count, int blocks_per_sm, cudaStream_t st) {
+static cudaError_t launch_walk_tt(const WalkParams& P, int sm_count, cudaStream_t st) {
     if (STREAMING && !P.ix.edges_at_starts) // the reference's control flow to the letter (hand-made index files)
-        return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, STREAMING, false>(P, sm_count, blocks_per_sm, st);
-    if (!WIDE && P.ix.compact) // one-hot layout (device_index.cuh)
-        return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false, !WIDE>(P, sm_count, blocks_per_sm, st);
-    return launch_walk2_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false, false>(P, sm_count, blocks_per_sm, st);
+        return launch_walk_ttt<STREAMING, WIDE, COUNT, OUT32, KW, STREAMING, LAY_CLASSIC>(P, sm_count, st);
+    if (!WIDE && P.ix.compact) { // one-hot layouts (device_index.cuh)
+        if (P.ix.layout == LAY_C64) return launch_walk_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false, WIDE ? LAY_CLASSIC : LAY_C64>(P, sm_count, st);
+        return launch_walk_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false, WIDE ? LAY_CLASSIC : LAY_C96>(P, sm_count, st);
+    }
+    return launch_walk_ttt<STREAMING, WIDE, COUNT, OUT32, KW, false, LAY_CLASSIC>(P, sm_count, st);
 }
 
 template <bool STREAMING, bool WIDE, int KW>
-static cudaError_t launch_walk2_t(const WalkParams& P, bool count, int sm_count, int blocks_per_sm, cudaStream_t st) {
+static cudaError_t launch_walk_t(const WalkParams& P, bool count, int sm_count, cudaStream_t st) {
     if (P.out32) {
-        if (WIDE || count) return cudaErrorInvalidValue;
-        return launch_walk2_tt<STREAMING, false, false, true, KW>(P, sm_count, blocks_per_sm, st);
+        if (WIDE || count) return cudaErrorInvalidValue; // int32 results exist only for narrow, uncounted batches
+        return launch_walk_tt<STREAMING, false, false, true, KW>(P, sm_count, st);
     }
-    return count ? launch_walk2_tt<STREAMING, WIDE, true, false, KW>(P, sm_count, blocks_per_sm, st)
-                 : launch_walk2_tt<STREAMING, WIDE, false, false, KW>(P, sm_count, blocks_per_sm, st);
+    return count ? launch_walk_tt<STREAMING, WIDE, true, false, KW>(P, sm_count, st)
+                 : launch_walk_tt<STREAMING, WIDE, false, false, KW>(P, sm_count, st);
 }
 
-static int walk_generation() { // SBWT_B200_WALK=1 selects the lane-state-machine kernel of walk_kernel.cuh (A/B measurements)
-    const char* e = getenv("SBWT_B200_WALK");
-    return e ? atoi(e) : 2;
-}
-
-// One persistent wave: grid = SM count x resident blocks per SM (occupancy query), each warp owning a
-// contiguous range of work items.
+// One persistent wave: grid = SM count x resident blocks per SM (occupancy query); work is handed out through a global cursor.
 static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, bool count, cudaStream_t st) {
-    int blocks_per_sm = 0;
-    if (const char* e = getenv("SBWT_B200_BLOCKS_PER_SM")) blocks_per_sm = std::max(0, atoi(e));
-    apply_l2_fetch_granularity();
-    // The compact layout pays in streaming mode, whose 8 B-per-k-mer result stream competes with the index for L2.
+    // The compact layouts pay in streaming mode, whose 8 B-per-k-mer result stream competes with the index for L2.
     // The per-k-mer search path re-reads the wide top of the tree, is bound by L2 sector throughput and issue slots,
     // and is faster on the 224-column classic sectors (fewer two-sector steps): profiles/r01h_compact_ab.txt.
-    // SBWT_B200_COMPACT_SEARCH=1 (or SBWT_B200_COMPACT=2) uses it there as well.
-    if (!streaming && P.ix.compact) {
-        const char* cs = getenv("SBWT_B200_COMPACT_SEARCH");
-        const char* cm = getenv("SBWT_B200_COMPACT");
-        if (!((cs && atoi(cs) > 0) || (cm && atoi(cm) >= 2))) P.ix.compact = nullptr;
-    }
-    const char* el = getenv("SBWT_B200_L2_EVICT_LAST");
-    P.index_evict_last = el ? atoi(el) : 1;
-    const char* fr = getenv("SBWT_B200_L2_FRAC");
-    P.l2_frac = fr ? (float)atof(fr) : 1.0f;
-    const char* ns = getenv("SBWT_B200_DEBUG_NOSTORE");
-    P.debug_no_store = ns ? atoi(ns) : 0;
+    if (!streaming && !ix->compact_in_search) { P.ix.compact = nullptr; P.ix.layout = LAY_CLASSIC; }
+    P.table_streams = ix->table_bytes > ((int64_t)16 << 20) ? 1 : 0;
     // probe stride of the streaming walk: a from-scratch walk on this index dies after about log4(n) characters, and a
     // probe that dies at character j proves k - j k-mers absent. Any stride >= 1 gives the same results; it needs the
     // search table to follow from the bit vectors (monotonicity of the interval step), else every k-mer is searched.
-    P.probe_stride = 0;
-    if (streaming && ix->table_from_bits) {
-        int log4n = 0;
-        while (log4n < 32 && (1ll << (2 * log4n)) < ix->n_nodes) log4n++;
-        const int64_t d = ix->k - log4n - 2;
-        P.probe_stride = d >= 8 ? (uint32_t)d : 0u;
-        if (const char* pe = getenv("SBWT_B200_PROBE")) P.probe_stride = (uint32_t)std::max(0, atoi(pe));
-    }
-    {
-        const char* pe = getenv("SBWT_B200_L2_PERSIST");
-        const bool want = pe && atoi(pe) > 0;
-        if (want && g_persist_bytes == 0) {
-            int max_persist = 0, max_win = 0;
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device);
-            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ix->device);
-            if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
-                g_persist_bytes = (size_t)max_persist;
-                g_persist_window_max = (size_t)max_win;
-                fprintf(stderr, "[sbwt_b200] L2 persistence: set-aside %d MB, max window %d MB\n", max_persist >> 20, max_win >> 20);
-            }
-        } else if (!want && g_persist_bytes) {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
-            g_persist_bytes = 0;
-        }
-    }
+    P.probe_stride = streaming ? ix->probe_stride : 0u;
     const bool wide = ix->view.wide;
     cudaError_t e;
-    if (walk_generation() >= 2) {
-        CU(cudaMemsetAsync(P.cursor, 0, 8, st));
-        const bool k64 = ix->k > 32;
-#define WALK2(S_, W_) e = k64 ? launch_walk2_t<S_, W_, 2>(P, count, ix->sm_count, blocks_per_sm, st) \
-                              : launch_walk2_t<S_, W_, 1>(P, count, ix->sm_count, blocks_per_sm, st)
-        if (streaming) { if (wide) WALK2(true, true); else WALK2(true, false); }
-        else { if (wide) WALK2(false, true); else WALK2(false, false); }
-#undef WALK2
-        LAUNCHED();
-        CU(e);
-        return 0;
-    }
-#define WALK(S_, W_) e = launch_walk_t<S_, W_>(P, count, ix->sm_count, blocks_per_sm, st)
+    CU(cudaMemsetAsync(P.cursor, 0, 8, st));
+    const bool k64 = ix->k > 32;
+#define WALK(S_, W_) e = k64 ? launch_walk_t<S_, W_, 2>(P, count, ix->sm_count, st) : launch_walk_t<S_, W_, 1>(P, count, ix->sm_count, st)
     if (streaming) { if (wide) WALK(true, true); else WALK(true, false); }
     else { if (wide) WALK(false, true); else WALK(false, false); }
 #undef WALK
@@ -771,22 +684,21 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
     if (n_reads == 0) return 0;
     if (s->timing && &sc == &s->sc) CU(cudaEventRecord(s->ev_start, st));
     if (launch_pack(d_ascii, n_bases, case_mode, sc.codes, sc.invalid, st)) return 1;
-    const bool gen2 = walk_generation() >= 2;
-    // walk2: search mode is planned as chunks of 32 k-mers (one lane per k-mer), streaming mode as windows of a read
-    const int window = gen2 && mode == SBWT_GPU_MODE_SEARCH ? 32 : (gen2 ? std::min(s->window, (1 << 23)) : s->window);
+    // search mode is planned as chunks of 32 k-mers (one lane per k-mer), streaming mode as windows of a read. The first
+    // k-mer of a window is searched from scratch, which gives streaming_search's answers only where those equal search()'s:
+    // an index that violates the edge invariant (LITERAL kernel) or whose table does not follow from its bit vectors
+    // is walked read by read, as SBWT.hh:556-576 does
+    const bool windows_ok = ix->view.edges_at_starts && ix->table_from_bits;
+    const int window = mode == SBWT_GPU_MODE_SEARCH ? 32 : (windows_ok ? std::min(s->window, 1 << 23) : (1 << 23));
     plan_count_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win); LAUNCHED();
     if (exclusive_scan_inplace(sc.n_out, n_reads, sc.partials, sc.totals + 0, st)) return 1;
     if (exclusive_scan_inplace(sc.n_win, n_reads, sc.partials, sc.totals + 1, st)) return 1;
-    if (gen2) plan_emit2_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win,
-                                                                        sc.invalid, sc.items);
-    else plan_emit_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win,
-                                                                  sc.invalid, sc.items);
+    plan_emit_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win, sc.invalid, sc.items);
     LAUNCHED();
     CU(cudaGetLastError());
     WalkParams P;
     P.ix = ix->view;
     P.codes = reinterpret_cast<const uint32_t*>(sc.codes); P.invalid = sc.invalid;
-    P.n_chunks = (uint32_t)(sc.n_words / 2);
     P.items = sc.items;
     P.out32 = out32 ? (int32_t*)d_out : nullptr;
     P.n_items = sc.totals + 1;
@@ -1319,7 +1231,6 @@ extern "C" int sbwt_gpu_sector_probe(int device, int64_t buffer_bytes, int64_t n
     if (bytes_per_load != 32 && bytes_per_load != 64) return set_error("bytes_per_load must be 32 or 64");
     if (sbwt_gpu_device_count() <= 0) return set_error("no CUDA device available");
     DeviceGuard guard(device);
-    apply_l2_fetch_granularity();
     void* buf = nullptr;
     uint32_t* sink = nullptr;
     CU(cudaMalloc(&buf, (size_t)buffer_bytes));

@@ -1,33 +1,48 @@
-// walk_kernel.cuh -- the colex-interval walk on the device (sm_100a).
+// walk_kernel.cuh -- the colex-interval walk on the device (sm_100a), phase-sorted.
 //
 // Replaces SBWT::search (include/sbwt/SBWT.hh:390-415), SBWT::update_sbwt_interval
 // (SBWT.hh:423-437) and SBWT::streaming_search (SBWT.hh:545-581) together with the per-read
 // loops of src/CLI/sbwt_search.cpp:45-91.
 //
-// Work item = up to `window` consecutive k-mers of one read (a whole read when it is short).
-// One LANE owns one item at a time and is a small state machine. Every trip of the warp loop
-// has exactly ONE point where the warp waits for memory: the (one or two) index sectors of the
-// lane's interval step. Everything else a lane needs is already on chip when it is used:
+// A k-mer's walk has two very different phases. Right after the table jump (kmer_prefix_precalc,
+// SBWT.hh:404) the interval [l, r] is WIDE: a step needs rank_c(l) and rank_c(r+1), often from two
+// sectors, and an absent k-mer dies here within a few steps. Once the interval is a SINGLETON
+// (l == r) a step is one sector, one rank and one bit test -- and this is also exactly the
+// streaming step of SBWT.hh:561-575, because in a reference-built index only suffix-group starts
+// carry edges (SURVEY.md section 8(a) note 7): a set bit_c(col) proves col is its group's start.
+// A warp whose lanes are in different phases pays for both on every trip, so the phases are run as
+// separate lock-step loops, and every warp sorts its own work between them through small queues in
+// shared memory (no global traffic, no second launch):
 //
-//   * the packed read lives in a per-lane ring in shared memory (256 bases of 2-bit codes and
-//     invalid flags), filled by cp.async one 64-base chunk ahead of the walk;
-//   * the row of the search table (kmer_prefix_precalc, SBWT.hh:404) for the NEXT k-mer is
-//     requested while the current from-scratch k-mer is being walked, so a run of absent
-//     k-mers (the expensive case: every one of them is a fresh search) never waits for it.
+//   NARROW  32 lanes = 32 k-mers (consecutive k-mers of one read; in streaming mode the first
+//           k-mers of 32 work items). Each lane loads its k-mer into registers, takes its table
+//           row and runs general interval steps until its interval is empty (result -1), the
+//           k-mer is complete, or the interval has been a singleton for kSingleHold + 1 steps.
+//           Survivors go to a queue.
+//   CHAIN   singleton steps only. Search mode (and the stragglers of streaming mode): 32 lanes = 32
+//           survivors finishing their own k-mer (SBWT.hh:425-436 on a singleton interval).
+//           Streaming mode: every lane owns kChains survivors at once (their loads are in flight
+//           together) and follows each through the rest of its own k-mer and then through the
+//           following k-mers of its work item, one step and one result each (SBWT.hh:561-575).
+//           The lanes first bring their chains to a common output phase (a few single stores), then
+//           run a steady-state loop in which every chain steps, the results of one output sector
+//           collect in registers and leave as one 32-byte store, and nothing else happens; a clear
+//           bit (a miss, or a column that is not its suffix group's start) or a flagged csector
+//           drops to a slow path that takes the literal walk-back over suffix_group_starts
+//           (SBWT.hh:562-563). When a chain ends in a miss the rest of the item goes to PROBE.
+//   PROBE   (streaming mode) runs of absent k-mers are not searched one by one. If the walk over
+//           S = read[m .. m+j] dies at character j, no node's label ends with S, and because the
+//           SBWT holds every prefix of every k-mer as (a suffix of) some node, no indexed k-mer
+//           contains S anywhere: every k-mer of the read that covers [m, m+j] is absent, i.e. the
+//           k-mers starting in [m+j-k+1, m]. So a range of k-mers left behind by a miss is probed at
+//           every D-th k-mer only (D = P.probe_stride, about k - log4(n) - 2); probes that die early
+//           enough prove their whole segment absent and the -1s are written with coalesced stores.
+//           The first segment that is not proven absent restarts the read there as a fresh item
+//           (one full search, then the streaming chain again), exactly the control flow of
+//           SBWT.hh:556-576 -- only the proofs of absence are cheaper. Results are identical.
 //
-//   STEP   one interval step  [l,r] -> [C[c]+rank_c(l), C[c]+rank_c(r+1)-1]  (two sectors, one
-//          when l and r+1 fall into the same 224-column block). A streaming step (previous k-mer
-//          found at column col, SBWT.hh:561-575) is the same step on [col, col] with the new
-//          character: in a reference-built index only suffix-group starts carry edges
-//          (SURVEY.md section 8(a) note 7), so a set bit_c(col) already proves col is the group
-//          start; a clear bit (or an index violating the invariant) takes the literal
-//          walk-back over suffix_group_starts on a slow path.
-//   ADVANCE  runs when a lane finishes a k-mer: one result is stored, the lane moves to the next
-//          k-mer of its item and either parks in STEP again or answers on the spot the k-mers
-//          that need no walk (a non-ACGT byte inside, SBWT.hh:399,428,568; first p characters
-//          absent from the table, SBWT.hh:424; p == k).
-//
-// Finished lanes refill from the warp's own contiguous item range (ballot/popc).
+// Work (32-k-mer chunks in search mode, work items in streaming mode) is handed out through one
+// global cursor, so the grid is persistent and self-balancing.
 #pragma once
 
 #include <type_traits>
@@ -38,35 +53,18 @@ namespace sbwt_b200 {
 
 struct WalkParams {
     DeviceIndexView ix;
-    const uint32_t* codes;    // 2-bit bases, 16 per u32 word (64 bases = one 16-byte chunk)
+    const uint32_t* codes;    // 2-bit bases, 16 per u32 word
     const uint32_t* invalid;  // 1 bit per base, 32 per u32 word
-    uint32_t n_chunks;        // 64-base chunks the two arrays hold (allocation, not batch size)
     const WalkItem* items;
     const int64_t* n_items;   // device scalar
     int64_t* out;             // results as int64 ...
     int32_t* out32;           // ... or as int32 (OUT32 kernels; callers use them only when n_nodes < 2^31)
     unsigned long long* stats; // [lookups, hits, rank_ops, sectors] (COUNT only)
-    unsigned long long* cursor; // next unclaimed work item (walk2_kernel; zeroed before every launch)
-    int index_evict_last;      // L2 policy of the index / table loads (1 = evict_last; 2, 3: experiments with l2_frac)
-    float l2_frac;
-    int debug_no_store;        // measurement only (SBWT_B200_DEBUG_NOSTORE): results are not written
-    uint32_t probe_stride;     // walk2_kernel, streaming mode: distance in k-mers between the probes of a range of
-                               // presumed misses (0 = every k-mer after a miss is searched on its own)
+    unsigned long long* cursor; // next unclaimed work item (zeroed before every launch)
+    int table_streams;         // 1: the search table is far larger than L2 -> its rows are read with evict_first
+    uint32_t probe_stride;     // streaming mode: distance in k-mers between the probes of a range of presumed
+                               // misses (0 = every k-mer after a miss is searched on its own)
 };
-
-constexpr int kRingCodeWords = 16; // u32 words of codes per lane: 4 chunks of 64 bases
-constexpr int kRingFlagWords = 8;  // u32 words of invalid flags per lane
-constexpr int kWalkThreads = 256;
-
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
 
 // one row {l, r} of the search table; absent rows are all ones
 template <bool WIDE>
@@ -77,7 +75,7 @@ struct TableRow<false> {
     __device__ __forceinline__ bool absent() const { return l == 0xFFFFFFFFu; }
     static __device__ __forceinline__ TableRow load(const void* table, uint32_t idx, uint64_t pol) {
         TableRow t;
-        asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
                      : "=r"(t.l), "=r"(t.r)
                      : "l"(reinterpret_cast<const uint2*>(table) + idx), "l"(pol));
         return t;
@@ -89,215 +87,931 @@ struct TableRow<true> {
     __device__ __forceinline__ bool absent() const { return l < 0; }
     static __device__ __forceinline__ TableRow load(const void* table, uint32_t idx, uint64_t pol) {
         TableRow t;
-        asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
                      : "=l"(t.l), "=l"(t.r)
                      : "l"(reinterpret_cast<const longlong2*>(table) + idx), "l"(pol));
         return t;
     }
 };
 
-template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32>
-__global__ void __launch_bounds__(kWalkThreads, WIDE ? 4 : 5) walk_kernel(const WalkParams P) {
-    typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t; // columns fit 32 bits in narrow mode
-    __shared__ uint32_t ring[(kRingCodeWords + kRingFlagWords) * kWalkThreads];
-    const DeviceIndexView& ix = P.ix;
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t gw = (blockIdx.x * kWalkThreads + tid) >> 5, nwarps = (gridDim.x * kWalkThreads) >> 5;
-    const uint32_t n_items = (uint32_t)*P.n_items;
-    // contiguous item range of this warp
-    uint32_t next = (uint32_t)(((uint64_t)n_items * gw) / nwarps);
-    const uint32_t end = (uint32_t)(((uint64_t)n_items * (gw + 1)) / nwarps);
+constexpr int kWalkThreads = 256;
+constexpr int kWalkWarps = kWalkThreads / 32;
+#ifndef SBWT_B200_WALK_MINBLOCKS
+#define SBWT_B200_WALK_MINBLOCKS 4
+#endif
+#ifndef SBWT_B200_SINGLE_HOLD
+#define SBWT_B200_SINGLE_HOLD 2
+#endif
+#ifndef SBWT_B200_CHAINS
+#define SBWT_B200_CHAINS 2
+#endif
+constexpr uint32_t kSingleHold = SBWT_B200_SINGLE_HOLD; // extra NARROW steps on a singleton interval before it is queued (drops most chance survivors)
 
-    const int k = ix.k, p = ix.tp; // p: characters answered by the search table
-    const uint32_t pmask = p ? (uint32_t)((1ull << (2 * p)) - 1ull) : 0u;
-    const Sector* const sec_base = ix.sectors;
-    const uint64_t pol = make_l2_policy(P.index_evict_last != 0);
-    const pos_t last_col = (pos_t)(ix.n_nodes - 1);
-    // per-lane ring: code word W (absolute index) at ring[(W & 15) * 256 + tid], flag word V at ring[(16 + (V & 7)) * 256 + tid]
-    uint32_t ring_t = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)tid * 4u;
-    asm volatile("" : "+r"(ring_t)); // keep it in a register (the compiler otherwise rebuilds it from %tid every trip)
-    constexpr uint32_t kFlagOff = kRingCodeWords * kWalkThreads * 4;
+// chains per lane of the streaming CHAIN phase (wide indexes keep one: their columns and results are 64-bit registers)
+template <bool STREAMING, bool WIDE, bool LITERAL>
+struct ChainCount {
+    static constexpr int value = (STREAMING && !LITERAL && !WIDE) ? SBWT_B200_CHAINS : 1;
+};
 
-    auto load_chunk = [&](uint32_t ch) { // 64 bases: 4 code words + 2 flag words, asynchronously
-        if (ch < P.n_chunks) {
-            const uint32_t* gc = P.codes + (size_t)ch * 4;
-            const uint32_t* gv = P.invalid + (size_t)ch * 2;
-            const uint32_t dc = ring_t + ((ch & 3u) << 12);
-            cp_async_4(dc, gc);
-            cp_async_4(dc + 1024, gc + 1);
-            cp_async_4(dc + 2048, gc + 2);
-            cp_async_4(dc + 3072, gc + 3);
-            const uint32_t dv = ring_t + kFlagOff + ((ch & 3u) << 11);
-            cp_async_4(dv, gv);
-            cp_async_4(dv + 1024, gv + 1);
-        }
+template <bool WIDE, int NCH>
+struct WalkQueues {
+    typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
+    static constexpr int kCapV = 64;            // at most 32 are waiting when up to 32 more are pushed
+    static constexpr int kCap = 32 + 32 * NCH;  // S + P + F never exceed this together (see the scheduler)
+    // survivors that only have their own k-mer left (search mode, and the TODO ranges of streaming mode)
+    uint32_t v_base[kCapV], v_out[kCapV], v_meta[kCapV];
+    pos_t v_col[kCapV];
+    // survivors that go on streaming through their work item
+    uint32_t s_base[kCap], s_out[kCap], s_meta[kCap];
+    pos_t s_col[kCap];
+    // ranges of k-mers to be answered one lane per k-mer
+    uint32_t t_base[kCap], t_out[kCap], t_cnt[kCap];
+    // streaming mode: ranges (free of invalid bases) to be probed, and fresh items (restarts inside a read)
+    uint32_t p_base[kCap], p_out[kCap], p_cnt[kCap];
+    uint32_t f_base[kCap], f_out[kCap], f_cnt[kCap];
+    uint32_t own[32]; // PROBE: lane -> (range, probe number)
+};
+
+// the k-mer starting at base b as 2-bit codes, 16 per word, character j at bits [2j, 2j+2) of the window
+template <int KW>
+struct KmerWin {
+    uint32_t w[2 * KW];
+};
+
+template <int KW>
+__device__ __forceinline__ KmerWin<KW> load_win(const uint32_t* __restrict__ codes, uint32_t b) {
+    const uint32_t* p = codes + (b >> 4);
+    const uint32_t sh = (b & 15u) * 2u;
+    uint32_t x[2 * KW + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * KW + 1; i++) x[i] = __ldg(p + i);
+    KmerWin<KW> win;
+#pragma unroll
+    for (int i = 0; i < 2 * KW; i++) win.w[i] = __funnelshift_r(x[i], x[i + 1], sh);
+    return win;
+}
+
+template <int KW>
+__device__ __forceinline__ uint32_t win_char(const KmerWin<KW>& win, uint32_t j) {
+    uint32_t w = win.w[0];
+#pragma unroll
+    for (int i = 1; i < 2 * KW; i++) w = ((j >> 4) == (uint32_t)i) ? win.w[i] : w;
+    return (w >> ((j & 15u) * 2u)) & 3u;
+}
+
+// does the k-mer starting at base b cover a base outside ACGT (SBWT.hh:399,428)?
+template <int KW>
+__device__ __forceinline__ bool kmer_invalid(const uint32_t* __restrict__ inv, uint32_t b, int k) {
+    const uint32_t* p = inv + (b >> 5);
+    const uint32_t sh = b & 31u;
+    const uint32_t f0 = __ldg(p), f1 = __ldg(p + 1);
+    const uint32_t m0 = __funnelshift_r(f0, f1, sh);
+    if (KW == 1) return (m0 & (k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u))) != 0;
+    const uint32_t f2 = __ldg(p + 2);
+    const uint32_t m1 = __funnelshift_r(f1, f2, sh);
+    const int k1 = k - 32; // KW == 2 is used for 32 < k <= 64
+    return (m0 | (m1 & (k1 >= 32 ? 0xFFFFFFFFu : ((1u << k1) - 1u)))) != 0;
+}
+
+template <bool OUT32>
+__device__ __forceinline__ void store_result(const WalkParams& P, uint32_t o, int64_t v) {
+    if (OUT32) asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(P.out32 + o), "r"((int32_t)v) : "memory");
+    else asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(P.out + o), "l"(v) : "memory");
+}
+
+// One whole 32-byte sector of results (4 x int64 or 8 x int32) in one store (STG.E.256).
+__device__ __forceinline__ void st_sector_cs(void* p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+
+// The LITERAL chain writes one result per lane per step, each lane into its own read's slice of the output: as
+// single stores those are 32 partial-sector writes per warp and step, which L2 has to merge (and
+// fill from DRAM when the sector is gone again before its last part arrives: ncu r01d, 463 M
+// write-lookup misses and 17 GB of extra DRAM reads per 9.6 GB of results). So every lane collects
+// the results of one output sector in shared memory ([slot][lane]: conflict-free) and writes the
+// sector with one 256-bit store; only the ragged ends of a lane's run are written one by one.
+// (The non-LITERAL streaming chain keeps them in registers instead, see below.)
+template <bool OUT32>
+struct OutStage {
+    typedef typename std::conditional<OUT32, int32_t, int64_t>::type val_t;
+    static constexpr uint32_t R = OUT32 ? 8u : 4u; // results per sector
+    val_t v[R][32];
+};
+struct NoStage {};
+
+// ------------------------------------------------------------------ interval steps on the three layouts
+//
+// issue()/eval() split one singleton step into its memory request and its arithmetic, so that a lane can have the
+// requests of several chains in flight before it touches the first answer. eval() returns false when the answer has
+// to come from the classic sectors instead (a flagged csector); classic_step() gives it.
+template <bool WIDE, int LAY>
+struct Stepper {
+    typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
+    const Sector* sec;     // classic sectors
+    const Sector* cmp;     // csectors (LAY_C96 / LAY_C64)
+    const uint32_t* cbase; // LAY_C96
+    const int64_t* sbbase; // WIDE
+    int64_t n_sb;
+    int sb_shift;
+    uint64_t pol;          // L2 policy of the structure the walk lives on
+    uint64_t pol_cold;     // classic sectors of a compact index (the rarely read structure)
+
+    struct Load {
+        Sector s;
+        uint32_t base; // LAY_C96: cbase word
+        int64_t wbase; // WIDE: superblock base
     };
 
-    uint32_t cur = 0;        // first base of the current k-mer (index in the packed batch)
-    uint32_t oidx = 0;       // next result slot
-    uint32_t remaining = 0;  // k-mers left in the item, current one included; 0 = the lane needs an item
-    uint32_t vfrom = 0;      // k-mers starting before this base cover an invalid base
-    pos_t l = 0, r = 0;      // current interval
-    uint32_t j = 0;          // characters of the current k-mer already consumed
-    uint32_t fs = 0;         // this STEP is a streaming step (previous k-mer was found at column l)
-    uint32_t pf_valid = 0;   // trow holds the table row of k-mer cur + 1
-    // what ADVANCE has to do for this lane: nothing (the lane is parked in a STEP or idle), store -1,
-    // store l (the k-mer was found at column l), or set up the first k-mer of a new item
-    enum : uint32_t { A_NONE = 0, A_MISS = 1, A_HIT = 2, A_FRESH = 3 };
-    uint32_t pend = A_NONE;
-    TableRow<WIDE> trow;
-    trow.l = 0; trow.r = 0;
-    unsigned long long st_lookups = 0, st_hits = 0, st_ranks = 0, st_sectors = 0;
+    __device__ __forceinline__ void issue(Load& L, pos_t col, int c) const {
+        if (LAY == LAY_C64) {
+            L.s = ld_sector(cmp + ((uint32_t)col >> 6), pol);
+        } else if (LAY == LAY_C96) {
+            const uint32_t cb = (uint32_t)col / (uint32_t)kCBlockCols;
+            L.base = ld_cbase(cbase, cb, c); // in flight together with the csector
+            L.s = ld_sector(cmp + cb, pol);
+        } else {
+            const BlockPos bp = split_pos<WIDE>((int64_t)col);
+            if (WIDE) L.wbase = __ldg(sbbase + (int64_t)c * n_sb + (bp.blk >> sb_shift));
+            L.s = ld_sector(sector_ptr<WIDE>(sec, bp.blk, c), pol);
+        }
+    }
 
-    while (true) {
-        // ---- refill finished lanes from the warp's range
-        const unsigned need = __ballot_sync(FULL, remaining == 0);
-        if (need) {
-            if (next >= end) {
-                if (need == FULL) break;
-            } else {
-                const uint32_t mine = next + __popc(need & lt_mask);
-                next += __popc(need);
-                if (remaining == 0 && mine < end) {
-                    const uint4 it = __ldg(reinterpret_cast<const uint4*>(P.items) + mine);
-                    cur = it.x; oidx = it.y; remaining = it.z; vfrom = it.w;
-                    const uint32_t ch = cur >> 6;
-                    cp_async_wait_all(); // the previous item's read-ahead may still be landing in the ring
-                    load_chunk(ch);
-                    load_chunk(ch + 1);
-                    load_chunk(ch + 2);
-                    cp_async_wait_all();
-                    pend = A_FRESH; pf_valid = 0;
-                }
+    __device__ __forceinline__ bool eval(const Load& L, pos_t col, int c, pos_t& ncol, bool& hit) const {
+        if (LAY == LAY_C64) {
+            const CompactRank cr = c64_rank(L.s, c, (uint32_t)col & 63u);
+            ncol = (pos_t)cr.value;
+            hit = cr.bit != 0;
+            return !c64_flagged(L.s);
+        } else if (LAY == LAY_C96) {
+            const uint32_t cb = (uint32_t)col / (uint32_t)kCBlockCols, coff = (uint32_t)col - cb * (uint32_t)kCBlockCols;
+            const CompactRank cr = compact_rank(compact_match(L.s, c), L.base, coff);
+            ncol = (pos_t)cr.value;
+            hit = cr.bit != 0;
+            // (base is never all ones; testing it makes the flag test wait for it, so ptxas cannot sink its load behind a
+            // branch on the csector, where it would add a second dependent memory latency to every step)
+            return !(csector_flagged(L.s) | (L.base == 0xFFFFFFFFu));
+        } else {
+            const BlockPos bp = split_pos<WIDE>((int64_t)col);
+            const SectorPrefix pf = sector_prefix(L.s);
+            const uint32_t f = bp.off >> 5, rm = bp.off & 31u;
+            const uint32_t w = sector_word(L.s, f);
+            ncol = (pos_t)(L.s.w[0] + __byte_perm(pf.X, pf.Y, f) + __popc(w & ((1u << rm) - 1u)));
+            if (WIDE) ncol += (pos_t)L.wbase;
+            hit = ((w >> rm) & 1u) != 0;
+            return true;
+        }
+    }
+
+    // the same step from the classic sectors (every layout has them); blk = the block that was read
+    __device__ __forceinline__ void classic_step(pos_t col, int c, pos_t& ncol, bool& hit, int64_t& blk) const {
+        const BlockPos bp = split_pos<WIDE>((int64_t)col);
+        blk = bp.blk;
+        const Sector s = ld_sector(sector_ptr<WIDE>(sec, bp.blk, c), LAY == LAY_CLASSIC ? pol : pol_cold);
+        int64_t v = (int64_t)sector_rank(s, bp.off);
+        if (WIDE) v += __ldg(sbbase + (int64_t)c * n_sb + (bp.blk >> sb_shift));
+        ncol = (pos_t)v;
+        hit = sector_bit(s, bp.off) != 0;
+    }
+
+    // general step [l, r] -> [C[c] + rank_c(l), C[c] + rank_c(r + 1) - 1]; returns the sectors it had to read (1 or 2)
+    __device__ __forceinline__ uint32_t narrow(pos_t l, pos_t r, int c, pos_t& nl, pos_t& nr) const {
+        bool two = false, classic = true;
+        if (LAY == LAY_C64) {
+            const uint32_t p0 = (uint32_t)l, p1 = (uint32_t)r + 1u;
+            const uint32_t cb0 = p0 >> 6, cb1 = p1 >> 6;
+            two = cb1 != cb0;
+            const Sector s0 = ld_sector(cmp + cb0, pol);
+            Sector s1;
+            if (two) s1 = ld_sector(cmp + cb1, pol);
+            if (!(c64_flagged(s0) | (two && c64_flagged(s1)))) {
+                nl = (pos_t)c64_rank(s0, c, p0 & 63u).value;
+                nr = (pos_t)(two ? c64_rank(s1, c, p1 & 63u).value : c64_rank(s0, c, p1 & 63u).value);
+                classic = false;
+            }
+        } else if (LAY == LAY_C96) {
+            const uint32_t p0 = (uint32_t)l, p1 = (uint32_t)r + 1u;
+            const uint32_t cb0 = p0 / (uint32_t)kCBlockCols, cb1 = p1 / (uint32_t)kCBlockCols;
+            two = cb1 != cb0;
+            const uint32_t base0 = ld_cbase(cbase, cb0, c); // in flight together with the csectors
+            uint32_t base1 = base0;
+            if ((cb1 >> kCSbShift) != (cb0 >> kCSbShift)) base1 = ld_cbase(cbase, cb1, c);
+            const Sector s0 = ld_sector(cmp + cb0, pol);
+            Sector s1;
+            if (two) s1 = ld_sector(cmp + cb1, pol);
+            if (!(csector_flagged(s0) | (two && csector_flagged(s1)) | ((base0 & base1) == 0xFFFFFFFFu))) { // (bases: see eval)
+                const CompactMatch m0 = compact_match(s0, c);
+                nl = (pos_t)compact_rank(m0, base0, p0 - cb0 * (uint32_t)kCBlockCols).value;
+                if (two) nr = (pos_t)compact_rank(compact_match(s1, c), base1, p1 - cb1 * (uint32_t)kCBlockCols).value;
+                else nr = (pos_t)compact_rank(m0, base0, p1 - cb0 * (uint32_t)kCBlockCols).value;
+                classic = false;
             }
         }
-
-        // ---- STEP: the same instructions for every lane parked in a step
-        const bool step = remaining != 0 && pend == A_NONE;
-        const uint32_t q = cur + j;
-        const int c = (int)((lds_u32(ring_t + ((q << 6) & 0x3C00u)) >> ((q & 15u) * 2u)) & 3u);
-        const BlockPos b0 = split_pos<WIDE>((int64_t)l), b1 = split_pos<WIDE>((int64_t)r + 1);
-        const bool two = step && (b1.blk != b0.blk);
-        Sector s0, s1;
-        if (step) s0 = ld_sector(sector_ptr<WIDE>(sec_base, b0.blk, c), pol);
-        if (two) s1 = ld_sector(sector_ptr<WIDE>(sec_base, b1.blk, c), pol);
-        else s1 = s0;
-
-        const SectorPrefix pf0 = sector_prefix(s0);
-        const SectorPrefix pf1 = two ? sector_prefix(s1) : pf0;
-        pos_t nl = (pos_t)sector_rank_fast(s0, pf0, b0.off);
-        pos_t nr = (pos_t)sector_rank_fast(s1, pf1, b1.off);
-        if (WIDE && step) {
-            nl += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b0.blk >> ix.sb_shift));
-            nr += (pos_t)__ldg(ix.sbbase + (int64_t)c * ix.n_sb + (b1.blk >> ix.sb_shift));
+        if (classic) {
+            const uint64_t pc = LAY == LAY_CLASSIC ? pol : pol_cold;
+            const BlockPos b0 = split_pos<WIDE>((int64_t)l), b1 = split_pos<WIDE>((int64_t)r + 1);
+            two = b1.blk != b0.blk;
+            const Sector s0 = ld_sector(sector_ptr<WIDE>(sec, b0.blk, c), pc);
+            Sector s1;
+            if (two) s1 = ld_sector(sector_ptr<WIDE>(sec, b1.blk, c), pc);
+            const SectorPrefix pf0 = sector_prefix(s0);
+            nl = (pos_t)sector_rank_fast(s0, pf0, b0.off);
+            if (two) {
+                const SectorPrefix pf1 = sector_prefix(s1);
+                nr = (pos_t)sector_rank_fast(s1, pf1, b1.off);
+            } else {
+                nr = (pos_t)sector_rank_fast(s0, pf0, b1.off);
+            }
+            if (WIDE) {
+                nl += (pos_t)__ldg(sbbase + (int64_t)c * n_sb + (b0.blk >> sb_shift));
+                nr += (pos_t)__ldg(sbbase + (int64_t)c * n_sb + (b1.blk >> sb_shift));
+            }
         }
         nr -= 1;
-        bool miss = nl > nr; // empty interval (SBWT.hh:433)
-        if (COUNT && step) { st_ranks += 2; st_sectors += two ? 2 : 1; }
-        if (STREAMING && fs && step && (miss || !ix.edges_at_starts)) {
-            // literal form (SBWT.hh:562-563): the step has to start from the suffix-group start of
-            // column l. With edges only at group starts a set bit proves l is the start, so only a
-            // clear bit (or an index that violates the invariant) gets here.
-            int64_t s = (int64_t)l;
-            while (true) {
-                const uint32_t w = __ldg(ix.sgs + (s >> 5)) & (0xFFFFFFFFu >> (31 - (int)(s & 31)));
-                if (w) { s = (s & ~31ll) + (31 - __clz(w)); break; }
-                s = (s & ~31ll) - 1;
+        return two ? 2u : 1u;
+    }
+};
+
+// LITERAL (streaming mode on an index that violates "only suffix-group starts carry edges", i.e. a
+// hand-made file): streaming answers may then differ from search() answers, so the reference's
+// control flow is followed to the letter -- after a miss the k-mers are searched one at a time and
+// streaming resumes from the first one found (SBWT.hh:556-576); invalid bases are met by the chain.
+// LAY: the layout rank steps are answered from (device_index.cuh); the compact ones serve narrow, non-LITERAL kernels,
+// and a block flagged there (some column with no edge or several) is answered from the classic sectors.
+template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL, int LAY>
+__global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLOCKS) walk_kernel(const WalkParams P) {
+    static_assert(STREAMING || !LITERAL, "LITERAL is a streaming-mode variant");
+    static_assert(LAY == LAY_CLASSIC || (!WIDE && !LITERAL), "the compact layouts serve narrow indexes that keep the edge invariant");
+    typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
+    constexpr int NCH = ChainCount<STREAMING, WIDE, LITERAL>::value;
+    typedef WalkQueues<WIDE, NCH> QT;
+    __shared__ QT queues[kWalkWarps];
+    QT& Q = queues[threadIdx.x >> 5];
+    typedef typename std::conditional<LITERAL, OutStage<OUT32>, NoStage>::type StageT;
+    __shared__ StageT stages[LITERAL ? kWalkWarps : 1];
+    constexpr uint32_t OR = OUT32 ? 8u : 4u; // results per 32-byte output sector
+    // phase of result 0 inside its sector
+    const uint32_t oph = OUT32 ? (uint32_t)(((uintptr_t)P.out32 >> 2) & 7u) : (uint32_t)(((uintptr_t)P.out >> 3) & 3u);
+    const DeviceIndexView& ix = P.ix;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t n_items = (uint32_t)*P.n_items;
+    const uint32_t k = (uint32_t)ix.k, p = (uint32_t)ix.tp; // p: characters answered by the search table
+    const uint32_t pmask = p ? (uint32_t)((1ull << (2 * p)) - 1ull) : 0u;
+    Stepper<WIDE, LAY> ST;
+    ST.sec = ix.sectors; ST.cmp = ix.compact; ST.cbase = ix.cbase; ST.sbbase = ix.sbbase; ST.n_sb = ix.n_sb; ST.sb_shift = ix.sb_shift;
+    ST.pol = make_l2_policy(true);       // the index stays in L2 while reads and results stream through it
+    ST.pol_cold = make_l2_policy(false);
+    uint64_t pol_t = ST.pol;             // table rows
+    if (P.table_streams) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_t));
+    const pos_t last_col = (pos_t)(ix.n_nodes - 1);
+    constexpr uint32_t kGrab = STREAMING ? 32u : 8u; // items (streaming) or chunks (search) per cursor bump
+
+    uint32_t nV = 0, nS = 0, nT = 0, nP = 0, nF = 0; // queue fill, warp-uniform
+    uint32_t in_next = 0, in_end = 0;    // grabbed input range
+    bool input_done = false;
+    unsigned long long st_lookups = 0, st_hits = 0, st_ranks = 0, st_sectors = 0;
+    // probe stride in k-mers (0 = no probing: every k-mer after a miss is searched on its own)
+    const uint32_t D = (STREAMING && !LITERAL) ? P.probe_stride : 0u;
+
+    while (true) {
+        // ---- what to do next (warp-uniform)
+        // Every S, P or F entry becomes at most one entry downstream (S -> P -> F -> S|P), so their
+        // total only grows when input is taken, and input is taken only while it is <= 32 NCH: none of
+        // those queues ever holds more than 32 + 32 NCH entries. T receives at most 32 NCH entries from a
+        // CHAIN (run only while T holds <= 32) and at most 32 from a NARROW (run only while T is empty).
+        enum : int { T_CHAIN_V, T_CHAIN_S, T_NARROW_TODO, T_NARROW_INPUT, T_PROBE, T_EXIT };
+        int task;
+        bool take_input = false;
+        if (nV >= 32) task = T_CHAIN_V;
+        else if (STREAMING && nS >= 32u * NCH && nT <= 32) task = T_CHAIN_S;
+        else if (nT > 0) task = T_NARROW_TODO;
+        else if (STREAMING && nP >= 16) task = T_PROBE;
+        else if (STREAMING && nF >= 32) task = T_NARROW_INPUT;
+        else if (!input_done && (!STREAMING || nS + nP + nF <= 32u * NCH)) {
+            if (in_next >= in_end) {
+                uint32_t g = 0;
+                if (lane == 0) g = (uint32_t)atomicAdd(P.cursor, (unsigned long long)kGrab);
+                g = __shfl_sync(FULL, g, 0);
+                if (g >= n_items) { input_done = true; continue; }
+                in_next = g;
+                in_end = min(g + kGrab, n_items);
             }
-            if (COUNT) st_sectors++;
-            if (s != (int64_t)l) {
-                const BlockPos bs = split_pos<WIDE>(s);
-                const Sector ss = ld_sector(sector_ptr<WIDE>(sec_base, bs.blk, c), pol);
-                if (COUNT) st_sectors += bs.blk != b0.blk;
-                miss = sector_bit(ss, bs.off) == 0;
-                nl = (pos_t)lf_value<WIDE>(ix, ss, bs.blk, bs.off, c);
-                nr = nl;
+            task = T_NARROW_INPUT;
+            take_input = true;
+        } else if (STREAMING && nP > 0) task = T_PROBE;
+        else if (STREAMING && nF > 0) task = T_NARROW_INPUT;
+        else if (STREAMING && nS > 0) task = T_CHAIN_S;
+        else if (nV > 0) task = T_CHAIN_V;
+        else task = T_EXIT;
+        if (task == T_EXIT) break;
+
+        if (STREAMING && !LITERAL && task == T_CHAIN_S) {
+            // ================================================================ CHAIN, streaming (SBWT.hh:561-575)
+            // Every lane owns up to NCH survivors. A chain first finishes its own k-mer (`quiet` steps without a result,
+            // then the step that completes it), then every further step answers the next k-mer of its work item.
+            const uint32_t m = min(32u * NCH, nS), q0 = nS - m;
+            nS = q0;
+            bool act[NCH];
+            pos_t col[NCH];
+            uint32_t pos[NCH], cw[NCH], nx[NCH], o[NCH], oend[NCH], quiet[NCH], pre[NCH];
+            bool fs[NCH]; // the chain is past its first k-mer: its steps are streaming steps
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                const uint32_t qi = (uint32_t)i * 32u + (uint32_t)lane;
+                act[i] = qi < m;
+                col[i] = 0; pos[i] = 0; cw[i] = 0; nx[i] = 0; o[i] = 0; oend[i] = 0; quiet[i] = 0; pre[i] = 0; fs[i] = false;
+                if (act[i]) {
+                    const uint32_t b = Q.s_base[q0 + qi], meta = Q.s_meta[q0 + qi];
+                    o[i] = Q.s_out[q0 + qi];
+                    col[i] = Q.s_col[q0 + qi];
+                    const uint32_t j = meta & 0xFFu;
+                    oend[i] = o[i] + (meta >> 8);
+                    pos[i] = b + j; // next base to consume
+                    cw[i] = __ldg(P.codes + (pos[i] >> 4));
+                    nx[i] = __ldg(P.codes + (pos[i] >> 4) + 1);
+                    if (j == k) { // NARROW already completed the first k-mer: its column is the answer (SBWT.hh:410-413)
+                        store_result<OUT32>(P, o[i], (int64_t)col[i]);
+                        if (COUNT) { st_lookups++; st_hits++; }
+                        o[i]++;
+                        fs[i] = true;
+                        if (o[i] == oend[i]) act[i] = false;
+                    } else {
+                        quiet[i] = k - j - 1u;
+                    }
+                    // results written one by one until the chain's next result starts an output sector; the chain's own
+                    // first k-mer (when still open) is the first of them
+                    const uint32_t first_emit = o[i]; // index of the next result this chain produces
+                    const uint32_t a = (0u - (first_emit + oph)) & (OR - 1u);
+                    pre[i] = quiet[i] + a;
+                }
+            }
+            __syncwarp();
+
+            // one step of chain i on character c: its answer from the layout (L already issued) or from the slow path
+            auto resolve = [&](pos_t colv, int c, bool streaming_step, pos_t& ncol, bool& hit) {
+                // classic sectors; a clear bit on a streaming step takes the literal walk-back (SBWT.hh:562-563): the step
+                // starts from the suffix-group start of col (which alone carries the group's edges)
+                int64_t cblk;
+                ST.classic_step(colv, c, ncol, hit, cblk);
+                if (!hit && streaming_step) {
+                    int64_t g = (int64_t)colv;
+                    while (true) {
+                        const uint32_t sw = __ldg(ix.sgs + (g >> 5)) & (0xFFFFFFFFu >> (31 - (int)(g & 31)));
+                        if (sw) { g = (g & ~31ll) + (31 - __clz(sw)); break; }
+                        g = (g & ~31ll) - 1;
+                    }
+                    if (COUNT) st_sectors++;
+                    if (g != (int64_t)colv) {
+                        int64_t gblk;
+                        ST.classic_step((pos_t)g, c, ncol, hit, gblk);
+                        if (COUNT) st_sectors += gblk != cblk;
+                    }
+                }
+            };
+            // the rest of a chain's item after a miss is searched from scratch (SBWT.hh:557-559): probed (D) or one lane each
+            auto push_rest = [&](bool want, uint32_t kstart, uint32_t ov, uint32_t oendv) { // (warp-uniform call)
+                const unsigned pm = __ballot_sync(FULL, want);
+                if (pm) { // (a chain only covers k-mers free of invalid bases, so the range may be probed)
+                    const uint32_t at = (D ? nP : nT) + __popc(pm & lt_mask);
+                    if (want) {
+                        if (D) { Q.p_base[at] = kstart + 1u; Q.p_out[at] = ov; Q.p_cnt[at] = oendv - ov; }
+                        else { Q.t_base[at] = kstart + 1u; Q.t_out[at] = ov; Q.t_cnt[at] = oendv - ov; }
+                    }
+                    if (D) nP += __popc(pm); else nT += __popc(pm);
+                }
+            };
+            auto advance = [&](int i) { // one base consumed
+                pos[i]++;
+                const uint32_t ph = pos[i] & 15u;
+                if (ph == 0) cw[i] = nx[i];
+                // the next code word, every 16 bases, loaded IN PLACE under a predicate: nothing reads nx for the next 16
+                // steps, so no step waits for this load (a plain conditional load went through a temporary register and a
+                // move that stalled every iteration on some lane's refill: 15 % of the round-1 kernel's stall samples)
+                asm volatile("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
+                             : "+r"(nx[i]) : "l"(P.codes + (pos[i] >> 4) + 1), "r"(ph));
+            };
+
+            while (true) {
+                // ---- general loop: own k-mers, the results in front of the next whole output sector, and everything
+                // unusual (misses, walk-backs, flagged csectors, chain ends). Chain i steps while pre[i] > 0.
+                while (true) {
+                    bool run[NCH], any = false;
+#pragma unroll
+                    for (int i = 0; i < NCH; i++) { run[i] = act[i] && pre[i] > 0; any |= run[i]; }
+                    if (!__any_sync(FULL, any)) break;
+                    typename Stepper<WIDE, LAY>::Load L[NCH];
+                    int c[NCH];
+#pragma unroll
+                    for (int i = 0; i < NCH; i++) {
+                        c[i] = (int)((cw[i] >> ((pos[i] & 15u) * 2u)) & 3u);
+                        if (run[i]) ST.issue(L[i], col[i], c[i]);
+                    }
+                    uint32_t wantm = 0; // bit i: chain i ended in a miss and leaves k-mers behind
+                    uint32_t kstart[NCH];
+#pragma unroll
+                    for (int i = 0; i < NCH; i++) {
+                        kstart[i] = 0;
+                        if (run[i]) {
+                            pos_t ncol = 0;
+                            bool hit = false;
+                            const bool streaming_step = fs[i];
+                            if (!ST.eval(L[i], col[i], c[i], ncol, hit) || (!hit && streaming_step)) resolve(col[i], c[i], streaming_step, ncol, hit);
+                            if (COUNT) { st_ranks += 2; st_sectors += 1; }
+                            pre[i]--;
+                            if (hit) {
+                                col[i] = ncol;
+                                advance(i);
+                                if (quiet[i] > 0) quiet[i]--;
+                                else {
+                                    store_result<OUT32>(P, o[i], (int64_t)col[i]);
+                                    if (COUNT) { st_lookups++; st_hits++; }
+                                    o[i]++;
+                                    fs[i] = true;
+                                    if (o[i] == oend[i]) act[i] = false;
+                                }
+                            } else { // the k-mer this step belongs to is absent: [col, col] -> empty (SBWT.hh:433) / l != r (SBWT.hh:574)
+                                kstart[i] = pos[i] - (k - 1u - quiet[i]);
+                                store_result<OUT32>(P, o[i], -1);
+                                if (COUNT) st_lookups++;
+                                o[i]++;
+                                act[i] = false;
+                                if (o[i] < oend[i]) wantm |= 1u << i;
+                            }
+                        }
+                    }
+                    if (__any_sync(FULL, wantm != 0)) {
+#pragma unroll
+                        for (int i = 0; i < NCH; i++) push_rest((wantm >> i) & 1u, kstart[i], o[i], oend[i]);
+                        __syncwarp();
+                    }
+                }
+
+                // ---- how many whole output sectors every running chain still has in front of it
+                uint32_t myr = 0xFFFFFFFFu;
+                bool anyact = false;
+#pragma unroll
+                for (int i = 0; i < NCH; i++) {
+                    if (act[i]) {
+                        const uint32_t left = oend[i] - o[i];
+                        if (left < OR) pre[i] = left; // fewer than a sector: finished in the general loop
+                        myr = min(myr, left / OR);
+                        anyact = true;
+                    }
+                }
+                if (!__any_sync(FULL, anyact)) break;
+                const uint32_t rounds = __reduce_min_sync(FULL, myr);
+                if (rounds == 0) continue;
+
+                // ---- steady state: every running chain's next result opens an output sector (a chain whose own k-mer is
+                // still open has quiet == 0 here: its next step completes it) and none of them ends within `rounds` sectors.
+                // One step and one result per chain and iteration, the results of a sector collect in registers and leave as
+                // one 32-byte store per chain. The first iteration in which any chain's step is not a plain hit is left
+                // uncommitted to the general loop.
+                pos_t slot[NCH][OR];
+#pragma unroll
+                for (int i = 0; i < NCH; i++)
+#pragma unroll
+                    for (uint32_t t = 0; t < OR; t++) slot[i][t] = 0;
+                uint32_t broke_at = OR; // OR: the run ended on a sector boundary
+                uint32_t done = 0;      // sectors written per chain
+                for (uint32_t rd = 0; rd < rounds; rd++) {
+#pragma unroll
+                    for (uint32_t sl = 0; sl < OR; sl++) {
+                        typename Stepper<WIDE, LAY>::Load L[NCH];
+                        int c[NCH];
+#pragma unroll
+                        for (int i = 0; i < NCH; i++) {
+                            c[i] = (int)((cw[i] >> ((pos[i] & 15u) * 2u)) & 3u);
+                            if (act[i]) ST.issue(L[i], col[i], c[i]);
+                        }
+                        pos_t ncol[NCH];
+                        bool okall = true;
+#pragma unroll
+                        for (int i = 0; i < NCH; i++) {
+                            ncol[i] = 0;
+                            if (act[i]) {
+                                bool hit = false;
+                                const bool fast = ST.eval(L[i], col[i], c[i], ncol[i], hit);
+                                okall &= fast && hit;
+                            }
+                        }
+                        if (!__all_sync(FULL, okall)) { broke_at = sl; break; }
+#pragma unroll
+                        for (int i = 0; i < NCH; i++) {
+                            if (act[i]) {
+                                slot[i][sl] = ncol[i];
+                                col[i] = ncol[i];
+                                advance(i);
+                            }
+                        }
+                    }
+                    if (broke_at != OR) break;
+#pragma unroll
+                    for (int i = 0; i < NCH; i++) {
+                        if (act[i]) {
+                            uint32_t wv[8];
+                            if (OUT32) {
+#pragma unroll
+                                for (int t = 0; t < 8; t++) wv[t] = (uint32_t)slot[i][t & (OR - 1u)];
+                                st_sector_cs(P.out32 + o[i], wv);
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 4; t++) {
+                                    const unsigned long long q = (unsigned long long)(int64_t)slot[i][t & (OR - 1u)];
+                                    wv[2 * t] = (uint32_t)q;
+                                    wv[2 * t + 1] = WIDE ? (uint32_t)(q >> 32) : 0u; // (narrow: every value here is a column < 2^32)
+                                }
+                                st_sector_cs(P.out + o[i], wv);
+                            }
+                            o[i] += OR;
+                        }
+                    }
+                    done++;
+                }
+                // ---- bookkeeping of the run: staged results of a broken sector go out one by one, and every chain is
+                // brought back to a sector boundary by the general loop (the chain that broke the run takes its unusual
+                // step there)
+                const uint32_t nb = broke_at != OR ? broke_at : 0u;
+#pragma unroll
+                for (int i = 0; i < NCH; i++) {
+                    if (act[i]) {
+                        if (COUNT) { const uint32_t n = done * OR + nb; st_ranks += 2ull * n; st_sectors += n; st_lookups += n; st_hits += n; }
+                        if (done + nb > 0) fs[i] = true;
+#pragma unroll
+                        for (uint32_t t = 0; t < OR; t++)
+                            if (t < nb) store_result<OUT32>(P, o[i] + t, (int64_t)slot[i][t]);
+                        o[i] += nb;
+                        if (o[i] == oend[i]) act[i] = false;
+                        else if (broke_at != OR) {
+                            const uint32_t a2 = (0u - (o[i] + oph)) & (OR - 1u);
+                            pre[i] = a2 ? a2 : OR;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+
+        if (task == T_CHAIN_V || task == T_CHAIN_S) {
+            // ================================================================ CHAIN: survivors' own k-mers; LITERAL streaming
+            const bool sb = STREAMING && LITERAL && task == T_CHAIN_S;
+            uint32_t* const qb = sb ? Q.s_base : Q.v_base;
+            uint32_t* const qo = sb ? Q.s_out : Q.v_out;
+            uint32_t* const qm = sb ? Q.s_meta : Q.v_meta;
+            pos_t* const qc = sb ? Q.s_col : Q.v_col;
+            const uint32_t nq = sb ? nS : nV;
+            const uint32_t m = min(32u, nq), q0 = nq - m;
+            if (sb) nS = q0; else nV = q0;
+            bool act = (uint32_t)lane < m;
+            uint32_t o = 0, j = 0, rem = 0, pos = 0, cw = 0, nx = 0;
+            pos_t col = 0;
+            if (act) {
+                const uint32_t b = qb[q0 + lane], meta = qm[q0 + lane];
+                o = qo[q0 + lane];
+                col = qc[q0 + lane];
+                j = meta & 0xFFu;
+                rem = meta >> 8;
+                pos = b + j; // next base to consume
+                cw = __ldg(P.codes + (pos >> 4));
+                nx = __ldg(P.codes + (pos >> 4) + 1);
+            }
+            __syncwarp();
+            bool fs = false; // the lane is past its first k-mer: its steps are streaming steps (SBWT.hh:561-575)
+            uint32_t gs = o; // first result staged and not yet written
+            // result number x of this lane -> stage; a completed sector goes out in one store
+            auto emit = [&](uint32_t x, int64_t v) {
+                if (!LITERAL || !sb) { // one result per lane: nothing to collect
+                    store_result<OUT32>(P, x, v);
+                    gs = x + 1u;
+                    return;
+                }
+                if constexpr (LITERAL) {
+                    OutStage<OUT32>& OS = stages[threadIdx.x >> 5];
+                    const uint32_t sl = (x + oph) & (OR - 1u);
+                    OS.v[sl][lane] = (typename OutStage<OUT32>::val_t)v;
+                    if (sl == OR - 1u) {
+                        if (x - gs == OR - 1u) {
+                            uint32_t wv[8];
+                            if (OUT32) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) wv[i] = (uint32_t)OS.v[i & (OR - 1u)][lane];
+                                st_sector_cs(P.out32 + (x - 7u), wv);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    const unsigned long long q = (unsigned long long)OS.v[i & (OR - 1u)][lane];
+                                    wv[2 * i] = (uint32_t)q;
+                                    wv[2 * i + 1] = (uint32_t)(q >> 32);
+                                }
+                                st_sector_cs(P.out + (x - 3u), wv);
+                            }
+                        } else {
+                            for (uint32_t y = gs; y <= x; y++) store_result<OUT32>(P, y, (int64_t)OS.v[(y + oph) & (OR - 1u)][lane]);
+                        }
+                        gs = x + 1u;
+                    }
+                }
+            };
+            auto drain = [&](uint32_t end) { // the lane's run is over: write what is still staged, [gs, end)
+                if constexpr (LITERAL) {
+                    OutStage<OUT32>& OS = stages[threadIdx.x >> 5];
+                    for (uint32_t y = gs; y < end; y++) store_result<OUT32>(P, y, (int64_t)OS.v[(y + oph) & (OR - 1u)][lane]);
+                }
+                gs = end;
+            };
+            while (true) {
+                if (act && j == k) { // a k-mer's interval is a singleton (SBWT.hh:410-413): its column is the answer
+                    emit(o, (int64_t)col);
+                    if (COUNT) { st_lookups++; st_hits++; }
+                    o++;
+                    rem--;
+                    if (rem == 0) { act = false; drain(o); }
+                    else { j = k - 1; fs = true; }
+                }
+                if (!__any_sync(FULL, act)) break;
+                bool miss = false;
+                if (act) {
+                    const int c = (int)((cw >> ((pos & 15u) * 2u)) & 3u);
+                    pos_t ncol = 0;
+                    int64_t cblk = -1; // classic block of col, when it was read
+                    bool hit = false;
+                    typename Stepper<WIDE, LAY>::Load L;
+                    ST.issue(L, col, c);
+                    if (!ST.eval(L, col, c, ncol, hit)) ST.classic_step(col, c, ncol, hit, cblk);
+                    else if (LAY == LAY_CLASSIC) cblk = split_pos<WIDE>((int64_t)col).blk;
+                    miss = !hit; // [col, col] -> empty interval (SBWT.hh:433) / l != r (SBWT.hh:574)
+                    if (COUNT) { st_ranks += 2; st_sectors += 1; }
+                    bool bad = false; // LITERAL: the chain can run into a base outside ACGT (SBWT.hh:565-568)
+                    if (LITERAL && fs) bad = ((__ldg(P.invalid + (pos >> 5)) >> (pos & 31u)) & 1u) != 0;
+                    if (STREAMING && LITERAL && fs && !bad) {
+                        // literal form (SBWT.hh:562-563): the step starts from the suffix-group start of col
+                        int64_t g = (int64_t)col;
+                        while (true) {
+                            const uint32_t sw = __ldg(ix.sgs + (g >> 5)) & (0xFFFFFFFFu >> (31 - (int)(g & 31)));
+                            if (sw) { g = (g & ~31ll) + (31 - __clz(sw)); break; }
+                            g = (g & ~31ll) - 1;
+                        }
+                        if (COUNT) st_sectors++;
+                        if (g != (int64_t)col) {
+                            int64_t gblk;
+                            ST.classic_step((pos_t)g, c, ncol, hit, gblk);
+                            if (COUNT) st_sectors += gblk != cblk;
+                            miss = !hit;
+                        }
+                    }
+                    if (bad) miss = true;
+                    if (!miss) {
+                        col = ncol;
+                        j++;
+                        pos++;
+                        if ((pos & 15u) == 0) { cw = nx; nx = __ldg(P.codes + (pos >> 4) + 1); }
+                    }
+                }
+                const bool ended = act && miss;
+                if (ended) {
+                    emit(o, -1);
+                    if (COUNT) st_lookups++;
+                    o++;
+                    rem--;
+                    act = false;
+                    drain(o);
+                }
+                if (STREAMING) { // the k-mers after a miss are searched from scratch (SBWT.hh:557-559), one lane each
+                    const bool push = ended && rem > 0;
+                    const unsigned pm = __ballot_sync(FULL, push);
+                    if (pm) {
+                        const uint32_t at = nT + __popc(pm & lt_mask);
+                        if (push) { Q.t_base[at] = pos - j + 1; Q.t_out[at] = o; Q.t_cnt[at] = rem; }
+                        nT += __popc(pm);
+                        __syncwarp();
+                    }
+                }
+            }
+            continue;
+        }
+
+        // ==================================================================== NARROW
+        // lanes = first k-mers of up to 32 work items or fresh items (LITERAL: also the next k-mer of a TODO
+        // range, alone); or 32 k-mers of a TODO range / search chunk; or the probes of a few P ranges
+        const bool probe = STREAMING && task == T_PROBE;
+        const bool first = STREAMING && (task == T_NARROW_INPUT || LITERAL);
+        bool act = false;
+        uint32_t b = 0, o = 0, cnt = 1, nvalid = 1;
+        uint32_t pr_tb = 0, pr_to = 0, pr_tc = 0, pr_np = 0, pr_S = 0, G = 0, seg_lo = 0, xm = 0; // PROBE
+        if (probe) {
+            // lanes 0 .. G-1 hold the top G ranges of P (as many as give <= 32 probes), then every lane takes one probe
+            const uint32_t n_take = min(nP, 32u);
+            if ((uint32_t)lane < n_take) {
+                const uint32_t t = nP - 1 - lane;
+                pr_tb = Q.p_base[t]; pr_to = Q.p_out[t]; pr_tc = Q.p_cnt[t];
+                pr_np = min((pr_tc + D - 1) / max(D, 1u), 32u);
+            }
+            pr_S = pr_np;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, pr_S, s);
+                if (lane >= s) pr_S += t;
+            }
+            G = __popc(__ballot_sync(FULL, (uint32_t)lane < n_take && pr_S <= 32u));
+            const uint32_t total = __shfl_sync(FULL, pr_S, G - 1);
+            __syncwarp();
+            if ((uint32_t)lane < G)
+                for (uint32_t t = 0; t < pr_np; t++) Q.own[pr_S - pr_np + t] = (uint32_t)lane | (t << 8);
+            nP -= G;
+            __syncwarp();
+            act = (uint32_t)lane < total;
+            const uint32_t ow = act ? Q.own[lane] : 0u;
+            const uint32_t tb = __shfl_sync(FULL, pr_tb, ow & 0xFFu), to = __shfl_sync(FULL, pr_to, ow & 0xFFu);
+            const uint32_t tc = __shfl_sync(FULL, pr_tc, ow & 0xFFu);
+            seg_lo = (ow >> 8) * D;
+            xm = min(seg_lo + D, tc) - 1u; // the probe is the last k-mer of its segment
+            b = tb + xm;
+            o = to + xm;
+        } else if (task == T_NARROW_TODO) {
+            const uint32_t t = nT - 1;
+            const uint32_t tb = Q.t_base[t], to = Q.t_out[t], tc = Q.t_cnt[t];
+            __syncwarp();
+            if (LITERAL) { // one k-mer; its survivor streams on through the rest of the range
+                act = lane == 0;
+                b = tb; o = to; cnt = tc; nvalid = tc;
+                nT = t;
+            } else {
+                act = (uint32_t)lane < tc;
+                b = tb + lane;
+                o = to + lane;
+                if (tc > 32) {
+                    if (lane == 0) { Q.t_base[t] = tb + 32; Q.t_out[t] = to + 32; Q.t_cnt[t] = tc - 32; }
+                } else nT = t;
+            }
+            __syncwarp();
+        } else if (!STREAMING) {
+            const uint4 it = __ldg(reinterpret_cast<const uint4*>(P.items) + in_next);
+            in_next++;
+            act = (uint32_t)lane < it.z;
+            b = it.x + lane;
+            o = it.y + lane;
+        } else {
+            // fresh items first, then new work items
+            const uint32_t n_f = min(nF, 32u);
+            bool have = false;
+            if ((uint32_t)lane < n_f) {
+                const uint32_t t = nF - 1 - lane;
+                b = Q.f_base[t]; o = Q.f_out[t]; cnt = Q.f_cnt[t]; nvalid = cnt;
+                have = true;
+            }
+            nF -= n_f;
+            if (take_input) {
+                const uint32_t m = min(32u - n_f, in_end - in_next);
+                if ((uint32_t)lane >= n_f && (uint32_t)lane - n_f < m) {
+                    const uint4 it = __ldg(reinterpret_cast<const uint4*>(P.items) + in_next + ((uint32_t)lane - n_f));
+                    b = it.x; o = it.y; cnt = it.z; nvalid = it.w;
+                    have = true;
+                }
+                in_next += m;
+            }
+            act = have && nvalid > 0;
+            // an item whose first k-mer covers an invalid base is answered one lane per k-mer
+            const bool push = have && nvalid == 0;
+            const unsigned pm = __ballot_sync(FULL, push);
+            if (pm) {
+                const uint32_t at = nT + __popc(pm & lt_mask);
+                if (push) { Q.t_base[at] = b; Q.t_out[at] = o; Q.t_cnt[at] = cnt; }
+                nT += __popc(pm);
             }
         }
-        // the lane's state after the step, as selects (no control flow: every lane runs the same code)
-        if (step) {
-            l = nl;
-            r = nr;
-            j++;
-            fs = 0;
-            // a k-mer interval is a singleton (SBWT.hh:410-413)
-            pend = miss ? (uint32_t)A_MISS : (j == (uint32_t)k ? (uint32_t)A_HIT : (uint32_t)A_NONE);
+
+        KmerWin<KW> win;
+#pragma unroll
+        for (int i = 0; i < 2 * KW; i++) win.w[i] = 0;
+        bool alive = act;
+        if (act) {
+            win = load_win<KW>(P.codes, b);
+            if (!probe && (!first || (LITERAL && task == T_NARROW_TODO))) alive = !kmer_invalid<KW>(P.invalid, b, (int)k);
+        }
+        pos_t l = 0, r = last_col;
+        if (p != 0 && alive) {
+            // first character = least significant digit of the table index (SBWT.hh:396-401)
+            const TableRow<WIDE> row = TableRow<WIDE>::load(ix.table, win.w[0] & pmask, pol_t);
+            l = (pos_t)row.l;
+            r = (pos_t)row.r;
+            if (row.absent()) alive = false;
+            if (COUNT) st_sectors++;
+        }
+        // jl: characters consumed; when the walk dies, the string of the first jl + 1 characters is absent
+        // (a row missing from the table: its p characters are)
+        uint32_t jl = (p != 0 && act && !alive) ? p - 1u : p, single = (alive && l == r) ? 1u : 0u;
+        while (true) {
+            const bool go = alive && jl < k && single <= kSingleHold;
+            if (!__any_sync(FULL, go)) break;
+            if (go) {
+                const int c = (int)win_char<KW>(win, jl);
+                pos_t nl = 0, nr = 0;
+                const uint32_t ns = ST.narrow(l, r, c, nl, nr);
+                if (COUNT) { st_ranks += 2; st_sectors += ns; }
+                if (nl > nr) alive = false; // empty interval (SBWT.hh:433)
+                else {
+                    l = nl;
+                    r = nr;
+                    jl++;
+                    single = (nl == nr) ? single + 1 : 0u;
+                }
+            }
+        }
+        const bool dead = act && !alive;
+        if (probe) {
+            // a dead probe proves the k-mers [xm + jl + 1 - k, xm] of its range absent; "covered": its whole segment
+            const bool covered = dead && (int)(xm + jl + 1u) - (int)k <= (int)seg_lo;
+            const unsigned badmask = __ballot_sync(FULL, act && !covered);
+            uint32_t nfill = 0;
+            bool cont = false, fresh = false;
+            if ((uint32_t)lane < G) {
+                const uint32_t lo = pr_S - pr_np;
+                const unsigned bm = badmask & ((pr_np >= 32u ? FULL : ((1u << pr_np) - 1u)) << lo);
+                if (bm) { // restart the read at the first segment that is not proven absent
+                    nfill = (uint32_t)(__ffs(bm) - 1 - (int)lo) * D;
+                    cont = fresh = true;
+                } else { // all probed segments are absent; a range longer than 32 segments goes on being probed
+                    nfill = min(pr_tc, pr_np * D);
+                    cont = nfill < pr_tc;
+                }
+            }
+            const unsigned fm = __ballot_sync(FULL, cont && fresh), rm = __ballot_sync(FULL, cont && !fresh);
+            if (fm) {
+                const uint32_t at = nF + __popc(fm & lt_mask);
+                if (cont && fresh) { Q.f_base[at] = pr_tb + nfill; Q.f_out[at] = pr_to + nfill; Q.f_cnt[at] = pr_tc - nfill; }
+                nF += __popc(fm);
+            }
+            if (rm) {
+                const uint32_t at = nP + __popc(rm & lt_mask);
+                if (cont && !fresh) { Q.p_base[at] = pr_tb + nfill; Q.p_out[at] = pr_to + nfill; Q.p_cnt[at] = pr_tc - nfill; }
+                nP += __popc(rm);
+            }
+            for (uint32_t g = 0; g < G; g++) { // the proven misses, 32 consecutive results per store
+                const uint32_t to = __shfl_sync(FULL, pr_to, g), nf = __shfl_sync(FULL, nfill, g);
+                for (uint32_t x = lane; x < nf; x += 32) {
+                    store_result<OUT32>(P, to + x, -1);
+                    if (COUNT) st_lookups++;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        if (dead) {
+            store_result<OUT32>(P, o, -1);
+            if (COUNT) st_lookups++;
+        }
+        if (!first) {
+            if (alive && jl == k) { // complete: the interval is a singleton (SBWT.hh:410-413)
+                store_result<OUT32>(P, o, (int64_t)l);
+                if (COUNT) { st_lookups++; st_hits++; }
+            }
+            const bool surv = alive && jl < k;
+            const unsigned sm = __ballot_sync(FULL, surv);
+            if (sm) {
+                const uint32_t at = nV + __popc(sm & lt_mask);
+                if (surv) { Q.v_base[at] = b; Q.v_out[at] = o; Q.v_meta[at] = jl | (1u << 8); Q.v_col[at] = l; }
+                nV += __popc(sm);
+            }
+        } else {
+            // what streaming cannot reach is answered one lane per k-mer: everything after a first
+            // k-mer that is absent, and everything from the first k-mer that covers an invalid base on
+            // (with probing: the k-mers up to the first invalid base are probed, the rest is answered per k-mer)
+            const bool pd = dead && cnt > 1 && D == 0, pa = (alive || (dead && D != 0)) && nvalid < cnt;
+            const unsigned tm = __ballot_sync(FULL, pd || pa);
+            if (tm) {
+                const uint32_t at = nT + __popc(tm & lt_mask);
+                const uint32_t skip = pd ? 1u : nvalid;
+                if (pd || pa) { Q.t_base[at] = b + skip; Q.t_out[at] = o + skip; Q.t_cnt[at] = cnt - skip; }
+                nT += __popc(tm);
+            }
+            const bool pp = dead && D != 0 && nvalid > 1;
+            const unsigned ppm = __ballot_sync(FULL, pp);
+            if (ppm) {
+                const uint32_t at = nP + __popc(ppm & lt_mask);
+                if (pp) { Q.p_base[at] = b + 1; Q.p_out[at] = o + 1; Q.p_cnt[at] = nvalid - 1; }
+                nP += __popc(ppm);
+            }
+            const unsigned sm = __ballot_sync(FULL, alive);
+            if (sm) {
+                const uint32_t at = nS + __popc(sm & lt_mask);
+                if (alive) { Q.s_base[at] = b; Q.s_out[at] = o; Q.s_meta[at] = jl | (nvalid << 8); Q.s_col[at] = l; }
+                nS += __popc(sm);
+            }
         }
         __syncwarp();
-
-        // ---- ADVANCE, straight-line and predicated: store one result and set up the lane's next k-mer.
-        // A k-mer that needs no walk (a non-ACGT byte inside, its first p characters absent from the
-        // table, p == k) leaves `pend` set, and the lane comes back here on the next trip without a STEP.
-        {
-            const bool adv = pend != A_NONE;
-            const bool hit = pend == A_HIT;
-            const bool moved = adv && pend != A_FRESH; // a result to store, one k-mer forward
-            const bool stored = moved && !P.debug_no_store;
-            // one predicated streaming store (written as PTX: the compiler otherwise builds a jump table on `pend`)
-            if (OUT32) {
-                asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.cs.s32 [%1], %2; }" ::"r"((uint32_t)stored),
-                             "l"(P.out32 + oidx), "r"(hit ? (int32_t)l : -1)
-                             : "memory");
-            } else {
-                asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.cs.s64 [%1], %2; }" ::"r"((uint32_t)stored),
-                             "l"(P.out + oidx), "l"(hit ? (int64_t)l : (int64_t)-1)
-                             : "memory");
-            }
-            if (COUNT && moved) { st_lookups++; st_hits += hit; }
-            const uint32_t inc = moved ? 1u : 0u;
-            oidx += inc;
-            cur += inc;
-            remaining -= inc;
-            if (moved && (cur & 63u) == 0) { // entering a new chunk: the one after it was requested 64 k-mers ago
-                cp_async_wait_all();
-                load_chunk((cur >> 6) + 2);
-            }
-            const bool su = adv && remaining != 0; // a k-mer to set up
-            // the only base of this k-mer not seen by its predecessor
-            const uint32_t qn = cur + (uint32_t)k - 1u;
-            const uint32_t flag = (lds_u32(ring_t + kFlagOff + ((qn << 5) & 0x1C00u)) >> (qn & 31u)) & 1u;
-            if (su && flag) vfrom = qn + 1u;
-            const bool kvalid = cur >= vfrom;
-            const bool stream = STREAMING && su && kvalid && hit;
-            const bool scratch = su && kvalid && !stream;
-            TableRow<WIDE> row;
-            row.l = 0;
-            row.r = last_col;
-            bool row_absent = false;
-            uint32_t new_pf = 0;
-            if (p != 0) {
-                // the first 16 bases of the k-mer; first character = least significant digit (SBWT.hh:396-401)
-                const uint32_t w0 = lds_u32(ring_t + ((cur << 6) & 0x3C00u));
-                const uint32_t w1 = lds_u32(ring_t + (((cur + 16u) << 6) & 0x3C00u));
-                const uint32_t E = __funnelshift_r(w0, w1, (cur & 15u) * 2u);
-                row = trow;
-                if (scratch && !pf_valid) row = TableRow<WIDE>::load(ix.table, E & pmask, pol);
-                if (COUNT && scratch) st_sectors++; // one table sector per from-scratch k-mer, however it was fetched
-                if (scratch && remaining > 1) { // the next k-mer's row, in flight while this one is walked
-                    trow = TableRow<WIDE>::load(ix.table, (E >> 2) & pmask, pol);
-                    new_pf = 1;
-                }
-                row_absent = row.absent();
-            }
-            if (adv) pf_valid = new_pf;
-            if (stream) { r = l; j = (uint32_t)k - 1u; }
-            if (scratch) { l = (pos_t)row.l; r = (pos_t)row.r; j = (uint32_t)p; }
-            fs = stream ? 1u : 0u; // (a lane that did not advance is mid-walk: fs was cleared by its step)
-            pend = (su && !kvalid) || (scratch && row_absent) ? (uint32_t)A_MISS
-                 : (scratch && p == k)                       ? (uint32_t)A_HIT // the row is the answer (a singleton, SBWT.hh:410-413)
-                                                             : (uint32_t)A_NONE;
-        }
     }
 
     if (COUNT) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            st_lookups += __shfl_xor_sync(FULL, st_lookups, o);
-            st_hits += __shfl_xor_sync(FULL, st_hits, o);
-            st_ranks += __shfl_xor_sync(FULL, st_ranks, o);
-            st_sectors += __shfl_xor_sync(FULL, st_sectors, o);
+        for (int s = 16; s > 0; s >>= 1) {
+            st_lookups += __shfl_xor_sync(FULL, st_lookups, s);
+            st_hits += __shfl_xor_sync(FULL, st_hits, s);
+            st_ranks += __shfl_xor_sync(FULL, st_ranks, s);
+            st_sectors += __shfl_xor_sync(FULL, st_sectors, s);
         }
         if (lane == 0) {
             atomicAdd(P.stats + 0, st_lookups);
