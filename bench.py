@@ -52,6 +52,8 @@ WORKLOADS = {
                ref=("pangenome", 400, 5_000_000, 44), k=31, streaming=True, rc=True, reads=10_000_000),
     "c5": dict(desc="configs[4] at full size: the same 2 Gbp pangenome-like reference, k=63 (+RC), streaming_search, 88 lookups per 150-bp read",
                ref=("pangenome", 400, 5_000_000, 44), k=63, streaming=True, rc=True, reads=10_000_000),
+    "c2q": dict(desc="experiment: a quarter-size configs[1] reference (25 Mbp) -- the index certainly fits in L2", ref=("contigs", 25, 1_000_000, 42),
+                k=31, streaming=True, rc=False, reads=10_000_000),
     "tiny": dict(desc="smoke-sized: 2 Mbp random DNA, k=31, streaming", ref=("contigs", 2, 1_000_000, 42), k=31, streaming=True,
                  rc=False, reads=200_000),
 }

@@ -90,6 +90,9 @@ int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index *idx);
  * Results never depend on the layout. Replaces nothing in the reference: it is the device-side
  * counterpart of choosing the SubsetMatrixRank bit-vector representation (SubsetMatrixRank.hh:19-37). */
 int sbwt_gpu_index_compact_layout(const sbwt_gpu_index *idx, double *flagged_fraction);
+/* Bytes of L2 this index asked the device to set aside for its persisting (evict_last) lines: done for a one-hot
+ * index whose csectors fit on chip (cudaLimitPersistingL2CacheSize; SBWT_B200_L2_SET_ASIDE_MB overrides, 0 = never). */
+int64_t sbwt_gpu_index_l2_set_aside(const sbwt_gpu_index *idx);
 
 /* The walk starts from a device-side table of the intervals of all tp-mers. By default tp is a
  * few characters longer than the file's precalc length (runtime only: built on the device from
@@ -106,6 +109,31 @@ int sbwt_gpu_index_get_precalc(const sbwt_gpu_index *idx, int64_t *out_lr);
 /* SubsetMatrixRank::rank(pos, c) for n host-side queries (positions in [0, n_nodes], chars
  * as bytes; any byte outside ACGT gives 0). Small-batch diagnostic / parity entry point. */
 int sbwt_gpu_rank(sbwt_gpu_index *idx, const int64_t *pos, const char *chars, int64_t n, int64_t *out);
+
+/* ---- the other read-only queries of SBWT.hh, batched ---------------------
+ * Host arrays in, host arrays out, one kernel launch per call (device scratch is kept by the index). Strings are
+ * ascii[offsets[i] .. offsets[i+1]). Each entry answers with the arithmetic of the reference function it names. */
+
+/* SBWT::update_sbwt_interval (SBWT.hh:423-437) on n (string, interval) pairs: l[i], r[i] are read and overwritten.
+ * Raw bytes (only 'A','C','G','T' are valid); an interval with l == -1 passes through; a failure gives {-1,-1}. */
+int sbwt_gpu_update_interval_batch(sbwt_gpu_index *idx, const char *ascii, const int64_t *offsets, int64_t n,
+                                   int64_t *l, int64_t *r);
+/* SBWT::partial_search (SBWT.hh:526-537): the interval of the longest prefix of each string that is found
+ * (lower case folded to upper) and its length. */
+int sbwt_gpu_partial_search_batch(sbwt_gpu_index *idx, const char *ascii, const int64_t *offsets, int64_t n,
+                                  int64_t *l, int64_t *r, int64_t *matched);
+/* SBWT::forward (SBWT.hh:369-381): the node reached from nodes[i] over the edge chars[i], or -1. Fails like the
+ * reference when the index has no streaming support. */
+int sbwt_gpu_forward_batch(sbwt_gpu_index *idx, const int64_t *nodes, const char *chars, int64_t n, int64_t *out);
+/* SubsetMatrixRank::contains (SubsetMatrixRank.hh:39-48): out[i] = 1 if column pos[i] has an edge chars[i]. */
+int sbwt_gpu_contains_batch(sbwt_gpu_index *idx, const int64_t *pos, const char *chars, int64_t n, uint8_t *out);
+/* SBWT::get_kmer (SBWT.hh:701-725): the k-character label of node colex_ranks[i] ('$'-padded on the left) at
+ * out[i * k .. (i+1) * k), not NUL-terminated. */
+int sbwt_gpu_get_kmer_batch(sbwt_gpu_index *idx, const int64_t *colex_ranks, int64_t n, char *out);
+/* SBWT::ascii_export_sets (SBWT.hh:750-773): per column its characters (the last one lower-cased) or '$', then one
+ * newline. *n_bytes receives the text length; with out == NULL or capacity too small only the length is returned
+ * (and the call fails). At most 4 * n_nodes + 1 bytes. */
+int sbwt_gpu_ascii_export_sets(sbwt_gpu_index *idx, char *out, int64_t capacity, int64_t *n_bytes);
 
 /* ---- batches ----------------------------------------------------------- */
 

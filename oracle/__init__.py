@@ -59,6 +59,17 @@ def lib():
         L.sbwt_oracle_query_batch.restype = C.c_int64
         L.sbwt_oracle_search_file.argtypes = [C.POINTER(_Index), C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.sbwt_oracle_search_file.restype = C.c_int64
+        L.sbwt_oracle_contains.argtypes = [C.POINTER(_Index), C.c_int64, C.c_char]
+        L.sbwt_oracle_forward.argtypes = [C.POINTER(_Index), C.c_int64, C.c_char]
+        L.sbwt_oracle_forward.restype = C.c_int64
+        L.sbwt_oracle_partial_search.argtypes = [C.POINTER(_Index), C.c_char_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.sbwt_oracle_partial_search.restype = C.c_int64
+        L.sbwt_oracle_update_interval.argtypes = [C.POINTER(_Index), C.c_char_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.sbwt_oracle_update_interval.restype = None
+        L.sbwt_oracle_get_kmer.argtypes = [C.POINTER(_Index), C.c_int64, C.c_char_p]
+        L.sbwt_oracle_get_kmer.restype = None
+        L.sbwt_oracle_export_sets.argtypes = [C.POINTER(_Index), C.c_void_p]
+        L.sbwt_oracle_export_sets.restype = C.c_int64
         L.sbwt_oracle_format_line.argtypes = [C.c_void_p, C.c_int64, C.c_char_p]
         L.sbwt_oracle_format_line.restype = C.c_size_t
         _lib = L
@@ -118,6 +129,37 @@ class OracleIndex:
             raise RuntimeError("Error: streaming search support not built")
         assert n == out.size, (n, out.size)
         return out
+
+    # ---- the other read-only queries (SBWT.hh:369-381, 423-437, 526-537, 701-773)
+
+    def contains(self, pos: int, c: str) -> bool:
+        return bool(lib().sbwt_oracle_contains(C.byref(self._idx), pos, c.encode()))
+
+    def forward(self, node: int, c: str) -> int:
+        r = lib().sbwt_oracle_forward(C.byref(self._idx), node, c.encode())
+        if r == -2:
+            raise RuntimeError("Error: Streaming support required for SBWT::forward")
+        return r
+
+    def partial_search(self, s: bytes) -> tuple[int, int, int]:
+        l, r = C.c_int64(0), C.c_int64(0)
+        m = lib().sbwt_oracle_partial_search(C.byref(self._idx), s, len(s), C.byref(l), C.byref(r))
+        return l.value, r.value, m
+
+    def update_interval(self, s: bytes, l: int, r: int) -> tuple[int, int]:
+        lo, hi = C.c_int64(l), C.c_int64(r)
+        lib().sbwt_oracle_update_interval(C.byref(self._idx), s, len(s), C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def get_kmer(self, colex_rank: int) -> bytes:
+        buf = C.create_string_buffer(int(self.k) + 1)
+        lib().sbwt_oracle_get_kmer(C.byref(self._idx), colex_rank, buf)
+        return buf.raw[: self.k]
+
+    def export_sets(self) -> bytes:
+        buf = np.empty(4 * self.n_nodes + 1, dtype=np.uint8)
+        n = lib().sbwt_oracle_export_sets(C.byref(self._idx), buf.ctypes.data)
+        return bytes(buf[:n])
 
     def search_file(self, query_path: str, out_path: str) -> int:
         err = C.create_string_buffer(512)

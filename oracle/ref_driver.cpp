@@ -211,6 +211,53 @@ static int cmd_ranks(int argc, char** argv) {
     return 0;
 }
 
+// The other read-only queries of SBWT.hh, for the golden fixtures of tests/golden/*/f4.txt:
+//   partial  -q reads        one line per read: "l r matched"                     (SBWT::partial_search, SBWT.hh:526-537)
+//   forward  (stdin: "node c" per line)  one result per line                        (SBWT::forward, SBWT.hh:369-381)
+//   getkmer  (stdin: colex rank per line) one k-mer label per line                  (SBWT::get_kmer, SBWT.hh:701-725)
+//   export   -o file         SBWT::ascii_export_sets (SBWT.hh:750-773)
+static int cmd_partial(int argc, char** argv) {
+    plain_matrix_t idx;
+    load_index(arg(argc, argv, "-i"), idx);
+    seq_io::Reader<> reader(arg(argc, argv, "-q"));
+    while (true) {
+        int64_t len = reader.get_next_read_to_buffer();
+        if (len == 0) break;
+        auto res = idx.partial_search(reader.read_buf, len);
+        std::cout << res.first.first << " " << res.first.second << " " << res.second << "\n";
+    }
+    return 0;
+}
+
+static int cmd_forward(int argc, char** argv) {
+    plain_matrix_t idx;
+    load_index(arg(argc, argv, "-i"), idx);
+    int64_t node;
+    char c;
+    while (std::cin >> node >> c) std::cout << idx.forward(node, c) << "\n";
+    return 0;
+}
+
+static int cmd_getkmer(int argc, char** argv) {
+    plain_matrix_t idx;
+    load_index(arg(argc, argv, "-i"), idx);
+    int64_t rank;
+    string buf(idx.get_k(), ' ');
+    while (std::cin >> rank) {
+        idx.get_kmer(rank, &buf[0]);
+        std::cout << buf << "\n";
+    }
+    return 0;
+}
+
+static int cmd_export(int argc, char** argv) {
+    plain_matrix_t idx;
+    load_index(arg(argc, argv, "-i"), idx);
+    throwing_ofstream out(arg(argc, argv, "-o"), ios::binary);
+    idx.ascii_export_sets(out.stream);
+    return 0;
+}
+
 static int cmd_dump(int argc, char** argv) {
     plain_matrix_t idx;
     load_index(arg(argc, argv, "-i"), idx);
@@ -224,7 +271,7 @@ static int cmd_dump(int argc, char** argv) {
 int main(int argc, char** argv) {
     set_log_level(LogLevel::OFF);
     if (argc < 2) {
-        std::cerr << "usage: sbwt_ref {search|timed|build-inmem|ranks|dump} ..." << std::endl;
+        std::cerr << "usage: sbwt_ref {search|timed|build-inmem|ranks|dump|partial|forward|getkmer|export} ..." << std::endl;
         return 1;
     }
     string cmd = argv[1];
@@ -234,6 +281,10 @@ int main(int argc, char** argv) {
         if (cmd == "build-inmem") return cmd_build_inmem(argc, argv);
         if (cmd == "ranks") return cmd_ranks(argc, argv);
         if (cmd == "dump") return cmd_dump(argc, argv);
+        if (cmd == "partial") return cmd_partial(argc, argv);
+        if (cmd == "forward") return cmd_forward(argc, argv);
+        if (cmd == "getkmer") return cmd_getkmer(argc, argv);
+        if (cmd == "export") return cmd_export(argc, argv);
     } catch (const std::exception& e) { // sbwt.cpp:51-57
         std::cerr << "Runtime error: " << e.what() << std::endl;
         return 1;

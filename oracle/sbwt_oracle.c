@@ -195,6 +195,80 @@ int64_t sbwt_oracle_search(const sbwt_oracle_index *idx, const char *kmer) {
     return l;
 }
 
+/* ------------------------------------------------- other read-only queries */
+
+/* SubsetMatrixRank::contains, SubsetMatrixRank.hh:39-48. */
+int sbwt_oracle_contains(const sbwt_oracle_index *idx, int64_t pos, char c) {
+    int ci = char_idx(c);
+    if (ci < 0) return 0;
+    return (int)((idx->bits[ci][pos >> 6] >> (pos & 63)) & 1);
+}
+
+/* SBWT::forward, SBWT.hh:369-381. Returns -2 when the index has no streaming
+ * support (the reference throws). */
+int64_t sbwt_oracle_forward(const sbwt_oracle_index *idx, int64_t node, char c) {
+    if (idx->sgs_len == 0) return -2;
+    while (!((idx->sgs[node >> 6] >> (node & 63)) & 1)) node--; /* the first node is always marked */
+    int64_t r1 = sbwt_oracle_rank(idx, node, c), r2 = sbwt_oracle_rank(idx, node + 1, c);
+    if (r1 == r2) return -1;
+    return idx->C[char_idx(c)] + r1;
+}
+
+/* SBWT::partial_search, SBWT.hh:526-537: the interval of the longest prefix of
+ * input that is found, and its length. */
+int64_t sbwt_oracle_partial_search(const sbwt_oracle_index *idx, const char *input, int64_t len,
+                                   int64_t *l_out, int64_t *r_out) {
+    int64_t l = 0, r = idx->n_nodes - 1;
+    for (int64_t i = 0; i < len; i++) {
+        char c = (input[i] >= 'a' && input[i] <= 'z') ? (char)(input[i] - 32) : input[i]; /* toupper */
+        int64_t nl = l, nr = r;
+        sbwt_oracle_update_interval(idx, &c, 1, &nl, &nr);
+        if (nl == -1) { *l_out = l; *r_out = r; return i; }
+        l = nl; r = nr;
+    }
+    *l_out = l; *r_out = r;
+    return len;
+}
+
+/* SBWT::get_kmer, SBWT.hh:701-725: the label of a node, '$'-padded on the
+ * left; the backward step is a binary search over rank (no select support). */
+void sbwt_oracle_get_kmer(const sbwt_oracle_index *idx, int64_t colex_rank, char *buf) {
+    static const char alphabet[4] = {'A', 'C', 'G', 'T'};
+    for (int64_t i = 0; i < idx->k; i++) {
+        if (colex_rank == 0) {
+            buf[idx->k - 1 - i] = '$';
+        } else {
+            int ci = 0;
+            while (ci + 1 < 4 && colex_rank >= idx->C[ci + 1]) ci++;
+            char c = alphabet[ci];
+            buf[idx->k - 1 - i] = c;
+            int64_t rel = colex_rank - idx->C[ci], p = 0, step = idx->n_nodes;
+            while (step > 0) {
+                while (p + step <= idx->n_nodes && sbwt_oracle_rank(idx, p + step, c) <= rel) p += step;
+                step /= 2;
+            }
+            colex_rank = p;
+        }
+    }
+}
+
+/* SBWT::ascii_export_sets, SBWT.hh:750-773: per column its characters (the last
+ * one lower-cased) or '$' for an empty set, then one newline. buf must hold
+ * 4 * n_nodes + 1 bytes; returns the bytes written. */
+int64_t sbwt_oracle_export_sets(const sbwt_oracle_index *idx, char *buf) {
+    static const char alphabet[4] = {'A', 'C', 'G', 'T'};
+    int64_t n = 0;
+    for (int64_t col = 0; col < idx->n_nodes; col++) {
+        int64_t start = n;
+        for (int ci = 0; ci < 4; ci++)
+            if ((idx->bits[ci][col >> 6] >> (col & 63)) & 1) buf[n++] = alphabet[ci];
+        if (n == start) buf[n++] = '$';
+        else buf[n - 1] = (char)(buf[n - 1] + 32); /* tolower */
+    }
+    buf[n++] = '\n';
+    return n;
+}
+
 static inline char up(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
 
 /* SBWT.hh:545-581. */

@@ -76,6 +76,14 @@ int64_t sbwt_oracle_query_batch(const sbwt_oracle_index *idx, const char *ascii,
                                 const int64_t *offsets, int64_t n_reads, int streaming,
                                 int64_t *out);
 
+/* The other read-only queries of the index. */
+int sbwt_oracle_contains(const sbwt_oracle_index *idx, int64_t pos, char c);      /* SubsetMatrixRank.hh:39-48 */
+int64_t sbwt_oracle_forward(const sbwt_oracle_index *idx, int64_t node, char c);  /* SBWT.hh:369-381; -2 = no streaming support */
+int64_t sbwt_oracle_partial_search(const sbwt_oracle_index *idx, const char *input, int64_t len,
+                                   int64_t *l_out, int64_t *r_out);               /* SBWT.hh:526-537; returns the matched length */
+void sbwt_oracle_get_kmer(const sbwt_oracle_index *idx, int64_t colex_rank, char *buf);   /* SBWT.hh:701-725; k bytes */
+int64_t sbwt_oracle_export_sets(const sbwt_oracle_index *idx, char *buf);          /* SBWT.hh:750-773; 4 n_nodes + 1 bytes */
+
 /* print_vector (sbwt_search.cpp:21-43): "<v> " per value then '\n'.
  * Returns the number of bytes written to buf (buf must hold 21*n+1 bytes). */
 size_t sbwt_oracle_format_line(const int64_t *v, int64_t n, char *buf);

@@ -34,6 +34,8 @@ EXPORTS = [
     "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
     "sbwt_gpu_index_set_table_length", "sbwt_gpu_index_table_length",
     "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text", "sbwt_gpu_widen_i32", "sbwt_gpu_expand_sparse", "sbwt_gpu_session_widen_threads", "sbwt_gpu_query_host_sharded",
+    "sbwt_gpu_update_interval_batch", "sbwt_gpu_partial_search_batch", "sbwt_gpu_forward_batch", "sbwt_gpu_contains_batch",
+    "sbwt_gpu_get_kmer_batch", "sbwt_gpu_ascii_export_sets", "sbwt_gpu_index_l2_set_aside",
 ]
 
 TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
@@ -61,7 +63,7 @@ def lib():
         L.sbwt_gpu_index_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
         L.sbwt_gpu_index_destroy.argtypes = [vp]
         L.sbwt_gpu_index_destroy.restype = None
-        for name in ("k", "n_nodes", "n_kmers", "precalc_k", "device_bytes"):
+        for name in ("k", "n_nodes", "n_kmers", "precalc_k", "device_bytes", "l2_set_aside"):
             f = getattr(L, "sbwt_gpu_index_" + name)
             f.argtypes, f.restype = [vp], i64
         for name in ("has_streaming_support", "device", "edges_only_at_group_starts"):
@@ -103,6 +105,12 @@ def lib():
         L.sbwt_gpu_text_capacity.restype = i64
         L.sbwt_gpu_format_device.argtypes = [vp, vp, i32, vp, i64, vp, i64, vp, vp]
         L.sbwt_gpu_query_host_text.argtypes = [vp, vp, vp, i64, i32, i32, TEXT_SINK, vp, C.POINTER(i64)]
+        L.sbwt_gpu_update_interval_batch.argtypes = [vp, vp, vp, i64, vp, vp]
+        L.sbwt_gpu_partial_search_batch.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+        L.sbwt_gpu_forward_batch.argtypes = [vp, vp, vp, i64, vp]
+        L.sbwt_gpu_contains_batch.argtypes = [vp, vp, vp, i64, vp]
+        L.sbwt_gpu_get_kmer_batch.argtypes = [vp, vp, i64, vp]
+        L.sbwt_gpu_ascii_export_sets.argtypes = [vp, vp, i64, C.POINTER(i64)]
         _lib = L
     return _lib
 
@@ -191,6 +199,7 @@ class Index:
     has_streaming_support = property(lambda s: bool(lib().sbwt_gpu_index_has_streaming_support(s._h)))
     device = property(lambda s: lib().sbwt_gpu_index_device(s._h))
     device_bytes = property(lambda s: lib().sbwt_gpu_index_device_bytes(s._h))
+    l2_set_aside = property(lambda s: lib().sbwt_gpu_index_l2_set_aside(s._h))
     edges_only_at_group_starts = property(lambda s: bool(lib().sbwt_gpu_index_edges_only_at_group_starts(s._h)))
 
     @property
@@ -224,6 +233,52 @@ class Index:
         out = np.empty(pos.size, dtype=np.int64)
         _check(lib().sbwt_gpu_rank(self._h, pos.ctypes.data, chars, pos.size, out.ctypes.data))
         return out
+
+
+    # ---- the other read-only queries of SBWT.hh, batched (sbwt_gpu_*_batch)
+
+    def update_interval(self, ascii_: np.ndarray, offsets: np.ndarray, l, r) -> tuple[np.ndarray, np.ndarray]:
+        """SBWT::update_sbwt_interval on n (string, interval) pairs."""
+        ascii_ = np.ascontiguousarray(ascii_, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        l, r = np.array(l, dtype=np.int64), np.array(r, dtype=np.int64)
+        _check(lib().sbwt_gpu_update_interval_batch(self._h, ascii_.ctypes.data, offsets.ctypes.data, offsets.size - 1, l.ctypes.data, r.ctypes.data))
+        return l, r
+
+    def partial_search(self, ascii_: np.ndarray, offsets: np.ndarray) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """SBWT::partial_search per string: (l, r, matched length)."""
+        ascii_ = np.ascontiguousarray(ascii_, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        l, r, m = (np.empty(n, dtype=np.int64) for _ in range(3))
+        _check(lib().sbwt_gpu_partial_search_batch(self._h, ascii_.ctypes.data, offsets.ctypes.data, n, l.ctypes.data, r.ctypes.data, m.ctypes.data))
+        return l, r, m
+
+    def forward(self, nodes, chars: bytes) -> np.ndarray:
+        nodes = np.ascontiguousarray(nodes, dtype=np.int64)
+        assert len(chars) == nodes.size
+        out = np.empty(nodes.size, dtype=np.int64)
+        _check(lib().sbwt_gpu_forward_batch(self._h, nodes.ctypes.data, chars, nodes.size, out.ctypes.data))
+        return out
+
+    def contains(self, pos, chars: bytes) -> np.ndarray:
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        assert len(chars) == pos.size
+        out = np.empty(pos.size, dtype=np.uint8)
+        _check(lib().sbwt_gpu_contains_batch(self._h, pos.ctypes.data, chars, pos.size, out.ctypes.data))
+        return out
+
+    def get_kmers(self, colex_ranks) -> list[bytes]:
+        rk = np.ascontiguousarray(colex_ranks, dtype=np.int64)
+        out = np.empty(rk.size * self.k, dtype=np.uint8)
+        _check(lib().sbwt_gpu_get_kmer_batch(self._h, rk.ctypes.data, rk.size, out.ctypes.data))
+        return [bytes(out[i * self.k:(i + 1) * self.k]) for i in range(rk.size)]
+
+    def ascii_export_sets(self) -> bytes:
+        out = np.empty(4 * self.n_nodes + 1, dtype=np.uint8)
+        n = C.c_int64(0)
+        _check(lib().sbwt_gpu_ascii_export_sets(self._h, out.ctypes.data, out.size, C.byref(n)))
+        return bytes(out[:n.value])
 
 
 class Session:

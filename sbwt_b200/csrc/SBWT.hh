@@ -6,7 +6,7 @@
 // for the one instantiation in scope, plain_matrix_sbwt_t (include/sbwt/variants.hh:19):
 //   sbwt::SBWT<sbwt::GpuSubsetMatrixRank>
 // Every query method is a thin call into the C ABI of include/sbwt_b200.h; nothing is computed
-// on the CPU. Construction from reads (KMC) and the k-mer export / select methods are out of
+// on the CPU. Construction from reads (KMC) and the select-support methods are out of
 // scope.
 //
 // Differences a caller can observe, all on the direct-API path only (the `sbwt search` command
@@ -242,53 +242,58 @@ public:
         return n_lookups;
     }
 
-    // SBWT.hh:418-437: extend the interval I by the characters of S. Two device rank queries per character.
+    // SBWT.hh:418-437: extend the interval I by the characters of S -- one kernel launch for the whole string
+    // (sbwt_gpu_update_interval_batch), not one device round trip per character.
     std::pair<int64_t, int64_t> update_sbwt_interval(const std::string& S, std::pair<int64_t, int64_t> I) const {
         return update_sbwt_interval(S.c_str(), (int64_t)S.size(), I);
     }
     std::pair<int64_t, int64_t> update_sbwt_interval(const char* S, int64_t S_length, std::pair<int64_t, int64_t> I) const {
         if (I.first == -1) return I;
-        for (int64_t i = 0; i < S_length; i++) {
-            const char c = S[i];
-            const int idx = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
-            if (idx == -1) return {-1, -1};
-            const int64_t pos[2] = {I.first, I.second + 1};
-            const char ch[2] = {c, c};
-            int64_t rk[2];
-            gpu_check(sbwt_gpu_rank(dev, pos, ch, 2, rk));
-            I.first = C[idx] + rk[0];
-            I.second = C[idx] + rk[1] - 1;
-            if (I.first > I.second) return {-1, -1};
-        }
-        return I;
+        const int64_t off[2] = {0, S_length};
+        int64_t l = I.first, r = I.second;
+        gpu_check(sbwt_gpu_update_interval_batch(dev, S, off, 1, &l, &r));
+        return {l, r};
+    }
+    // n (string, interval) pairs in one launch; strings are ascii[offsets[i], offsets[i+1])
+    void update_sbwt_interval_batch(const char* ascii, const int64_t* offsets, int64_t n, int64_t* l, int64_t* r) const {
+        gpu_check(sbwt_gpu_update_interval_batch(dev, ascii, offsets, n, l, r));
     }
 
     // SBWT.hh:369-381: follow the edge labelled c out of `node`; -1 if there is none (or c is not in ACGT).
     int64_t forward(int64_t node, char c) const {
-        if (!has_streaming_query_support()) throw std::runtime_error("Error: Streaming support required for SBWT::forward");
-        while (!((suffix_group_starts[(size_t)node >> 6] >> (node & 63)) & 1)) node--; // the first node is always marked
-        const int idx = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
-        const int64_t pos[2] = {node, node + 1};
-        const char ch[2] = {c, c};
-        int64_t rk[2];
-        gpu_check(sbwt_gpu_rank(dev, pos, ch, 2, rk));
-        if (rk[0] == rk[1]) return -1; // no edge (also every c outside ACGT: its rank is 0 everywhere)
-        return C[idx] + rk[0];
+        int64_t out = -1;
+        gpu_check(sbwt_gpu_forward_batch(dev, &node, &c, 1, &out)); // (fails like the reference without streaming support)
+        return out;
+    }
+    std::vector<int64_t> forward_batch(const std::vector<int64_t>& nodes, const std::string& chars) const {
+        std::vector<int64_t> out(nodes.size());
+        gpu_check(sbwt_gpu_forward_batch(dev, nodes.data(), chars.data(), (int64_t)nodes.size(), out.data()));
+        return out;
     }
 
     // SBWT.hh:526-542: longest prefix of input that is found; returns ({l,r}, length matched).
     std::pair<std::pair<int64_t, int64_t>, int64_t> partial_search(const std::string& input) const { return partial_search(input.c_str(), (int64_t)input.size()); }
     std::pair<std::pair<int64_t, int64_t>, int64_t> partial_search(const char* input, int64_t len) const {
-        int64_t l = 0, r = n_nodes - 1;
-        for (int64_t i = 0; i < len; i++) {
-            char c = input[i];
-            if (c >= 'a' && c <= 'z') c = (char)(c - 32); // toupper, SBWT.hh:530
-            std::pair<int64_t, int64_t> nxt = update_sbwt_interval(&c, 1, {l, r});
-            if (nxt.first == -1) return {{l, r}, i};
-            l = nxt.first;
-            r = nxt.second;
-        }
-        return {{l, r}, len};
+        const int64_t off[2] = {0, len};
+        int64_t l = 0, r = 0, m = 0;
+        gpu_check(sbwt_gpu_partial_search_batch(dev, input, off, 1, &l, &r, &m));
+        return {{l, r}, m};
+    }
+    void partial_search_batch(const char* ascii, const int64_t* offsets, int64_t n, int64_t* l, int64_t* r, int64_t* matched) const {
+        gpu_check(sbwt_gpu_partial_search_batch(dev, ascii, offsets, n, l, r, matched));
+    }
+
+    // SBWT.hh:701-725: the k-mer (label) of a node into buf (k bytes, '$'-padded on the left).
+    void get_kmer(int64_t colex_rank, char* buf) const { gpu_check(sbwt_gpu_get_kmer_batch(dev, &colex_rank, 1, buf)); }
+    void get_kmer_batch(const int64_t* colex_ranks, int64_t n, char* buf) const { gpu_check(sbwt_gpu_get_kmer_batch(dev, colex_ranks, n, buf)); }
+
+    // SBWT.hh:750-773: the subsets as text, written by the device.
+    template <typename out_stream_t>
+    void ascii_export_sets(out_stream_t& out) const {
+        std::vector<char> text((size_t)(4 * n_nodes + 1));
+        int64_t n = 0;
+        gpu_check(sbwt_gpu_ascii_export_sets(dev, text.data(), (int64_t)text.size(), &n));
+        out.write(text.data(), n);
     }
 
     // ---- serialization (SBWT.hh:463-522); the variant string is written/read by the caller ----

@@ -1,10 +1,12 @@
 // sbwt_gpu.cu -- the extern "C" layer of include/sbwt_b200.h: index creation, sessions,
 // kernel launches and the host<->device pipeline. No torch types, no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -17,6 +19,7 @@
 #include "device_index.cuh"
 #include "format_kernels.cuh"
 #include "host_widen.hpp"
+#include "query_kernels.cuh"
 #include "sbwt_file.hpp"
 #include "walk_kernel.cuh"
 
@@ -82,8 +85,13 @@ struct sbwt_gpu_index {
     int64_t table_bytes = 0;
     bool table_from_bits = true; // the file's table equals what the bit vectors imply, so any table length is admissible
     bool compact_in_search = false; // the per-k-mer search path also walks the compact layout (default: classic sectors)
+    int64_t l2_set_aside = 0;       // bytes of L2 set aside for persisting (evict_last) lines by this index, 0 = none
     uint32_t probe_stride = 0;      // streaming walk: distance between the probes of a range of presumed misses (0 = none)
     void* d_sgs = nullptr;
+    // grow-only device scratch of the small-batch entry points (rank, forward, partial_search ...): no cudaMalloc per call
+    std::mutex scratch_mutex;
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
 
 struct Scratch {
@@ -394,6 +402,22 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
         }
     }
     if (int rc = sbwt_gpu_index_set_table_length(ix, tp)) { sbwt_gpu_index_destroy(ix); return rc; }
+    // L2 set-aside for a one-hot index that fits on chip: its csectors are read with an evict_last (= persisting) policy, and
+    // a set-aside of the structure's size keeps the result / read / table streams from displacing them. Measured on c2
+    // (profiles/r02h_l2_set_aside.txt: csector64, 50 MB: 8.62 ms without, 7.94 ms with 52 MB; larger set-asides starve the
+    // streams: 60 MB 8.35 ms, and 72 MB 2.2x slower in r02d). Device-wide limit, so only raised, and only for indexes it pays for.
+    if (ix->d_compact) {
+        const int64_t cbytes = ix->view.n_cblocks * (int64_t)sizeof(Sector);
+        int max_persist = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        const char* e = getenv("SBWT_B200_L2_SET_ASIDE_MB"); // 0 = never
+        int64_t want = e ? (int64_t)atoi(e) << 20 : (cbytes <= ((int64_t)56 << 20) ? cbytes + ((int64_t)2 << 20) : 0);
+        want = std::min<int64_t>(want, max_persist);
+        size_t have = 0;
+        cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+        if (want > (int64_t)have && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want) == cudaSuccess) ix->l2_set_aside = want;
+        cudaGetLastError();
+    }
     if (ix->table_from_bits) { // (see launch_walk)
         int log4n = 0;
         while (log4n < 32 && (1ll << (2 * log4n)) < ix->n_nodes) log4n++;
@@ -466,7 +490,7 @@ extern "C" void sbwt_gpu_index_destroy(sbwt_gpu_index* ix) {
     if (!ix) return;
     DeviceGuard guard(ix->device);
     cudaFree(ix->d_sectors); cudaFree(ix->d_sbbase); cudaFree(ix->d_precalc); cudaFree(ix->d_sgs); cudaFree(ix->d_table);
-    cudaFree(ix->d_compact); cudaFree(ix->d_cbase);
+    cudaFree(ix->d_compact); cudaFree(ix->d_cbase); cudaFree(ix->d_scratch);
     delete ix;
 }
 
@@ -482,6 +506,7 @@ extern "C" int sbwt_gpu_index_compact_layout(const sbwt_gpu_index* ix, double* f
     if (flagged_fraction) *flagged_fraction = ix->flagged_fraction;
     return ix->d_compact ? 1 : 0;
 }
+extern "C" int64_t sbwt_gpu_index_l2_set_aside(const sbwt_gpu_index* ix) { return ix ? ix->l2_set_aside : 0; }
 extern "C" int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index* ix) { return ix->view.edges_at_starts; }
 
 extern "C" int sbwt_gpu_index_get_precalc(const sbwt_gpu_index* ix, int64_t* out_lr) {
@@ -492,15 +517,34 @@ extern "C" int sbwt_gpu_index_get_precalc(const sbwt_gpu_index* ix, int64_t* out
     return 0;
 }
 
+// scratch of at least `bytes` (256-byte aligned pieces are carved out of it by the caller); call with scratch_mutex held
+static int index_scratch(sbwt_gpu_index* ix, size_t bytes, char** out) {
+    if (bytes > ix->scratch_bytes) {
+        cudaFree(ix->d_scratch);
+        ix->d_scratch = nullptr;
+        ix->scratch_bytes = 0;
+        const size_t want = std::max<size_t>(bytes + bytes / 2, (size_t)1 << 20);
+        CU(cudaMalloc(&ix->d_scratch, want));
+        ix->scratch_bytes = want;
+    }
+    *out = (char*)ix->d_scratch;
+    return 0;
+}
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
 extern "C" int sbwt_gpu_rank(sbwt_gpu_index* ix, const int64_t* pos, const char* chars, int64_t n, int64_t* out) {
     if (!ix) return set_error("null index");
     if (n <= 0) return 0;
+    if (!pos || !chars || !out) return set_error("null buffer");
     for (int64_t i = 0; i < n; i++)
         if (pos[i] < 0 || pos[i] > ix->n_nodes) return set_error("rank position %lld out of range [0, %lld]", (long long)pos[i], (long long)ix->n_nodes);
     DeviceGuard guard(ix->device);
-    int64_t *d_pos = nullptr, *d_out = nullptr;
-    char* d_ch = nullptr;
-    CU(cudaMalloc(&d_pos, n * 8)); CU(cudaMalloc(&d_out, n * 8)); CU(cudaMalloc(&d_ch, n));
+    std::lock_guard<std::mutex> lock(ix->scratch_mutex);
+    char* d = nullptr;
+    if (index_scratch(ix, 2 * al256((size_t)n * 8) + al256((size_t)n), &d)) return 1;
+    int64_t* d_pos = (int64_t*)d;
+    int64_t* d_out = (int64_t*)(d + al256((size_t)n * 8));
+    char* d_ch = d + 2 * al256((size_t)n * 8);
     CU(cudaMemcpy(d_pos, pos, n * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_ch, chars, n, cudaMemcpyHostToDevice));
     if (ix->view.wide) rank_kernel<true><<<grid_for(n, 256), 256>>>(ix->view, d_pos, d_ch, n, ix->C[0], ix->C[1], ix->C[2], ix->C[3], d_out);
@@ -508,11 +552,148 @@ extern "C" int sbwt_gpu_rank(sbwt_gpu_index* ix, const int64_t* pos, const char*
     LAUNCHED();
     CU(cudaGetLastError());
     CU(cudaMemcpy(out, d_out, n * 8, cudaMemcpyDeviceToHost));
-    cudaFree(d_pos); cudaFree(d_out); cudaFree(d_ch);
+    return 0;
+}
+
+// ------------------------------------------------------------------ the other read-only queries, batched (query_kernels.cuh)
+
+static int extend_batch(sbwt_gpu_index* ix, const char* ascii, const int64_t* off, int64_t n, int mode, int64_t* l, int64_t* r, int64_t* matched) {
+    if (!ix) return set_error("null index");
+    if (n < 0) return set_error("negative batch size");
+    if (n == 0) return 0;
+    if (!off || !l || !r || (mode == kExtendPartial && !matched)) return set_error("null buffer");
+    const int64_t bytes = off[n] - off[0];
+    if (bytes < 0 || (bytes > 0 && !ascii)) return set_error("invalid string offsets");
+    for (int64_t i = 0; i < n; i++)
+        if (off[i + 1] < off[i]) return set_error("string offsets must be non-decreasing");
+    if (mode == kExtendUpdate)
+        for (int64_t i = 0; i < n; i++)
+            if (l[i] != -1 && (l[i] < 0 || r[i] < l[i] - 1 || r[i] >= ix->n_nodes))
+                return set_error("interval %lld: [%lld, %lld] is not inside [0, %lld)", (long long)i, (long long)l[i], (long long)r[i], (long long)ix->n_nodes);
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->scratch_mutex);
+    char* d = nullptr;
+    const size_t s_off = al256((size_t)(n + 1) * 8), s_v = al256((size_t)n * 8), s_a = al256((size_t)bytes + 1);
+    if (index_scratch(ix, s_off + 3 * s_v + s_a, &d)) return 1;
+    int64_t* d_off = (int64_t*)d;
+    int64_t *d_l = (int64_t*)(d + s_off), *d_r = (int64_t*)(d + s_off + s_v), *d_m = (int64_t*)(d + s_off + 2 * s_v);
+    uint8_t* d_a = (uint8_t*)(d + s_off + 3 * s_v);
+    CU(cudaMemcpy(d_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice));
+    if (bytes) CU(cudaMemcpy(d_a, ascii + off[0], (size_t)bytes, cudaMemcpyHostToDevice));
+    if (mode == kExtendUpdate) {
+        CU(cudaMemcpy(d_l, l, (size_t)n * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_r, r, (size_t)n * 8, cudaMemcpyHostToDevice));
+    }
+    if (ix->view.wide) extend_kernel<true><<<grid_for(n, 256), 256>>>(ix->view, d_a, d_off, n, mode, d_l, d_r, d_m);
+    else extend_kernel<false><<<grid_for(n, 256), 256>>>(ix->view, d_a, d_off, n, mode, d_l, d_r, d_m);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(l, d_l, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(r, d_r, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (matched) CU(cudaMemcpy(matched, d_m, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int sbwt_gpu_update_interval_batch(sbwt_gpu_index* ix, const char* ascii, const int64_t* offsets, int64_t n, int64_t* l, int64_t* r) {
+    return extend_batch(ix, ascii, offsets, n, kExtendUpdate, l, r, nullptr);
+}
+extern "C" int sbwt_gpu_partial_search_batch(sbwt_gpu_index* ix, const char* ascii, const int64_t* offsets, int64_t n, int64_t* l, int64_t* r,
+                                             int64_t* matched) {
+    return extend_batch(ix, ascii, offsets, n, kExtendPartial, l, r, matched);
+}
+
+// positions + characters in, one value each out
+template <typename OutT, typename Launch>
+static int pos_char_batch(sbwt_gpu_index* ix, const int64_t* pos, const char* chars, int64_t n, int64_t max_pos, OutT* out, Launch launch) {
+    if (!ix) return set_error("null index");
+    if (n < 0) return set_error("negative batch size");
+    if (n == 0) return 0;
+    if (!pos || !chars || !out) return set_error("null buffer");
+    for (int64_t i = 0; i < n; i++)
+        if (pos[i] < 0 || pos[i] > max_pos) return set_error("position %lld out of range [0, %lld]", (long long)pos[i], (long long)max_pos);
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->scratch_mutex);
+    char* d = nullptr;
+    if (index_scratch(ix, 2 * al256((size_t)n * 8) + al256((size_t)n), &d)) return 1;
+    int64_t* d_pos = (int64_t*)d;
+    OutT* d_out = (OutT*)(d + al256((size_t)n * 8));
+    char* d_ch = d + 2 * al256((size_t)n * 8);
+    CU(cudaMemcpy(d_pos, pos, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_ch, chars, (size_t)n, cudaMemcpyHostToDevice));
+    launch(d_pos, d_ch, d_out);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d_out, (size_t)n * sizeof(OutT), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int sbwt_gpu_forward_batch(sbwt_gpu_index* ix, const int64_t* nodes, const char* chars, int64_t n, int64_t* out) {
+    if (ix && !ix->has_sgs) return set_error("Error: Streaming support required for SBWT::forward"); // SBWT.hh:370-371
+    return pos_char_batch<int64_t>(ix, nodes, chars, n, ix ? ix->n_nodes - 1 : 0, out, [&](const int64_t* d_pos, const char* d_ch, int64_t* d_out) {
+        if (ix->view.wide) forward_kernel<true><<<grid_for(n, 256), 256>>>(ix->view, d_pos, d_ch, n, d_out);
+        else forward_kernel<false><<<grid_for(n, 256), 256>>>(ix->view, d_pos, d_ch, n, d_out);
+    });
+}
+
+extern "C" int sbwt_gpu_contains_batch(sbwt_gpu_index* ix, const int64_t* pos, const char* chars, int64_t n, uint8_t* out) {
+    return pos_char_batch<uint8_t>(ix, pos, chars, n, ix ? ix->n_nodes - 1 : 0, out, [&](const int64_t* d_pos, const char* d_ch, uint8_t* d_out) {
+        if (ix->view.wide) contains_kernel<true><<<grid_for(n, 256), 256>>>(ix->view, d_pos, d_ch, n, d_out);
+        else contains_kernel<false><<<grid_for(n, 256), 256>>>(ix->view, d_pos, d_ch, n, d_out);
+    });
+}
+
+extern "C" int sbwt_gpu_get_kmer_batch(sbwt_gpu_index* ix, const int64_t* colex_ranks, int64_t n, char* out) {
+    if (!ix) return set_error("null index");
+    if (n < 0) return set_error("negative batch size");
+    if (n == 0) return 0;
+    if (!colex_ranks || !out) return set_error("null buffer");
+    for (int64_t i = 0; i < n; i++)
+        if (colex_ranks[i] < 0 || colex_ranks[i] >= ix->n_nodes) return set_error("colex rank %lld out of range [0, %lld)", (long long)colex_ranks[i], (long long)ix->n_nodes);
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->scratch_mutex);
+    char* d = nullptr;
+    if (index_scratch(ix, al256((size_t)n * 8) + al256((size_t)n * (size_t)ix->k), &d)) return 1;
+    int64_t* d_rk = (int64_t*)d;
+    char* d_out = d + al256((size_t)n * 8);
+    CU(cudaMemcpy(d_rk, colex_ranks, (size_t)n * 8, cudaMemcpyHostToDevice));
+    if (ix->view.wide) get_kmer_kernel<true><<<grid_for(n, 256), 256>>>(ix->view, d_rk, n, ix->C[0], ix->C[1], ix->C[2], ix->C[3], d_out);
+    else get_kmer_kernel<false><<<grid_for(n, 256), 256>>>(ix->view, d_rk, n, ix->C[0], ix->C[1], ix->C[2], ix->C[3], d_out);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d_out, (size_t)n * (size_t)ix->k, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int sbwt_gpu_ascii_export_sets(sbwt_gpu_index* ix, char* out, int64_t capacity, int64_t* n_bytes) {
+    if (!ix || !n_bytes) return set_error("null argument");
+    *n_bytes = 0;
+    DeviceGuard guard(ix->device);
+    std::lock_guard<std::mutex> lock(ix->scratch_mutex);
+    const int64_t n_words = (ix->n_nodes + 31) / 32;
+    char* d = nullptr;
+    const size_t s_len = al256((size_t)(n_words + 1) * 8), s_part = al256((size_t)scan_partials_needed(n_words) * 8);
+    if (index_scratch(ix, s_len + s_part + 256, &d)) return 1;
+    int64_t *d_len = (int64_t*)d, *d_part = (int64_t*)(d + s_len), *d_total = (int64_t*)(d + s_len + s_part);
+    export_len_kernel<<<grid_for(n_words, 256), 256>>>(ix->view, n_words, d_len); LAUNCHED();
+    if (exclusive_scan_inplace(d_len, n_words, d_part, d_total, 0)) return 1;
+    int64_t total = 0;
+    CU(cudaMemcpy(&total, d_total, 8, cudaMemcpyDeviceToHost));
+    *n_bytes = total + 1; // the text ends with one newline (SBWT.hh:772)
+    if (!out || capacity < total + 1) return set_error("ascii_export_sets needs a buffer of %lld bytes", (long long)(total + 1));
+    char* d_text = nullptr;
+    CU(cudaMalloc(&d_text, (size_t)total + 1));
+    export_emit_kernel<<<grid_for(n_words, 256), 256>>>(ix->view, n_words, d_len, d_text); LAUNCHED();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_text, (size_t)total, cudaMemcpyDeviceToHost);
+    cudaFree(d_text);
+    CU(e);
+    out[total] = '\n';
     return 0;
 }
 
 // ------------------------------------------------------------------ sessions
+
+static void session_count(int delta); // sessions alive in this process (see widen_thread_count)
 
 static void scratch_free(Scratch& sc) {
     cudaFree(sc.codes); cudaFree(sc.invalid); cudaFree(sc.n_out); cudaFree(sc.n_win); cudaFree(sc.partials);
@@ -548,6 +729,7 @@ extern "C" int sbwt_gpu_session_create(sbwt_gpu_index* ix, int64_t max_bases, in
     sbwt_gpu_session* s = new sbwt_gpu_session();
     s->idx = ix; s->max_bases = max_bases; s->max_reads = max_reads;
     if (const char* w = getenv("SBWT_B200_WINDOW")) s->window = std::max(1, atoi(w));
+    session_count(+1);
     if (scratch_alloc(s->sc, max_bases, max_reads, s->window)) { sbwt_gpu_session_destroy(s); return 1; }
     *out = s;
     return 0;
@@ -577,6 +759,7 @@ extern "C" int sbwt_gpu_session_last_timing(sbwt_gpu_session* s, double* prep_ms
 
 extern "C" void sbwt_gpu_session_destroy(sbwt_gpu_session* s) {
     if (!s) return;
+    session_count(-1);
     DeviceGuard guard(s->idx->device);
     scratch_free(s->sc);
     if (s->ev_start) { cudaEventDestroy(s->ev_start); cudaEventDestroy(s->ev_walk0); cudaEventDestroy(s->ev_walk1); }
@@ -613,13 +796,20 @@ static int launch_pack(const char* d_ascii, int64_t n_bases, int case_mode, uint
 
 template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL, int LAY>
 static cudaError_t launch_walk_ttt(const WalkParams& P, int sm_count, cudaStream_t st) {
-    static int occ = 0; // resident blocks per SM of this instantiation
-    if (occ == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, LAY>, kWalkThreads, 0);
+    constexpr size_t smem = sizeof(WalkShared<STREAMING, WIDE, OUT32, LITERAL>); // queues + stage: dynamic (more than 48 KB)
+    static int occ[64] = {0}; // resident blocks per SM of this instantiation, per device (the attribute below is per device too)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (occ[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(walk_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (occ < 1) occ = 1;
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, walk_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, LAY>, kWalkThreads, smem);
+        if (e != cudaSuccess) return e;
+        occ[dev] = o < 1 ? 1 : o;
     }
-    walk_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, LAY><<<(unsigned)(sm_count * occ), kWalkThreads, 0, st>>>(P);
+    walk_kernel<STREAMING, WIDE, COUNT, OUT32, KW, LITERAL, LAY><<<(unsigned)(sm_count * occ[dev]), kWalkThreads, smem, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -813,14 +1003,18 @@ static void CUDART_CB widen_callback(void* p) { // stream callback: no CUDA call
 }
 
 // How many host threads sign-extend int32 results into the caller's int64 array (0 = none: int64 values cross
-// PCIe). Default: the host's hardware threads divided by the visible GPUs (one process per GPU shares the host),
-// at most 8; fewer than 4 cannot keep up with a PCIe 5 x16 link, so the plain int64 copy is used instead.
+// PCIe). Default: the host's hardware threads divided by the GPUs THIS JOB drives -- LOCAL_WORLD_SIZE when a launcher
+// set it (one process per GPU), else the sessions alive in this process (one per device in sbwt_gpu_query_host_sharded)
+// -- at most 8; fewer than 4 cannot keep up with a PCIe 5 x16 link, so the plain int64 copy is used instead.
+// (Round 1 divided by the VISIBLE devices: a single-GPU job on an 8-GPU host got 4 threads and lost 20 %.)
+static std::atomic<int> g_live_sessions{0};
+static void session_count(int delta) { g_live_sessions.fetch_add(delta); }
 static int widen_thread_count() {
     if (const char* e = getenv("SBWT_B200_WIDEN_THREADS")) return std::max(0, std::min(64, atoi(e)));
-    int ndev = 1;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+    int share = std::max(1, g_live_sessions.load());
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = std::max(share, atoi(e));
     const int hw = (int)std::thread::hardware_concurrency();
-    const int t = std::min(8, hw / ndev); // 8 threads saturate the host's memory system (profiles/r01g_e2e_sweep.txt)
+    const int t = std::min(8, hw / share); // 8 threads saturate the host's memory system (profiles/r01g_e2e_sweep.txt)
     return t >= 4 ? t : 0;
 }
 
@@ -835,15 +1029,55 @@ static int64_t d2h_piece_values() {
     return (int64_t)64 << 20;
 }
 
+// After a failed host-buffer call nothing that was queued may still write into the caller's buffers: wait for every
+// slot's copies and stream callbacks (which hand work to the pool), then for the pool, and forget the half-done chunks.
+static void drain_slots(sbwt_gpu_session* s) {
+    const std::string keep = g_last_error;
+    for (HostSlot& h : s->slots) {
+        if (h.stream) cudaStreamSynchronize(h.stream);
+        h.back_pending = false; // (the hits of a sparse chunk are not fetched: its results are abandoned)
+        if (s->widen_pool) s->widen_pool->wait(&h.widen_ticket);
+        h.widen_pool = nullptr;
+        h.busy = false;
+        h.out_staged = false;
+        h.out_bytes = 0;
+    }
+    cudaGetLastError();
+    g_last_error = keep;
+}
+
+// every read must fit a device-side batch: checked before anything is queued
+static int validate_reads(const sbwt_gpu_session* s, const int64_t* off, int64_t n_reads) {
+    for (int64_t i = 0; i < n_reads; i++) {
+        const int64_t len = off[i + 1] - off[i];
+        if (len < 0) return set_error("read offsets must be non-decreasing");
+        if (len > s->max_bases) return set_error("read %lld (%lld bases) is longer than the session capacity (%lld bases)", (long long)i, (long long)len, (long long)s->max_bases);
+    }
+    return 0;
+}
+
+static int query_host_body(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                           int case_mode, void* out, bool out32);
+
 static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
                            int case_mode, void* out, bool out32) {
     if (!s) return set_error("null session");
     if (n_reads < 0) return set_error("negative batch size");
     if (n_reads == 0) return 0;
     if (!ascii || !off || !out) return set_error("null buffer");
+    if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
+    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
+    if (mode == SBWT_GPU_MODE_STREAMING && !s->idx->has_sgs) return set_error("Error: streaming search support not built");
+    if (validate_reads(s, off, n_reads)) return 1;
+    DeviceGuard guard(s->idx->device);
+    const int rc = query_host_body(s, ascii, off, n_reads, mode, case_mode, out, out32);
+    if (rc) drain_slots(s); // a CUDA or internal error in the middle of the pipeline
+    return rc;
+}
+
+static int query_host_body(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                           int case_mode, void* out, bool out32) {
     sbwt_gpu_index* ix = s->idx;
-    if (mode == SBWT_GPU_MODE_STREAMING && !ix->has_sgs) return set_error("Error: streaming search support not built");
-    DeviceGuard guard(ix->device);
     if (host_slots_init(s)) return 1;
     const bool pin_in = is_pinned(ascii), pin_off = is_pinned(off), pin_out = is_pinned(out);
     const int64_t k = ix->k;
@@ -865,8 +1099,6 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
         int64_t r1 = r0, bases = 0;
         while (r1 < n_reads && r1 - r0 < s->max_reads) {
             const int64_t len = off[r1 + 1] - off[r1];
-            if (len < 0) return set_error("read offsets must be non-decreasing");
-            if (len > s->max_bases) return set_error("read %lld (%lld bases) is longer than the session capacity (%lld bases)", (long long)r1, (long long)len, (long long)s->max_bases);
             if (bases + len > s->max_bases) break;
             bases += len;
             r1++;
@@ -1148,6 +1380,9 @@ static int slot_deliver_text(sbwt_gpu_session* s, HostSlot& h, sbwt_gpu_text_sin
     return 0;
 }
 
+static int query_host_text_body(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                                int case_mode, sbwt_gpu_text_sink sink, void* user, int64_t* n_lookups);
+
 extern "C" int sbwt_gpu_query_host_text(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
                                         int case_mode, sbwt_gpu_text_sink sink, void* user, int64_t* n_lookups) {
     if (!s) return set_error("null session");
@@ -1155,9 +1390,19 @@ extern "C" int sbwt_gpu_query_host_text(sbwt_gpu_session* s, const char* ascii, 
     if (n_reads < 0) return set_error("negative batch size");
     if (n_reads == 0) return 0;
     if (!ascii || !off || !sink) return set_error("null argument");
+    if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
+    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
+    if (mode == SBWT_GPU_MODE_STREAMING && !s->idx->has_sgs) return set_error("Error: streaming search support not built");
+    if (validate_reads(s, off, n_reads)) return 1;
+    DeviceGuard guard(s->idx->device);
+    const int rc = query_host_text_body(s, ascii, off, n_reads, mode, case_mode, sink, user, n_lookups);
+    if (rc) drain_slots(s); // also after a sink error: queued kernels still read the caller's (pinned) input buffers
+    return rc;
+}
+
+static int query_host_text_body(sbwt_gpu_session* s, const char* ascii, const int64_t* off, int64_t n_reads, int mode,
+                                int case_mode, sbwt_gpu_text_sink sink, void* user, int64_t* n_lookups) {
     sbwt_gpu_index* ix = s->idx;
-    if (mode == SBWT_GPU_MODE_STREAMING && !ix->has_sgs) return set_error("Error: streaming search support not built");
-    DeviceGuard guard(ix->device);
     if (host_slots_init(s)) return 1;
     for (int b = 0; b < 2; b++)
         if (!s->h_text[b]) {
@@ -1178,8 +1423,6 @@ extern "C" int sbwt_gpu_query_host_text(sbwt_gpu_session* s, const char* ascii, 
         int64_t r1 = r0, bases = 0;
         while (r1 < n_reads && r1 - r0 < s->max_reads) {
             const int64_t len = off[r1 + 1] - off[r1];
-            if (len < 0) return set_error("read offsets must be non-decreasing");
-            if (len > s->max_bases) return set_error("read %lld (%lld bases) is longer than the session capacity (%lld bases)", (long long)r1, (long long)len, (long long)s->max_bases);
             if (bases + len > s->max_bases) break;
             bases += len;
             r1++;

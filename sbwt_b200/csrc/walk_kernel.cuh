@@ -96,14 +96,24 @@ struct TableRow<true> {
 
 constexpr int kWalkThreads = 256;
 constexpr int kWalkWarps = kWalkThreads / 32;
+// resident blocks per SM the kernels are compiled for: 4 (64 registers) on the classic sectors, whose walks are bound by
+// DRAM line fetches and want warps; 3 (80 registers, no spills) for the streaming walk on the one-hot layouts
+// (profiles/r02f: c2 9.13 -> 8.72 ms on csector64, 11.0 -> 8.40 ms on csector96; c4s 17.7 vs 19.9 ms the other way)
 #ifndef SBWT_B200_WALK_MINBLOCKS
 #define SBWT_B200_WALK_MINBLOCKS 4
 #endif
+#ifndef SBWT_B200_WALK_MINBLOCKS_COMPACT
+#define SBWT_B200_WALK_MINBLOCKS_COMPACT 3
+#endif
+template <bool STREAMING, bool WIDE, int LAY>
+struct WalkBlocks {
+    static constexpr int value = WIDE ? 3 : ((STREAMING && LAY != LAY_CLASSIC) ? SBWT_B200_WALK_MINBLOCKS_COMPACT : SBWT_B200_WALK_MINBLOCKS);
+};
 #ifndef SBWT_B200_SINGLE_HOLD
 #define SBWT_B200_SINGLE_HOLD 2
 #endif
 #ifndef SBWT_B200_CHAINS
-#define SBWT_B200_CHAINS 2
+#define SBWT_B200_CHAINS 1
 #endif
 constexpr uint32_t kSingleHold = SBWT_B200_SINGLE_HOLD; // extra NARROW steps on a singleton interval before it is queued (drops most chance survivors)
 
@@ -175,12 +185,18 @@ __device__ __forceinline__ bool kmer_invalid(const uint32_t* __restrict__ inv, u
 
 template <bool OUT32>
 __device__ __forceinline__ void store_result(const WalkParams& P, uint32_t o, int64_t v) {
+#ifdef SBWT_B200_DEBUG_NOSTORE // measurement builds only (tools/build_variants.sh): what the result stream costs
+    if (v != -12345) return;
+#endif
     if (OUT32) asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(P.out32 + o), "r"((int32_t)v) : "memory");
     else asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(P.out + o), "l"(v) : "memory");
 }
 
 // One whole 32-byte sector of results (4 x int64 or 8 x int32) in one store (STG.E.256).
 __device__ __forceinline__ void st_sector_cs(void* p, const uint32_t (&w)[8]) {
+#ifdef SBWT_B200_DEBUG_NOSTORE
+    if (w[0] != 0xFFFFFFF7u) return;
+#endif
     asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                  : "memory");
@@ -200,6 +216,56 @@ struct OutStage {
     val_t v[R][32];
 };
 struct NoStage {};
+
+// Stage of the streaming CHAIN: the results of one round (kRound steps), one row per chain, 32 rows per chain slot of
+// the lanes. Rows are padded to an odd number of 64-bit units, so that both the per-step writes (32 lanes, one column)
+// and the flush (a few rows, consecutive columns) spread over the banks.
+template <bool WIDE, int NCH>
+struct ChainStage {
+    typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
+#ifndef SBWT_B200_ROUND
+#define SBWT_B200_ROUND 16
+#endif
+    static constexpr uint32_t kRound = WIDE ? 8u : (uint32_t)SBWT_B200_ROUND; // results per chain and round: one 128-byte line of int64 (narrow) / 64 bytes
+    static constexpr uint32_t kStride = kRound + (WIDE ? 1u : 2u);
+    pos_t v[NCH][32][kStride];
+    uint32_t obase[NCH][32]; // index of the result that slot 0 of the row stands for
+    uint32_t mask[NCH][32];  // slots of the row that hold a result of this round
+
+    // all 32 rows of chain slot i -> global memory; lanes take consecutive results of a row, so a row leaves in one piece
+    template <bool OUT32>
+    static __device__ __forceinline__ void flush(ChainStage& S, int i, int lane, int64_t* out, int32_t* out32) {
+        if (WIDE) { // 8 int64 per row: 8 lanes per row, 4 rows per pass
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int row = 4 * j + (lane >> 3), e = lane & 7;
+                if ((S.mask[i][row] >> e) & 1u)
+                    asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(out + (S.obase[i][row] + (uint32_t)e)), "l"((int64_t)S.v[i][row][e]) : "memory");
+            }
+        } else { // kRound u32 per row, two per lane: kRound / 2 lanes per row
+            constexpr int LPR = (int)kRound / 2, RPP = 32 / LPR; // lanes per row, rows per pass
+#pragma unroll
+            for (int j = 0; j < LPR; j++) {
+                const int row = RPP * j + lane / LPR, e = (lane % LPR) * 2;
+                const uint32_t m2 = (S.mask[i][row] >> e) & 3u;
+                if (m2) {
+                    const uint32_t a = (uint32_t)S.v[i][row][e], b = (uint32_t)S.v[i][row][e + 1];
+                    const uint32_t x = S.obase[i][row] + (uint32_t)e;
+                    if (OUT32) {
+                        if (m2 == 3u) asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(out32 + x), "r"(a), "r"(b) : "memory");
+                        else if (m2 == 1u) asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(out32 + x), "r"(a) : "memory");
+                        else asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(out32 + x + 1), "r"(b) : "memory");
+                    } else { // int64 results of a narrow index: a column (< 2^32) or -1
+                        const uint32_t ah = a == 0xFFFFFFFFu ? 0xFFFFFFFFu : 0u, bh = b == 0xFFFFFFFFu ? 0xFFFFFFFFu : 0u;
+                        if (m2 == 3u) asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(out + x), "r"(a), "r"(ah), "r"(b), "r"(bh) : "memory");
+                        else if (m2 == 1u) asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(out + x), "r"(a), "r"(ah) : "memory");
+                        else asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(out + x + 1), "r"(b), "r"(bh) : "memory");
+                    }
+                }
+            }
+        }
+    }
+};
 
 // ------------------------------------------------------------------ interval steps on the three layouts
 //
@@ -333,6 +399,16 @@ struct Stepper {
     }
 };
 
+// the block's shared memory: per warp its queues and the stage its streaming chain collects results in
+template <bool STREAMING, bool WIDE, bool OUT32, bool LITERAL>
+struct WalkShared {
+    static constexpr int NCH = ChainCount<STREAMING, WIDE, LITERAL>::value;
+    typedef typename std::conditional<LITERAL, OutStage<OUT32>,
+                                      typename std::conditional<STREAMING, ChainStage<WIDE, NCH>, NoStage>::type>::type StageT;
+    WalkQueues<WIDE, NCH> queues[kWalkWarps];
+    StageT stage[kWalkWarps];
+};
+
 // LITERAL (streaming mode on an index that violates "only suffix-group starts carry edges", i.e. a
 // hand-made file): streaming answers may then differ from search() answers, so the reference's
 // control flow is followed to the letter -- after a miss the k-mers are searched one at a time and
@@ -340,16 +416,17 @@ struct Stepper {
 // LAY: the layout rank steps are answered from (device_index.cuh); the compact ones serve narrow, non-LITERAL kernels,
 // and a block flagged there (some column with no edge or several) is answered from the classic sectors.
 template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL, int LAY>
-__global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLOCKS) walk_kernel(const WalkParams P) {
+__global__ void __launch_bounds__(kWalkThreads, WalkBlocks<STREAMING, WIDE, LAY>::value) walk_kernel(const WalkParams P) {
     static_assert(STREAMING || !LITERAL, "LITERAL is a streaming-mode variant");
     static_assert(LAY == LAY_CLASSIC || (!WIDE && !LITERAL), "the compact layouts serve narrow indexes that keep the edge invariant");
     typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
     constexpr int NCH = ChainCount<STREAMING, WIDE, LITERAL>::value;
     typedef WalkQueues<WIDE, NCH> QT;
-    __shared__ QT queues[kWalkWarps];
-    QT& Q = queues[threadIdx.x >> 5];
-    typedef typename std::conditional<LITERAL, OutStage<OUT32>, NoStage>::type StageT;
-    __shared__ StageT stages[LITERAL ? kWalkWarps : 1];
+    typedef WalkShared<STREAMING, WIDE, OUT32, LITERAL> SH;
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    SH& shm = *reinterpret_cast<SH*>(walk_smem);
+    QT& Q = shm.queues[threadIdx.x >> 5];
+    void* const stage_mem = &shm.stage[threadIdx.x >> 5];
     constexpr uint32_t OR = OUT32 ? 8u : 4u; // results per 32-byte output sector
     // phase of result 0 inside its sector
     const uint32_t oph = OUT32 ? (uint32_t)(((uintptr_t)P.out32 >> 2) & 7u) : (uint32_t)(((uintptr_t)P.out >> 3) & 3u);
@@ -412,17 +489,26 @@ __global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLO
             // ================================================================ CHAIN, streaming (SBWT.hh:561-575)
             // Every lane owns up to NCH survivors. A chain first finishes its own k-mer (`quiet` steps without a result,
             // then the step that completes it), then every further step answers the next k-mer of its work item.
+            // Results are produced in ROUNDS of kRound steps: a chain's result number x goes to slot (x + phase) mod kRound
+            // of its row of the warp's stage in shared memory, and after the round the warp writes all rows out together,
+            // every row as one contiguous piece of its read's results -- for int64 results a whole 128-byte line per chain
+            // (the round-1 kernel wrote 32-byte sectors one at a time: four partial-line writes per line, each chain
+            // holding a half-written line in L2; the result stream cost 40 % of the kernel, profiles/r02e).
+            typedef ChainStage<WIDE, NCH> CS;
+            constexpr uint32_t R = CS::kRound;
+            CS& STG = *reinterpret_cast<CS*>(stage_mem);
+            const uint32_t ophR = OUT32 ? (uint32_t)(((uintptr_t)P.out32 >> 2) & (R - 1u)) : (uint32_t)(((uintptr_t)P.out >> 3) & (R - 1u));
             const uint32_t m = min(32u * NCH, nS), q0 = nS - m;
             nS = q0;
             bool act[NCH];
             pos_t col[NCH];
-            uint32_t pos[NCH], cw[NCH], nx[NCH], o[NCH], oend[NCH], quiet[NCH], pre[NCH];
+            uint32_t pos[NCH], cw[NCH], nx[NCH], o[NCH], oend[NCH], quiet[NCH];
             bool fs[NCH]; // the chain is past its first k-mer: its steps are streaming steps
 #pragma unroll
             for (int i = 0; i < NCH; i++) {
                 const uint32_t qi = (uint32_t)i * 32u + (uint32_t)lane;
                 act[i] = qi < m;
-                col[i] = 0; pos[i] = 0; cw[i] = 0; nx[i] = 0; o[i] = 0; oend[i] = 0; quiet[i] = 0; pre[i] = 0; fs[i] = false;
+                col[i] = 0; pos[i] = 0; cw[i] = 0; nx[i] = 0; o[i] = 0; oend[i] = 0; quiet[i] = 0; fs[i] = false;
                 if (act[i]) {
                     const uint32_t b = Q.s_base[q0 + qi], meta = Q.s_meta[q0 + qi];
                     o[i] = Q.s_out[q0 + qi];
@@ -441,19 +527,13 @@ __global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLO
                     } else {
                         quiet[i] = k - j - 1u;
                     }
-                    // results written one by one until the chain's next result starts an output sector; the chain's own
-                    // first k-mer (when still open) is the first of them
-                    const uint32_t first_emit = o[i]; // index of the next result this chain produces
-                    const uint32_t a = (0u - (first_emit + oph)) & (OR - 1u);
-                    pre[i] = quiet[i] + a;
                 }
             }
             __syncwarp();
 
-            // one step of chain i on character c: its answer from the layout (L already issued) or from the slow path
+            // the answer of one step from the classic sectors; a clear bit on a streaming step takes the literal walk-back
+            // (SBWT.hh:562-563): the step starts from the suffix-group start of col (which alone carries the group's edges)
             auto resolve = [&](pos_t colv, int c, bool streaming_step, pos_t& ncol, bool& hit) {
-                // classic sectors; a clear bit on a streaming step takes the literal walk-back (SBWT.hh:562-563): the step
-                // starts from the suffix-group start of col (which alone carries the group's edges)
                 int64_t cblk;
                 ST.classic_step(colv, c, ncol, hit, cblk);
                 if (!hit && streaming_step) {
@@ -495,12 +575,11 @@ __global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLO
             };
 
             while (true) {
-                // ---- general loop: own k-mers, the results in front of the next whole output sector, and everything
-                // unusual (misses, walk-backs, flagged csectors, chain ends). Chain i steps while pre[i] > 0.
+                // ---- own k-mers: steps without a result. A miss here is the item's first k-mer being absent.
                 while (true) {
                     bool run[NCH], any = false;
 #pragma unroll
-                    for (int i = 0; i < NCH; i++) { run[i] = act[i] && pre[i] > 0; any |= run[i]; }
+                    for (int i = 0; i < NCH; i++) { run[i] = act[i] && quiet[i] > 0; any |= run[i]; }
                     if (!__any_sync(FULL, any)) break;
                     typename Stepper<WIDE, LAY>::Load L[NCH];
                     int c[NCH];
@@ -517,22 +596,13 @@ __global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLO
                         if (run[i]) {
                             pos_t ncol = 0;
                             bool hit = false;
-                            const bool streaming_step = fs[i];
-                            if (!ST.eval(L[i], col[i], c[i], ncol, hit) || (!hit && streaming_step)) resolve(col[i], c[i], streaming_step, ncol, hit);
+                            if (!ST.eval(L[i], col[i], c[i], ncol, hit)) resolve(col[i], c[i], false, ncol, hit);
                             if (COUNT) { st_ranks += 2; st_sectors += 1; }
-                            pre[i]--;
                             if (hit) {
                                 col[i] = ncol;
                                 advance(i);
-                                if (quiet[i] > 0) quiet[i]--;
-                                else {
-                                    store_result<OUT32>(P, o[i], (int64_t)col[i]);
-                                    if (COUNT) { st_lookups++; st_hits++; }
-                                    o[i]++;
-                                    fs[i] = true;
-                                    if (o[i] == oend[i]) act[i] = false;
-                                }
-                            } else { // the k-mer this step belongs to is absent: [col, col] -> empty (SBWT.hh:433) / l != r (SBWT.hh:574)
+                                quiet[i]--;
+                            } else { // [col, col] -> empty interval (SBWT.hh:433)
                                 kstart[i] = pos[i] - (k - 1u - quiet[i]);
                                 store_result<OUT32>(P, o[i], -1);
                                 if (COUNT) st_lookups++;
@@ -549,106 +619,102 @@ __global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLO
                     }
                 }
 
-                // ---- how many whole output sectors every running chain still has in front of it
-                uint32_t myr = 0xFFFFFFFFu;
-                bool anyact = false;
+                // ---- one round: chain i produces the results of slots [lo, lo + width) of its row
+                uint32_t lo[NCH], width[NCH];
+                uint32_t s_first = R, s_last = 0;
 #pragma unroll
                 for (int i = 0; i < NCH; i++) {
+                    lo[i] = 0; width[i] = 0;
                     if (act[i]) {
-                        const uint32_t left = oend[i] - o[i];
-                        if (left < OR) pre[i] = left; // fewer than a sector: finished in the general loop
-                        myr = min(myr, left / OR);
-                        anyact = true;
+                        lo[i] = (o[i] + ophR) & (R - 1u);
+                        width[i] = min(R - lo[i], oend[i] - o[i]);
+                        s_first = min(s_first, lo[i]);
+                        s_last = max(s_last, lo[i] + width[i]);
                     }
                 }
-                if (!__any_sync(FULL, anyact)) break;
-                const uint32_t rounds = __reduce_min_sync(FULL, myr);
-                if (rounds == 0) continue;
-
-                // ---- steady state: every running chain's next result opens an output sector (a chain whose own k-mer is
-                // still open has quiet == 0 here: its next step completes it) and none of them ends within `rounds` sectors.
-                // One step and one result per chain and iteration, the results of a sector collect in registers and leave as
-                // one 32-byte store per chain. The first iteration in which any chain's step is not a plain hit is left
-                // uncommitted to the general loop.
-                pos_t slot[NCH][OR];
+                s_first = __reduce_min_sync(FULL, s_first);
+                s_last = __reduce_max_sync(FULL, s_last);
+                if (s_last == 0) break; // no chain left
+                uint32_t endm = 0; // bit i: chain i ended in a miss during this round
+                for (uint32_t sl = s_first; sl < s_last; sl++) {
+                    bool run[NCH];
+                    typename Stepper<WIDE, LAY>::Load L[NCH];
+                    int c[NCH];
 #pragma unroll
-                for (int i = 0; i < NCH; i++)
+                    for (int i = 0; i < NCH; i++) {
+                        run[i] = (sl - lo[i]) < width[i]; // (unsigned: also false below lo; width is 0 for a chain that is not running)
+                        c[i] = (int)((cw[i] >> ((pos[i] & 15u) * 2u)) & 3u);
+                        if (run[i]) ST.issue(L[i], col[i], c[i]);
+                    }
+                    pos_t ncol[NCH];
+                    bool ok[NCH], okall = true;
 #pragma unroll
-                    for (uint32_t t = 0; t < OR; t++) slot[i][t] = 0;
-                uint32_t broke_at = OR; // OR: the run ended on a sector boundary
-                uint32_t done = 0;      // sectors written per chain
-                for (uint32_t rd = 0; rd < rounds; rd++) {
-#pragma unroll
-                    for (uint32_t sl = 0; sl < OR; sl++) {
-                        typename Stepper<WIDE, LAY>::Load L[NCH];
-                        int c[NCH];
-#pragma unroll
-                        for (int i = 0; i < NCH; i++) {
-                            c[i] = (int)((cw[i] >> ((pos[i] & 15u) * 2u)) & 3u);
-                            if (act[i]) ST.issue(L[i], col[i], c[i]);
+                    for (int i = 0; i < NCH; i++) {
+                        ncol[i] = 0; ok[i] = true;
+                        if (run[i]) {
+                            bool hit = false;
+                            const bool fast = ST.eval(L[i], col[i], c[i], ncol[i], hit);
+                            ok[i] = fast && hit;
+                            okall &= ok[i];
                         }
-                        pos_t ncol[NCH];
-                        bool okall = true;
+                    }
+                    if (__all_sync(FULL, okall)) { // the usual case: every running chain found its next k-mer
 #pragma unroll
                         for (int i = 0; i < NCH; i++) {
-                            ncol[i] = 0;
-                            if (act[i]) {
-                                bool hit = false;
-                                const bool fast = ST.eval(L[i], col[i], c[i], ncol[i], hit);
-                                okall &= fast && hit;
-                            }
-                        }
-                        if (!__all_sync(FULL, okall)) { broke_at = sl; break; }
-#pragma unroll
-                        for (int i = 0; i < NCH; i++) {
-                            if (act[i]) {
-                                slot[i][sl] = ncol[i];
+                            if (run[i]) {
+                                STG.v[i][lane][sl] = ncol[i];
                                 col[i] = ncol[i];
                                 advance(i);
                             }
                         }
-                    }
-                    if (broke_at != OR) break;
+                    } else {
+                        uint32_t wantm = 0;
+                        uint32_t kstart[NCH];
 #pragma unroll
-                    for (int i = 0; i < NCH; i++) {
-                        if (act[i]) {
-                            uint32_t wv[8];
-                            if (OUT32) {
-#pragma unroll
-                                for (int t = 0; t < 8; t++) wv[t] = (uint32_t)slot[i][t & (OR - 1u)];
-                                st_sector_cs(P.out32 + o[i], wv);
-                            } else {
-#pragma unroll
-                                for (int t = 0; t < 4; t++) {
-                                    const unsigned long long q = (unsigned long long)(int64_t)slot[i][t & (OR - 1u)];
-                                    wv[2 * t] = (uint32_t)q;
-                                    wv[2 * t + 1] = WIDE ? (uint32_t)(q >> 32) : 0u; // (narrow: every value here is a column < 2^32)
+                        for (int i = 0; i < NCH; i++) {
+                            kstart[i] = 0;
+                            if (run[i]) {
+                                bool hit = ok[i];
+                                // (a chain's first result may be its own k-mer's: that step is not a streaming step)
+                                if (!hit) resolve(col[i], c[i], fs[i] || sl > lo[i], ncol[i], hit);
+                                if (hit) {
+                                    STG.v[i][lane][sl] = ncol[i];
+                                    col[i] = ncol[i];
+                                    advance(i);
+                                } else { // the k-mer is absent: [col, col] -> empty (SBWT.hh:433) / l != r (SBWT.hh:574); the chain ends
+                                    STG.v[i][lane][sl] = (pos_t)-1;
+                                    kstart[i] = pos[i] - (k - 1u);
+                                    width[i] = sl + 1u - lo[i];
+                                    endm |= 1u << i;
+                                    if (o[i] + width[i] < oend[i]) wantm |= 1u << i;
+                                    if (COUNT) st_hits--; // (counted below with the round)
                                 }
-                                st_sector_cs(P.out + o[i], wv);
                             }
-                            o[i] += OR;
+                        }
+                        if (__any_sync(FULL, wantm != 0)) {
+#pragma unroll
+                            for (int i = 0; i < NCH; i++) push_rest((wantm >> i) & 1u, kstart[i], o[i] + width[i], oend[i]);
+                            __syncwarp();
                         }
                     }
-                    done++;
                 }
-                // ---- bookkeeping of the run: staged results of a broken sector go out one by one, and every chain is
-                // brought back to a sector boundary by the general loop (the chain that broke the run takes its unusual
-                // step there)
-                const uint32_t nb = broke_at != OR ? broke_at : 0u;
+                // ---- the round's results leave the stage: every row as one contiguous piece
+#pragma unroll
+                for (int i = 0; i < NCH; i++) {
+                    STG.obase[i][lane] = o[i] - lo[i];
+                    STG.mask[i][lane] = width[i] ? (((width[i] >= 32u ? 0u : (1u << width[i])) - 1u) << lo[i]) : 0u;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < NCH; i++) CS::template flush<OUT32>(STG, i, lane, P.out, P.out32);
+                __syncwarp();
 #pragma unroll
                 for (int i = 0; i < NCH; i++) {
                     if (act[i]) {
-                        if (COUNT) { const uint32_t n = done * OR + nb; st_ranks += 2ull * n; st_sectors += n; st_lookups += n; st_hits += n; }
-                        if (done + nb > 0) fs[i] = true;
-#pragma unroll
-                        for (uint32_t t = 0; t < OR; t++)
-                            if (t < nb) store_result<OUT32>(P, o[i] + t, (int64_t)slot[i][t]);
-                        o[i] += nb;
-                        if (o[i] == oend[i]) act[i] = false;
-                        else if (broke_at != OR) {
-                            const uint32_t a2 = (0u - (o[i] + oph)) & (OR - 1u);
-                            pre[i] = a2 ? a2 : OR;
-                        }
+                        if (COUNT) { st_ranks += 2ull * width[i]; st_sectors += width[i]; st_lookups += width[i]; st_hits += width[i]; }
+                        if (width[i]) fs[i] = true;
+                        o[i] += width[i];
+                        if (((endm >> i) & 1u) || o[i] == oend[i]) act[i] = false;
                     }
                 }
             }
@@ -690,7 +756,7 @@ __global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLO
                     return;
                 }
                 if constexpr (LITERAL) {
-                    OutStage<OUT32>& OS = stages[threadIdx.x >> 5];
+                    OutStage<OUT32>& OS = *reinterpret_cast<OutStage<OUT32>*>(stage_mem);
                     const uint32_t sl = (x + oph) & (OR - 1u);
                     OS.v[sl][lane] = (typename OutStage<OUT32>::val_t)v;
                     if (sl == OR - 1u) {
@@ -718,7 +784,7 @@ __global__ void __launch_bounds__(kWalkThreads, WIDE ? 3 : SBWT_B200_WALK_MINBLO
             };
             auto drain = [&](uint32_t end) { // the lane's run is over: write what is still staged, [gs, end)
                 if constexpr (LITERAL) {
-                    OutStage<OUT32>& OS = stages[threadIdx.x >> 5];
+                    OutStage<OUT32>& OS = *reinterpret_cast<OutStage<OUT32>*>(stage_mem);
                     for (uint32_t y = gs; y < end; y++) store_result<OUT32>(P, y, (int64_t)OS.v[(y + oph) & (OR - 1u)][lane]);
                 }
                 gs = end;

@@ -204,9 +204,48 @@ def case_c1(man, tmp):
     man["c1"] = entry
 
 
+def case_f4(man, name, queries, seed):
+    """The other read-only queries (SBWT.hh:369-381, 526-537, 701-773) answered by the reference's own methods through
+    `sbwt_ref partial / forward / getkmer / export`; written to <name>/f4.json."""
+    d = os.path.join(HERE, name)
+    idx = os.path.join(d, "index.sbwt")
+    n_nodes = oracle.OracleIndex(idx).n_nodes
+    rng = np.random.default_rng(seed)
+    part = [[int(x) for x in line.split()] for line in oracle.ref_run("partial", "-i", idx, "-q", os.path.join(d, queries)).stdout.decode().splitlines()]
+    nodes = np.concatenate([rng.integers(0, n_nodes, size=300), [0, 1, n_nodes - 1]]).astype(np.int64)
+    chars = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=nodes.size))
+    fwd = [int(x) for x in oracle.ref_run("forward", "-i", idx, stdin="".join(f"{n} {chr(c)}\n" for n, c in zip(nodes, chars)).encode()).stdout.split()]
+    ranks = np.concatenate([rng.integers(0, n_nodes, size=120), [0, 1, n_nodes - 1]]).astype(np.int64)
+    kmers = oracle.ref_run("getkmer", "-i", idx, stdin="".join(f"{r}\n" for r in ranks).encode()).stdout.decode().split()
+    tmp = tempfile.mkdtemp(prefix="golden_f4_")
+    try:
+        exp = os.path.join(tmp, "export.txt")
+        oracle.ref_run("export", "-i", idx, "-o", exp)
+        export = open(exp, "rb").read()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    out = {"queries": queries, "partial_search": part, "forward": {"nodes": nodes.tolist(), "chars": chars.decode(), "out": fwd},
+           "get_kmer": {"ranks": ranks.tolist(), "kmers": kmers}, "export_md5": hashlib.md5(export).hexdigest(), "export_len": len(export)}
+    if len(export) < 4000:
+        out["export_text"] = export.decode()
+    with open(os.path.join(d, "f4.json"), "w") as f:
+        json.dump(out, f)
+    man.setdefault(name, {})["f4"] = {"partial": len(part), "forward": len(fwd), "get_kmer": len(kmers), "export_md5": out["export_md5"]}
+
+
+F4_CASES = [("cli_k6", "queries.fna", 21), ("small_k31", "reads.fna", 22), ("small_k63_rc", "reads.fna", 23), ("small_k8_p0", "reads.fna", 24)]
+
+
 def main():
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     oracle.build(with_ref=True)
+    if "--only-f4" in sys.argv:  # add the f4.json fixtures to an existing set
+        man = json.load(open(os.path.join(HERE, "MANIFEST.json")))
+        for name, q, seed in F4_CASES:
+            case_f4(man, name, q, seed)
+        with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
+            json.dump(man, f, indent=1, sort_keys=True)
+        return
     man = {"generator": "tests/golden/make_golden.py", "expected_outputs_from": "oracle/_ref/sbwt_ref (reference classes)"}
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
@@ -215,6 +254,8 @@ def main():
         case_small(man, tmp, "small_k63_rc", synth.pangenome(6000, 4, 0.05, seed=9), k=63, p=8, add_rc=True, n_reads=400, seed=10)
         case_small(man, tmp, "small_k8_p0", synth.random_contigs(2, 3000, seed=11), k=8, p=0, add_rc=True, n_reads=300, seed=12)
         case_c1(man, tmp)
+        for name, q, seed in F4_CASES:
+            case_f4(man, name, q, seed)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:

@@ -575,3 +575,59 @@ def test_sharded_query_over_several_sessions():
     ses2 = S.Session(other, 1000, 10)
     with pytest.raises(S.SbwtGpuError, match="replicas of one index"):
         S.query_host_sharded([ses, ses2], a, off, S.MODE_STREAMING)
+
+
+@pytest.mark.parametrize("name", ["cli_k6", "small_k31", "small_k63_rc", "small_k8_p0"])
+def test_other_read_only_queries(name, monkeypatch):
+    """The batched device forms of partial_search, update_sbwt_interval, forward, contains, get_kmer and
+    ascii_export_sets (SBWT.hh:369-381, 423-437, 526-537, 701-773; SubsetMatrixRank.hh:39-48) against the reference's
+    own answers (f4.json) and, on random inputs, the C oracle; narrow and forced-wide layouts."""
+    f4 = json.load(open(golden(name, "f4.json")))
+    orc = oracle.OracleIndex(golden(name, "index.sbwt"))
+    reads = read_fasta_reads(golden(name, f4["queries"]))
+    for wide in (False, True):
+        if wide:
+            monkeypatch.setenv("SBWT_B200_FORCE_WIDE", "2")
+        idx = S.Index(golden(name, "index.sbwt"))
+        a, off = synth.ragged_to_batch(reads)
+        l, r, m = idx.partial_search(a, off)
+        assert np.stack([l, r, m], axis=1).tolist() == f4["partial_search"]
+        fw = f4["forward"]
+        np.testing.assert_array_equal(idx.forward(fw["nodes"], fw["chars"].encode()), fw["out"])
+        gk = f4["get_kmer"]
+        assert [x.decode() for x in idx.get_kmers(gk["ranks"])] == gk["kmers"]
+        text = idx.ascii_export_sets()
+        assert text == orc.export_sets() and len(text) == f4["export_len"]
+        # random inputs against the oracle
+        rng = np.random.default_rng(5)
+        n = orc.n_nodes
+        pos = rng.integers(0, n, size=2000)
+        chars = bytes(rng.choice(np.frombuffer(b"ACGTNa", np.uint8), size=pos.size))
+        np.testing.assert_array_equal(idx.contains(pos, chars), [orc.contains(int(p), chr(c)) for p, c in zip(pos, chars)])
+        np.testing.assert_array_equal(idx.forward(pos, chars), [orc.forward(int(p), chr(c)) for p, c in zip(pos, chars)])
+        # update_sbwt_interval: from the full interval, from intervals reached by a prefix, and {-1,-1} passing through
+        strs = [bytes(x) for x in reads[:200]] + [b"", b"ACGN", b"acgt"]
+        a2, off2 = synth.ragged_to_batch(strs)
+        l0 = np.zeros(len(strs), dtype=np.int64)
+        r0 = np.full(len(strs), n - 1, dtype=np.int64)
+        l0[5], r0[5] = -1, -1
+        gl, gr = idx.update_interval(a2, off2, l0, r0)
+        want = [orc.update_interval(s_, int(a_), int(b_)) for s_, a_, b_ in zip(strs, l0, r0)]
+        assert list(zip(gl.tolist(), gr.tolist())) == want
+        half = [s_[: len(s_) // 2] for s_ in strs]
+        rest = [s_[len(s_) // 2:] for s_ in strs]
+        a3, off3 = synth.ragged_to_batch(half)
+        hl, hr = idx.update_interval(a3, off3, l0, r0)
+        a4, off4 = synth.ragged_to_batch(rest)
+        fl, fr = idx.update_interval(a4, off4, hl, hr)
+        assert list(zip(fl.tolist(), fr.tolist())) == want
+        with pytest.raises(S.SbwtGpuError, match="out of range"):
+            idx.get_kmers([n])
+        idx.close()
+
+
+def test_forward_needs_streaming_support():
+    idx = S.Index(golden("cli_k6", "index_nostream.sbwt"))
+    with pytest.raises(S.SbwtGpuError, match="Streaming support required"):
+        idx.forward([1], b"A")
+    idx.close()

@@ -129,3 +129,36 @@ def test_against_live_reference_binary(tmp_path):
     got = oracle.ref_run("ranks", "-i", ix, stdin=inp).stdout.split()
     want = [idx.rank(int(p), c) for p in pos for c in "ACGT"]
     assert [int(x) for x in got] == want
+
+
+F4 = ["cli_k6", "small_k31", "small_k63_rc", "small_k8_p0"]
+
+
+@pytest.mark.parametrize("name", F4)
+def test_other_queries_against_the_reference(name):
+    """partial_search / forward / get_kmer / ascii_export_sets (SBWT.hh:369-381, 526-537, 701-773): the C restatement
+    against the answers of the reference's own methods (tests/golden/<name>/f4.json, written by `sbwt_ref`)."""
+    f4 = json.load(open(golden(name, "f4.json")))
+    idx = oracle.OracleIndex(golden(name, "index.sbwt"))
+    reads = read_fasta_reads(golden(name, f4["queries"]))
+    # (SeqIO upper-cases what `sbwt_ref partial` sees; partial_search upper-cases again, so the raw reads agree)
+    assert [list(idx.partial_search(r)) for r in reads] == f4["partial_search"]
+    fw = f4["forward"]
+    assert [idx.forward(n, c) for n, c in zip(fw["nodes"], fw["chars"])] == fw["out"]
+    gk = f4["get_kmer"]
+    assert [idx.get_kmer(r).decode() for r in gk["ranks"]] == gk["kmers"]
+    text = idx.export_sets()
+    assert len(text) == f4["export_len"] and hashlib.md5(text).hexdigest() == f4["export_md5"]
+    if "export_text" in f4:
+        assert text.decode() == f4["export_text"]
+    # contains() is the bit the export prints; update_interval composes to search()
+    n = idx.n_nodes
+    cols = text[:-1].decode()
+    pos, at = 0, 0
+    while at < len(cols) and pos < min(n, 500):
+        j = at
+        while cols[j].isupper():
+            j += 1
+        members = cols[at:j + 1].upper().replace("$", "")
+        assert [idx.contains(pos, c) for c in "ACGT"] == [c in members for c in "ACGT"]
+        pos, at = pos + 1, j + 1
