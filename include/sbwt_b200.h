@@ -156,6 +156,16 @@ int64_t sbwt_gpu_count_outputs(const int64_t *read_offsets, int64_t n_reads, int
 int sbwt_gpu_query_host(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,
                         int64_t n_reads, int mode, int case_mode, int64_t *out);
 
+/* Hits-only results, for callers that do not need a dense array: hit_mask receives one bit per result, numbered over
+ * the whole batch (bit i of word i / 32 = result i is found; (count_outputs + 31) / 32 words), and `hits` (may be
+ * NULL: membership only) the found values in result order, *n_hits of them (at most count_outputs; int32, so only for
+ * an index with fewer than 2^31 columns -- larger indexes get the bitmap alone). A miss is always -1
+ * (SBWT.hh:390-415, :545-581), so sbwt_gpu_query_host's array follows from the two. One bit per k-mer and four bytes
+ * per found k-mer cross PCIe, and with a pinned `hits` buffer no host thread touches the results: this is the call
+ * that scales with the number of GPUs on one host. */
+int sbwt_gpu_query_host_hits(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets, int64_t n_reads,
+                             int mode, int case_mode, uint32_t *hit_mask, int32_t *hits, int64_t *n_hits);
+
 /* Same, with int32 results: half the device-to-host bytes (the PCIe copy of the results is what bounds
  * an end-to-end batch). Only for an index with fewer than 2^31 columns (every value, and -1, fits);
  * fails otherwise. Values are the same numbers sbwt_gpu_query_host returns. */

@@ -49,6 +49,7 @@ def lib():
         L.sbwt_oracle_load.argtypes = [C.c_char_p, C.POINTER(_Index), C.c_char_p, C.c_size_t]
         L.sbwt_oracle_load.restype = C.c_int
         L.sbwt_oracle_free.argtypes = [C.POINTER(_Index)]
+        L.sbwt_oracle_from_arrays.argtypes = [C.POINTER(_Index), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
         L.sbwt_oracle_rank.argtypes = [C.POINTER(_Index), C.c_int64, C.c_char]
         L.sbwt_oracle_rank.restype = C.c_int64
         L.sbwt_oracle_rank_naive.argtypes = [C.POINTER(_Index), C.c_int64, C.c_char]
@@ -79,8 +80,19 @@ def lib():
 class OracleIndex:
     """A loaded plain-matrix index answering queries on the CPU, reference semantics."""
 
-    def __init__(self, path: str):
+    def __init__(self, path: str | None = None, *, arrays: dict | None = None):
         self._idx = _Index()
+        if arrays is not None:  # {"bits": [A, C, G, T] (uint64 words), "sgs": words | None, "n_nodes", "n_kmers", "k", "precalc_k"}
+            bits = [np.ascontiguousarray(b, dtype=np.uint64) for b in arrays["bits"]]
+            ptrs = (C.c_void_p * 4)(*[b.ctypes.data for b in bits])
+            sgs = arrays.get("sgs")
+            sgs = None if sgs is None else np.ascontiguousarray(sgs, dtype=np.uint64)
+            rc = lib().sbwt_oracle_from_arrays(C.byref(self._idx), ptrs, None if sgs is None else sgs.ctypes.data, arrays["n_nodes"],
+                                               arrays.get("n_kmers", 0), arrays["k"], arrays.get("precalc_k", 0))
+            if rc != 0:
+                raise MemoryError("sbwt_oracle_from_arrays")
+            self.path = None
+            return
         err = C.create_string_buffer(512)
         if lib().sbwt_oracle_load(path.encode(), C.byref(self._idx), err, 512) != 0:
             raise RuntimeError(err.value.decode())

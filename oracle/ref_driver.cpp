@@ -141,6 +141,7 @@ static int cmd_timed(int argc, char** argv) {
     int64_t k = idx.get_k();
     bool streaming = idx.has_streaming_query_support();
     vector<int64_t> counts(T, 0), hits(T, 0), sums(T, 0);
+    vector<uint64_t> wsums(T, 0); // sum of (1-based position inside the thread's slice) x value, modulo 2^64
     double best = 1e300;
     for (int rep = 0; rep < reps; rep++) {
         auto t0 = std::chrono::steady_clock::now();
@@ -149,28 +150,32 @@ static int cmd_timed(int argc, char** argv) {
             th.emplace_back([&, t]() {
                 size_t a = reads.size() * t / T, b = reads.size() * (t + 1) / T;
                 int64_t n = 0, h = 0, s = 0;
+                uint64_t ws = 0;
                 for (size_t i = a; i < b; i++) {
                     const string& R = reads[i];
                     if (streaming) {
                         vector<int64_t> v = idx.streaming_search(R.c_str(), R.size());
-                        for (int64_t x : v) { n++; h += x >= 0; s += x; }
+                        for (int64_t x : v) { n++; h += x >= 0; s += x; ws += (uint64_t)n * (uint64_t)x; }
                     } else {
                         for (int64_t j = 0; j < (int64_t)R.size() - k + 1; j++) {
                             int64_t x = idx.search(R.c_str() + j);
-                            n++; h += x >= 0; s += x;
+                            n++; h += x >= 0; s += x; ws += (uint64_t)n * (uint64_t)x;
                         }
                     }
                 }
-                counts[t] = n; hits[t] = h; sums[t] = s;
+                counts[t] = n; hits[t] = h; sums[t] = s; wsums[t] = ws;
             });
         }
         for (auto& x : th) x.join();
         double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         best = std::min(best, sec);
     }
+    // position-weighted checksum of the whole output: sum over results of (1-based index) x value, modulo 2^64 -- a
+    // permutation or a shift of the results changes it (the plain sum would not)
     int64_t n = 0, h = 0, s = 0;
-    for (int t = 0; t < T; t++) { n += counts[t]; h += hits[t]; s += sums[t]; }
-    std::cout << "{\"lookups\": " << n << ", \"hits\": " << h << ", \"checksum\": " << s << ", \"seconds\": " << best
+    uint64_t ws = 0;
+    for (int t = 0; t < T; t++) { ws += wsums[t] + (uint64_t)n * (uint64_t)sums[t]; n += counts[t]; h += hits[t]; s += sums[t]; }
+    std::cout << "{\"lookups\": " << n << ", \"hits\": " << h << ", \"checksum\": " << s << ", \"weighted_checksum\": " << ws << ", \"seconds\": " << best
               << ", \"threads\": " << T << ", \"reads\": " << reads.size() << ", \"streaming\": " << (streaming ? "true" : "false")
               << "}" << std::endl;
     return 0;

@@ -195,6 +195,71 @@ int64_t sbwt_oracle_search(const sbwt_oracle_index *idx, const char *kmer) {
     return l;
 }
 
+/* ------------------------------------------------------ index from arrays */
+
+/* rank_support_v5's constructor (rank_support_v5.hpp:65-109): per 2048-bit superblock one word with the ones
+ * before it and one word with the ones of its first 6, 12, 18, 24, 30 words at shifts 48, 36, 24, 12, 0. */
+static uint64_t *build_v5(const uint64_t *data, uint64_t nbits, uint64_t *nwords_out) {
+    const uint64_t W = (nbits + 63) / 64, nsb = (W * 64 >> 11) + 1;
+    uint64_t *bb = (uint64_t *)calloc(nsb * 2, 8);
+    if (!bb) return NULL;
+    uint64_t total = 0;
+    for (uint64_t sb = 0; sb < nsb; sb++) {
+        bb[2 * sb] = total;
+        uint64_t second = 0, sum = 0;
+        for (uint64_t j = 0; j < 32; j++) {
+            const uint64_t wi = 32 * sb + j;
+            if (j && j % 6 == 0 && wi <= W) second |= sum << (60 - 12 * (j / 6));
+            if (wi < W) sum += (uint64_t)popc64(data[wi]);
+        }
+        bb[2 * sb + 1] = second;
+        total += sum;
+    }
+    *nwords_out = nsb * 2;
+    return bb;
+}
+
+/* SBWT(A, C, G, T, streaming_support, k, n_kmers, precalc_k) (SBWT.hh:336-353): copies the four n_nodes-bit vectors
+ * (and suffix_group_starts, may be NULL), builds the rank directories, the C array (:345-349) and the p-mer table
+ * (do_kmer_prefix_precalc, :617-645). For indexes that exist only in memory (tests of very large layouts). */
+int sbwt_oracle_from_arrays(sbwt_oracle_index *idx, const uint64_t *const bits[4], const uint64_t *sgs, int64_t n_nodes,
+                            int64_t n_kmers, int64_t k, int64_t precalc_k) {
+    memset(idx, 0, sizeof *idx);
+    const uint64_t W = ((uint64_t)n_nodes + 63) / 64;
+    idx->n_nodes = n_nodes; idx->n_kmers = n_kmers; idx->k = k; idx->precalc_k = precalc_k;
+    for (int c = 0; c < 4; c++) {
+        idx->bits_len[c] = (uint64_t)n_nodes;
+        idx->bits[c] = (uint64_t *)calloc(W + 1, 8); /* one zero padding word: rank(n_nodes) may read it */
+        if (!idx->bits[c]) { sbwt_oracle_free(idx); return -1; }
+        memcpy(idx->bits[c], bits[c], W * 8);
+        idx->rs[c] = build_v5(idx->bits[c], (uint64_t)n_nodes, &idx->rs_words[c]);
+        if (!idx->rs[c]) { sbwt_oracle_free(idx); return -1; }
+    }
+    if (sgs) {
+        idx->sgs_len = (uint64_t)n_nodes;
+        idx->sgs = (uint64_t *)calloc(W + 1, 8);
+        if (!idx->sgs) { sbwt_oracle_free(idx); return -1; }
+        memcpy(idx->sgs, sgs, W * 8);
+    }
+    idx->C[0] = 1; /* one ghost dollar into the root */
+    for (int c = 0; c < 3; c++) idx->C[c + 1] = idx->C[c] + rank_v5(idx->bits[c], idx->rs[c], (uint64_t)n_nodes);
+    if (precalc_k > 0) {
+        static const char alphabet[4] = {'A', 'C', 'G', 'T'};
+        idx->n_precalc = (int64_t)1 << (2 * precalc_k);
+        idx->precalc = (int64_t *)malloc((size_t)idx->n_precalc * 16);
+        if (!idx->precalc) { sbwt_oracle_free(idx); return -1; }
+        char kmer[32];
+        for (int64_t i = 0; i < idx->n_precalc; i++) {
+            for (int64_t j = 0; j < precalc_k; j++) kmer[j] = alphabet[(i >> (2 * j)) & 3]; /* first character = lowest digit */
+            int64_t l = 0, r = n_nodes - 1;
+            sbwt_oracle_update_interval(idx, kmer, precalc_k, &l, &r);
+            idx->precalc[2 * i] = l;
+            idx->precalc[2 * i + 1] = r;
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------- other read-only queries */
 
 /* SubsetMatrixRank::contains, SubsetMatrixRank.hh:39-48. */

@@ -44,6 +44,10 @@ typedef struct sbwt_oracle_index {
 /* Load a serialized plain-matrix .sbwt file (variant string included).
  * Returns 0 on success; on failure returns nonzero and writes a message. */
 int sbwt_oracle_load(const char *path, sbwt_oracle_index *idx, char *err, size_t errlen);
+/* An index from four bit vectors in memory (SBWT.hh:336-353): rank directories (rank_support_v5.hpp:65-109), C array
+ * and p-mer table are built here. sgs may be NULL. Returns 0 on success. */
+int sbwt_oracle_from_arrays(sbwt_oracle_index *idx, const uint64_t *const bits[4], const uint64_t *sgs, int64_t n_nodes,
+                            int64_t n_kmers, int64_t k, int64_t precalc_k);
 void sbwt_oracle_free(sbwt_oracle_index *idx);
 
 /* rank_c(pos) through the rank_support_v5 arithmetic and the directory that

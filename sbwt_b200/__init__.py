@@ -35,7 +35,7 @@ EXPORTS = [
     "sbwt_gpu_index_set_table_length", "sbwt_gpu_index_table_length",
     "sbwt_gpu_text_capacity", "sbwt_gpu_format_device", "sbwt_gpu_query_host_text", "sbwt_gpu_widen_i32", "sbwt_gpu_expand_sparse", "sbwt_gpu_session_widen_threads", "sbwt_gpu_query_host_sharded",
     "sbwt_gpu_update_interval_batch", "sbwt_gpu_partial_search_batch", "sbwt_gpu_forward_batch", "sbwt_gpu_contains_batch",
-    "sbwt_gpu_get_kmer_batch", "sbwt_gpu_ascii_export_sets", "sbwt_gpu_index_l2_set_aside",
+    "sbwt_gpu_get_kmer_batch", "sbwt_gpu_ascii_export_sets", "sbwt_gpu_index_l2_set_aside", "sbwt_gpu_query_host_hits",
 ]
 
 TEXT_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
@@ -105,6 +105,7 @@ def lib():
         L.sbwt_gpu_text_capacity.restype = i64
         L.sbwt_gpu_format_device.argtypes = [vp, vp, i32, vp, i64, vp, i64, vp, vp]
         L.sbwt_gpu_query_host_text.argtypes = [vp, vp, vp, i64, i32, i32, TEXT_SINK, vp, C.POINTER(i64)]
+        L.sbwt_gpu_query_host_hits.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, C.POINTER(i64)]
         L.sbwt_gpu_update_interval_batch.argtypes = [vp, vp, vp, i64, vp, vp]
         L.sbwt_gpu_partial_search_batch.argtypes = [vp, vp, vp, i64, vp, vp, vp]
         L.sbwt_gpu_forward_batch.argtypes = [vp, vp, vp, i64, vp]
@@ -320,6 +321,20 @@ class Session:
     def widen_threads(self) -> int:
         """Host threads query_host widens int32 wire results with (0: int64 over PCIe, -1: undecided)."""
         return lib().sbwt_gpu_session_widen_threads(self._h)
+
+    def query_host_hits(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER, *, want_hits: bool = True,
+                        mask: np.ndarray | None = None, hits: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray | None, int]:
+        """sbwt_gpu_query_host_hits: (membership bitmap as uint32 words, found values in order or None, number of hits)."""
+        assert ascii_.dtype == np.uint8 and ascii_.flags.c_contiguous and offsets.dtype == np.int64 and offsets.flags.c_contiguous
+        n_out = self.count_outputs(offsets)
+        if mask is None:
+            mask = np.empty((n_out + 31) // 32, dtype=np.uint32)
+        if want_hits and hits is None:
+            hits = np.empty(max(1, n_out), dtype=np.int32)
+        n = C.c_int64(0)
+        _check(lib().sbwt_gpu_query_host_hits(self._h, ascii_.ctypes.data, offsets.ctypes.data, offsets.size - 1, mode, case_mode,
+                                              mask.ctypes.data, hits.ctypes.data if want_hits else None, C.byref(n)))
+        return mask, (hits[: n.value] if want_hits else None), n.value
 
     def query_host_i32(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER,
                        out: np.ndarray | None = None) -> np.ndarray:

@@ -433,6 +433,51 @@ __global__ void __launch_bounds__(256) sparse_pack_kernel(const int32_t* __restr
     }
 }
 
+// ------------------------------------------------------------------ hits-only results, in order (sbwt_gpu_query_host_hits)
+//
+// The caller-facing form of the sparse format: one membership bit per result, numbered over the WHOLE host batch (bit0 =
+// number of the chunk's first result), and the found values in result order. Blocks of 4096 bit positions, aligned to
+// the batch numbering; a chunk-local result i sits at bit sh + i of the chunk's first word, sh = bit0 & 31.
+//   pass 1: mask words + hits per block;  (exclusive scan of the block counts);  pass 2: the hits, packed in order.
+template <bool EMIT, typename T>
+__global__ void __launch_bounds__(256) hits_kernel(const T* __restrict__ vals, int64_t n, uint32_t sh, uint32_t* __restrict__ masks,
+                                                   int64_t* __restrict__ block_count, const int64_t* __restrict__ block_base,
+                                                   int32_t* __restrict__ packed) {
+    __shared__ uint32_t warp_cnt[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t g0 = (int64_t)blockIdx.x * (kSparseBlock / 32) + w * 16; // first mask word of this warp
+    int32_t v[16]; // (EMIT exists for int32 values only; for int64 values only the sign is used)
+    uint32_t m[16];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int64_t idx = (g0 + i) * 32 + lane - (int64_t)sh;
+        v[i] = (idx >= 0 && idx < n) ? (sizeof(T) == 4 ? (int32_t)vals[idx] : (vals[idx] < 0 ? -1 : 0)) : -1;
+        m[i] = __ballot_sync(0xFFFFFFFFu, v[i] >= 0);
+        cnt += __popc(m[i]);
+        if (!EMIT && lane == 0 && (g0 + i) * 32 < (int64_t)sh + n) masks[g0 + i] = m[i];
+    }
+    if (lane == 0) warp_cnt[w] = cnt;
+    __syncthreads();
+    if (!EMIT) {
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int i = 0; i < 8; i++) t += warp_cnt[i];
+            block_count[blockIdx.x] = t;
+        }
+        return;
+    }
+    uint32_t before = 0;
+    for (int i = 0; i < w; i++) before += warp_cnt[i];
+    int64_t pos = block_base[blockIdx.x] + before;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (v[i] >= 0) packed[pos + __popc(m[i] & lt)] = v[i];
+        pos += __popc(m[i]);
+    }
+}
+
 // ------------------------------------------------------------------ random-sector probe
 
 // Each thread issues `per_thread` independent random aligned loads of BYTES (32 or 64) and xors them.

@@ -86,7 +86,7 @@ struct Writer {
         if (!fp) throw std::runtime_error("Error opening file: " + name);
     }
     ~Writer() {
-        if (fp) fclose(fp);
+        if (fp) fclose(fp); // (error paths; finish() closes and checks on the normal one)
     }
     void put(const char* p, size_t n) {
         if (n && fwrite(p, 1, n, fp) != n) throw std::runtime_error("Error writing output");
@@ -133,6 +133,11 @@ struct Writer {
             deflate_member("", 0, part);
             put(part.data(), part.size());
         }
+        // a full disk shows up here at the latest: do not report success over a truncated file
+        const bool bad = fflush(fp) != 0 || ferror(fp);
+        const int rc = fclose(fp);
+        fp = nullptr;
+        if (bad || rc != 0) throw std::runtime_error("Error writing output");
     }
 };
 
@@ -204,6 +209,7 @@ static int64_t query_batch_multi(const vector<const sbwt::plain_matrix_sbwt_t*>&
 static int64_t run_file(const string& infile, const string& outfile, const vector<const sbwt::plain_matrix_sbwt_t*>& replicas, bool gzip_output,
                         const Options& opt, long long& query_micros) {
     const sbwt::plain_matrix_sbwt_t& index = *replicas[0];
+    const long long file_t0 = cur_time_micros();
     sbwt_b200::ParallelFastxReader reader(infile, opt.threads); // same batches and errors as the serial FastxReader
     Writer writer(outfile, gzip_output, opt.threads);
     SinkState sink{&writer, ""};
@@ -247,6 +253,11 @@ static int64_t run_file(const string& infile, const string& outfile, const vecto
         ahead.join();
     }
     writer.finish();
+    {
+        const double file_s = (double)(cur_time_micros() - file_t0) / 1e6;
+        write_log("queries: " + std::to_string(n_queries) + " in " + std::to_string(file_s) + " s of parsing + querying + writing (index load excluded): " +
+                  std::to_string((double)n_queries / std::max(file_s, 1e-9)) + " lookups/s");
+    }
     write_log("us/query: " + std::to_string((double)query_micros / std::max<int64_t>(n_queries, 1)) + " (excluding I/O etc)");
     return n_queries;
 }
@@ -277,26 +288,54 @@ static int search_main(int argc, char** argv) {
     vector<int> devices; // --devices a,b,...: one replica of the index per listed device, every batch split over them
     Options opt;
     if (argc == 1) { print_help(argv[0]); return 1; }
-    for (int i = 1; i < argc; i++) {
-        string a = argv[i];
-        auto value = [&](const char* name) -> string {
-            if (i + 1 >= argc) throw std::runtime_error(string("Option '") + name + "' is missing an argument");
-            return argv[++i];
-        };
-        if (a == "-h" || a == "--help") { print_help(argv[0]); return 1; }
-        else if (a == "-o" || a == "--out-file") { out_file = value("out-file"); have_o = true; }
-        else if (a == "-i" || a == "--index-file") { index_file = value("index-file"); have_i = true; }
-        else if (a == "-q" || a == "--query-file") { query_file = value("query-file"); have_q = true; }
-        else if (a == "-z" || a == "--gzip-output") gzip_output = true;
-        else if (a == "--device") device = std::stoi(value("device"));
-        else if (a == "--devices") {
-            std::stringstream ss(value("devices"));
+    // cxxopts' forms (sbwt_search.cpp:149-165): --name value, --name=value, -n value, -nvalue, grouped short flags (-zo out)
+    struct Opt { char short_name; const char* long_name; bool takes_value; };
+    static const Opt table[] = {{'o', "out-file", true}, {'i', "index-file", true}, {'q', "query-file", true}, {'z', "gzip-output", false},
+                                {'h', "help", false}, {0, "device", true}, {0, "devices", true}, {0, "batch-bases", true}, {0, "threads", true}};
+    bool want_help = false;
+    auto apply = [&](const Opt& o, const string& v) {
+        const string name = o.long_name;
+        if (name == "out-file") { out_file = v; have_o = true; }
+        else if (name == "index-file") { index_file = v; have_i = true; }
+        else if (name == "query-file") { query_file = v; have_q = true; }
+        else if (name == "gzip-output") gzip_output = true;
+        else if (name == "help") want_help = true;
+        else if (name == "device") device = std::stoi(v);
+        else if (name == "devices") {
+            std::stringstream ss(v);
             for (string tok; std::getline(ss, tok, ',');) devices.push_back(std::stoi(tok));
         }
-        else if (a == "--batch-bases") opt.batch_bases = std::stoll(value("batch-bases"));
-        else if (a == "--threads") opt.threads = std::stoi(value("threads"));
-        else throw std::runtime_error("Option '" + a + "' does not exist");
+        else if (name == "batch-bases") opt.batch_bases = std::stoll(v);
+        else if (name == "threads") opt.threads = std::stoi(v);
+    };
+    for (int i = 1; i < argc; i++) {
+        const string a = argv[i];
+        auto next_value = [&](const string& shown) -> string {
+            if (i + 1 >= argc) throw std::runtime_error("Option '" + shown + "' is missing an argument");
+            return argv[++i];
+        };
+        if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+            const size_t eq = a.find('=');
+            const string name = a.substr(2, eq == string::npos ? string::npos : eq - 2);
+            const Opt* o = nullptr;
+            for (const Opt& t : table) if (name == t.long_name) o = &t;
+            if (!o) throw std::runtime_error("Option '" + name + "' does not exist");
+            if (!o->takes_value) apply(*o, "");
+            else apply(*o, eq != string::npos ? a.substr(eq + 1) : next_value(name));
+        } else if (a.size() > 1 && a[0] == '-' && a != "--") {
+            for (size_t j = 1; j < a.size(); j++) {
+                const Opt* o = nullptr;
+                for (const Opt& t : table) if (t.short_name && a[j] == t.short_name) o = &t;
+                if (!o) throw std::runtime_error(string("Option '") + a[j] + "' does not exist");
+                if (!o->takes_value) { apply(*o, ""); continue; }
+                apply(*o, j + 1 < a.size() ? a.substr(j + 1) : next_value(string(1, a[j]))); // the rest of the token, or the next one
+                break;
+            }
+        } // (anything else is a positional argument: cxxopts keeps those aside without complaint, and so does this)
     }
+    if (want_help) { print_help(argv[0]); return 1; }
+    if (opt.batch_bases <= 0) throw std::runtime_error("Option 'batch-bases' must be positive");
+    if (opt.threads <= 0) throw std::runtime_error("Option 'threads' must be positive");
     if (!have_i) throw std::runtime_error("Option 'index-file' has no value");
     check_readable(index_file);
     if (!have_q) throw std::runtime_error("Option 'query-file' has no value");

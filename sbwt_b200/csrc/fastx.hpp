@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -180,16 +181,34 @@ public:
 
     // Fills a batch of whole reads: stops before exceeding max_bases (unless the batch is empty) or
     // max_reads. offsets gets n+1 entries starting at 0. Returns the number of reads (0 = end of file).
+    // A malformed record does not swallow the reads in front of it: they are returned as a (short) batch and the error is
+    // raised by the next call -- the reference answers and prints read by read, so everything before the bad record has
+    // been written when it throws (sbwt_search.cpp:45-65 over SeqIO.hh:255-360).
     int64_t next_batch(int64_t max_bases, int64_t max_reads, std::vector<char>& ascii, std::vector<int64_t>& offsets) {
         ascii.clear();
         offsets.clear();
         offsets.push_back(0);
+        if (pending_error) {
+            std::exception_ptr e = pending_error;
+            pending_error = nullptr;
+            std::rethrow_exception(e);
+        }
         while ((int64_t)offsets.size() - 1 < max_reads && (int64_t)ascii.size() < max_bases) {
-            if (next_read(ascii) == 0) break;
+            try {
+                if (next_read(ascii) == 0) break;
+            } catch (...) {
+                ascii.resize((size_t)offsets.back()); // (whatever the failed record had appended)
+                if (offsets.size() == 1) throw;
+                pending_error = std::current_exception();
+                break;
+            }
             offsets.push_back((int64_t)ascii.size());
         }
         return (int64_t)offsets.size() - 1;
     }
+
+private:
+    std::exception_ptr pending_error;
 };
 
 // Parallel batch reader for uncompressed FASTA / FASTQ files: the same batches, byte for byte, as

@@ -169,3 +169,70 @@ def test_devices_option_splits_every_batch_over_index_replicas(tmp_path):
     r = run("search", "-i", g("index.sbwt"), "-q", g("reads.fna"), "-o", o, "--batch-bases", "5000", "--devices", devs)
     assert r.returncode == 0, r.stderr
     assert open(o, "rb").read() == expected
+
+
+# ------------------------------------------------------------------ GPU: the command line against the reference's own reader / loop
+
+@pytest.mark.gpu
+def test_cli_matches_the_reference_on_wellformed_and_malformed_files(tmp_path):
+    """`sbwt_search` against `oracle/_ref/sbwt_ref search` (seq_io::Reader + the reference's classes) file by file: same
+    exit code, same error message, same output bytes -- including what has been written before a malformed record is
+    met (the reference answers read by read; the GPU pipeline hands a parse error on only after the reads in front of
+    it have been answered). Corpus: tests/test_fastx.py (every malformation SeqIO singles out) + well-formed files."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/sbwt_ref not built")
+    import numpy as np
+    from test_fastx import BAD, fasta, fastq
+    ix = golden("cli_k6", "index.sbwt")
+    rng = np.random.default_rng(4)
+    corpus = dict(BAD)
+    corpus["ok_multi.fna"] = fasta(rng, 60, True, max_len=120)
+    corpus["ok.fq"] = fastq(rng, 60, max_len=120)
+    corpus["ok_crlf.fna"] = fasta(rng, 20, True, crlf=True, max_len=60)
+    for name, data in sorted(corpus.items()):
+        for prefix in (b"", (fastq(rng, 30, max_len=80) if name.endswith(".fq") else fasta(rng, 30, True, max_len=80))):
+            if "wrong_start" in name or name.startswith("empty"):
+                prefix = b""
+            p = tmp_path / name
+            p.write_bytes(prefix + data)
+            o_ref, o_gpu = str(tmp_path / "ref.txt"), str(tmp_path / "gpu.txt")
+            for f in (o_ref, o_gpu):
+                if os.path.exists(f):
+                    os.remove(f)
+            ref = subprocess.run([oracle.REF_BIN, "search", "-i", ix, "-q", str(p), "-o", o_ref], capture_output=True, text=True)
+            for extra in ([], ["--batch-bases", "100"]):
+                gpu = run("search", "-i", ix, "-q", str(p), "-o", o_gpu, *extra)
+                assert gpu.returncode == ref.returncode, (name, gpu.stderr, ref.stderr)
+                if ref.returncode != 0:
+                    want = [line for line in ref.stderr.splitlines() if "rror" in line][-1]
+                    got = [line for line in gpu.stderr.splitlines() if "rror" in line][-1]
+                    assert got == want, (name, got, want)
+                ref_out = open(o_ref, "rb").read() if os.path.exists(o_ref) else b""
+                gpu_out = open(o_gpu, "rb").read() if os.path.exists(o_gpu) else b""
+                assert gpu_out == ref_out, (name, extra, len(gpu_out), len(ref_out))
+
+
+@pytest.mark.gpu
+def test_cxxopts_option_forms(tmp_path):
+    """--name=value, -nvalue and grouped short flags, as cxxopts accepts them (sbwt_search.cpp:149-165)."""
+    import gzip
+    ix, q = golden("cli_k6", "index.sbwt"), golden("cli_k6", "queries.fna")
+    known = open(golden("cli_k6", "known_answer.txt")).read()
+    o = str(tmp_path / "o.txt")
+    for args in (["--index-file=" + ix, "--query-file=" + q, "--out-file=" + o], ["-i" + ix, "-q" + q, "-o" + o],
+                 ["-i", ix, "--query-file", q, "-o", o, "stray-positional"]):
+        if os.path.exists(o):
+            os.remove(o)
+        r = run("search", *args)
+        assert r.returncode == 0, r.stderr
+        assert open(o).read() == known
+    oz = str(tmp_path / "o.txt.gz")
+    r = run("search", "-i", ix, "-q", q, "-zo", oz)
+    assert r.returncode == 0, r.stderr
+    assert gzip.open(oz).read().decode() == known
+    r = run("search", "-i", ix, "-q", q, "-o")
+    assert r.returncode == 1 and "is missing an argument" in r.stderr
+    r = run("search", "-i", ix, "-q", q, "-o", o, "--no-such-option")
+    assert r.returncode == 1 and "does not exist" in r.stderr
+    r = run("search", "-i", ix, "-q", q, "-o", o, "--batch-bases", "0")
+    assert r.returncode == 1 and "must be positive" in r.stderr

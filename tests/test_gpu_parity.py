@@ -169,6 +169,21 @@ def test_index_create_from_arrays_and_violated_invariant(tmp_path):
     assert not idx.edges_only_at_group_starts
     ses = S.Session(idx, a.size, len(reads))
     np.testing.assert_array_equal(ses.query_host(a, off, S.MODE_STREAMING), want)
+    # reads far longer than a work-item window (256 k-mers): on such an index the streaming answers depend on the previous
+    # k-mer across what would be a window boundary (SBWT.hh:556-576), so the batch is planned one item per read
+    ref = np.frombuffer(b"".join(read_fasta_reads(golden(name, "input.fna"))), dtype=np.uint8)
+    long_reads = []
+    for i in range(12):
+        o = int(rng.integers(0, ref.size - 2500))
+        r = ref[o:o + int(rng.integers(600, 2400))].copy()
+        for q in rng.integers(0, r.size, size=int(rng.integers(0, 5))):
+            r[int(q)] = ord("ACGTN"[int(rng.integers(0, 5))])
+        long_reads.append(bytes(r))
+    a2, off2 = synth.ragged_to_batch(long_reads)
+    want2 = oracle.OracleIndex(p).query_batch(a2, off2, streaming=True)
+    ses2 = S.Session(idx, a2.size, len(long_reads))
+    np.testing.assert_array_equal(ses2.query_host(a2, off2, S.MODE_STREAMING), want2)
+    ses2.close()
     idx2 = S.Index(p)
     assert not idx2.edges_only_at_group_starts
     # an inconsistent C array is rejected
@@ -630,4 +645,54 @@ def test_forward_needs_streaming_support():
     idx = S.Index(golden("cli_k6", "index_nostream.sbwt"))
     with pytest.raises(S.SbwtGpuError, match="Streaming support required"):
         idx.forward([1], b"A")
+    idx.close()
+
+
+def test_hits_only_results():
+    """sbwt_gpu_query_host_hits: membership bitmap over the whole batch + the found values in order reproduce the dense
+    result array of the oracle; chunked sessions (chunk boundaries inside mask words), pinned and pageable buffers,
+    bitmap alone, both modes, and the bitmap alone on an index that is forced wide."""
+    vals, _ = parse_expected(c1_expected())
+    reads = c1_reads()
+    a, off = synth.ragged_to_batch(reads)
+    idx = S.Index(golden("c1", "index.sbwt"))
+    n_out = vals.size
+
+    def expand(mask, hits):
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[:n_out].astype(bool)
+        out = np.full(n_out, -1, dtype=np.int64)
+        out[bits] = hits
+        return out
+
+    for max_bases, max_reads in ((a.size, len(reads)), (7001, 13), (100_000, 1000)):
+        ses = S.Session(idx, max_bases, max_reads)
+        for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+            mask, hits, n = ses.query_host_hits(a, off, mode)
+            assert n == int((vals >= 0).sum())
+            np.testing.assert_array_equal(expand(mask, hits), vals)
+        mask2, none, n2 = ses.query_host_hits(a, off, S.MODE_STREAMING, want_hits=False)
+        assert none is None and n2 == n and np.array_equal(mask2, mask)
+        pm, ph = S.pinned_empty(mask.size, np.uint32), S.pinned_empty(n_out, np.int32)
+        pm[:] = 0xFFFFFFFF
+        mask3, hits3, n3 = ses.query_host_hits(a, off, S.MODE_STREAMING, mask=pm, hits=ph)
+        np.testing.assert_array_equal(expand(mask3, hits3), vals)
+        ses.close()
+    idx.close()
+
+
+def test_hits_only_bitmap_on_wide_index(monkeypatch):
+    monkeypatch.setenv("SBWT_B200_FORCE_WIDE", "3")
+    name = "small_k31"
+    vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+    reads = read_fasta_reads(golden(name, "reads.fna"))
+    a, off = synth.ragged_to_batch(reads)
+    idx = S.Index(golden(name, "index.sbwt"))
+    ses = S.Session(idx, 5000, 50)
+    mask, _, n = ses.query_host_hits(a, off, S.MODE_STREAMING, want_hits=False)
+    bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[: vals.size].astype(bool)
+    np.testing.assert_array_equal(bits, vals >= 0)
+    assert n == int((vals >= 0).sum())
+    with pytest.raises(S.SbwtGpuError, match="fewer than 2\\^31"):
+        ses.query_host_hits(a, off, S.MODE_STREAMING)
+    ses.close()
     idx.close()
