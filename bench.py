@@ -1,29 +1,38 @@
 #!/usr/bin/env python
 """bench.py -- k-mer lookups/s of the plain-matrix SBWT query path on B200.
 
-A "step" is one pass of the hot path (pack -> plan -> walk) over one batch of synthetic reads.
-Default workload = BASELINE.json configs[1] ("c2"): 100 Mbp random-DNA reference, k=31
-plain-matrix index with streaming support (p=8), 10 M x 150 bp reads at 50 % hit rate,
-streaming_search. `--workload c3` is the same index without streaming support (per-k-mer
-search), `--workload c4s` / `c5s` a scaled pangenome-like index (+RC, k = 31 / 63) that exceeds L2.
+A "step" is one pass of the hot path (pack -> plan -> walk) over one batch of synthetic reads (10 M x 150 bp per GPU).
+Headline workload = BASELINE.json configs[1] ("c2"): 100 Mbp random-DNA reference, k=31 plain-matrix index with
+streaming support (p=8), reads at 50 % hit rate, streaming_search. The default run ALSO measures the other single-GPU
+configurations and attaches them under "workloads": c3 = configs[2] (the same reference without streaming support:
+per-k-mer search), c4s / c5s = configs[3] / [4] on a 40-copy scale model of the pangenome-like reference (index > L2).
+`--workload c4` / `c5` run those two at FULL size (400 copies = 2 Gbp +RC, 2.6 G / 4 G columns: ~2-5 min of index
+construction on the box, so not part of the default run; records under profiles/).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4s|c5s|tiny] [--reads R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--legs a,b,..|none]
 
-Prints ONE JSON line (rank 0). `value` is measured with inputs resident in HBM, `e2e` through
-sbwt_gpu_query_host with pinned HOST buffers (H2D + D2H inside the timed region). `roofline` carries the
-counted algorithmic sector bytes of the walk kernel against the measured HBM copy peak, the DRAM bytes one
-launch really moves (profiles/traffic.json, from ncu), the measured random-sector ceilings and the same kernel
-timed with the shorter search table; `cpu_baseline` is the reference's own query code on the host cores.
-`--impl reference` runs only that (the reference arm of the contract).
-Multi-GPU (torchrun, one rank per GPU): the index is replicated, every rank answers its own
-shard of reads, no collective on the data path (weak scaling); NCCL is used only for the
-barrier and the max-over-ranks of the timing the contract asks for.
+Prints ONE JSON line (rank 0):
+  value      lookups/s with inputs resident in HBM (pack + plan + walk on device buffers), max over ranks
+  e2e        the same metric through sbwt_gpu_query_host with pinned HOST buffers (H2D + D2H inside the timed region),
+             plus the int32, hits-only and bitmap-only forms of the call and the measured host-memory ceiling
+  roofline   walk kernel: counted distinct index sectors x 32 B / mean kernel time against the measured HBM copy peak,
+             and the sector RATE against the measured random-sector ceiling of the level the index lives in
+  parity     GPU results of this run against the reference's own classes (oracle/_ref/sbwt_ref) on the same reads:
+             lookups, hits, sum and position-weighted checksum of the results
+  cpu_baseline  the reference's query code on the host cores (default build and hardware-popcount build, 1 and N cores,
+             in memory and as N single-threaded processes with I/O)
+  workloads  the same measurements (value, kernel, roofline fractions, parity) for the other configurations
+`--impl reference` runs only the reference arm of the contract (CPU).
+Multi-GPU (torchrun, one rank per GPU): the index is replicated, every rank answers its own shard of reads, no
+collective on the data path (weak scaling); NCCL is used only for the barrier and the max-over-ranks of the timing.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -37,6 +46,7 @@ sys.path.insert(0, ROOT)
 from sbwt_b200.testing import build_index, synth  # noqa: E402
 
 CACHE = os.path.join(ROOT, ".cache", "bench")
+MASK64 = (1 << 64) - 1
 
 WORKLOADS = {
     # name: reference generator, k, streaming, add_rc, default reads
@@ -48,7 +58,7 @@ WORKLOADS = {
                 ref=("pangenome", 40, 5_000_000, 44), k=31, streaming=True, rc=True, reads=10_000_000),
     "c5s": dict(desc="configs[4] scaled: the same pangenome-like reference, k=63 (+RC), index > L2, streaming_search, 88 lookups per 150-bp read",
                 ref=("pangenome", 40, 5_000_000, 44), k=63, streaming=True, rc=True, reads=10_000_000),
-    "c4": dict(desc="configs[3] at full size: pangenome-like 400 x 5 Mbp mutated copies (5% subst.) = 2 Gbp, k=31 +RC (~3.2 G columns: narrow layout with values >= 2^31), streaming_search",
+    "c4": dict(desc="configs[3] at full size: pangenome-like 400 x 5 Mbp mutated copies (5% subst.) = 2 Gbp, k=31 +RC (2.56 G columns: narrow layout with values >= 2^31), streaming_search",
                ref=("pangenome", 400, 5_000_000, 44), k=31, streaming=True, rc=True, reads=10_000_000),
     "c5": dict(desc="configs[4] at full size: the same 2 Gbp pangenome-like reference, k=63 (+RC), streaming_search, 88 lookups per 150-bp read",
                ref=("pangenome", 400, 5_000_000, 44), k=63, streaming=True, rc=True, reads=10_000_000),
@@ -57,17 +67,23 @@ WORKLOADS = {
     "tiny": dict(desc="smoke-sized: 2 Mbp random DNA, k=31, streaming", ref=("contigs", 2, 1_000_000, 42), k=31, streaming=True,
                  rc=False, reads=200_000),
 }
+DEFAULT_LEGS = {"c2": ["c3", "c4s", "c5s"]}  # measured next to the headline workload in the default run
+L2_RESIDENT_BYTES = 60 << 20                 # randomly read data up to this size stays in L2 (profiles/r01g_l2_capacity.txt)
 
 
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+_REF_CACHE: dict = {}
+
+
 def reference_matrix(spec):
-    kind, n, length, seed = spec
-    if kind == "contigs":
-        return synth.random_contigs(n, length, seed)
-    return synth.pangenome(length, n, 0.05, seed)
+    if spec not in _REF_CACHE:
+        kind, n, length, seed = spec
+        _REF_CACHE.clear()  # (one at a time: the full-size pangenome is 2 GB)
+        _REF_CACHE[spec] = synth.random_contigs(n, length, seed) if kind == "contigs" else synth.pangenome(length, n, 0.05, seed)
+    return _REF_CACHE[spec]
 
 
 def ensure_index(name: str, w: dict) -> tuple[str, np.ndarray]:
@@ -142,6 +158,16 @@ def peaks() -> tuple[float, str]:
     return 6650.0, "fallback"
 
 
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def write_sample_fasta(path: str, reads: np.ndarray) -> None:
     n, L = reads.shape
     m = np.empty((n, L + 3), dtype=np.uint8)
@@ -149,33 +175,370 @@ def write_sample_fasta(path: str, reads: np.ndarray) -> None:
     m.tofile(path)
 
 
-def cpu_reference(index_path: str, reads: np.ndarray, streaming: bool, threads: int | None = None, reps: int = 1) -> dict:
-    """Time the reference's own query code (oracle/_ref/sbwt_ref, compiled from /root/reference) on the
-    host cores over a bounded sample; falls back to the C port of the oracle when _ref is absent."""
+# ---------------------------------------------------------------------------------------------- the reference on the host
+
+def ref_timed(index_path: str, reads: np.ndarray, streaming: bool, threads: int, popcnt: bool = True, reps: int = 1) -> dict:
+    """The reference's own query code (oracle/_ref/sbwt_ref[_popcnt], compiled from /root/reference) over `reads`, T threads
+    sharing one loaded index, only the query loop timed; falls back to the C port of the oracle when _ref is absent.
+    Returns lookups, hits, checksum, weighted_checksum, seconds, value."""
     import oracle
-    threads = threads or os.cpu_count() or 1
-    n = int(min(reads.shape[0], 2_000_000))  # c2: ~3 s on 16 threads (~50 core-seconds); c3: ~20 s
-    sample = reads[:n]
-    if oracle.ref_available():
+    n = reads.shape[0]
+    binary = os.path.join(os.path.dirname(oracle.REF_BIN), "sbwt_ref_popcnt" if popcnt else "sbwt_ref")
+    if not os.path.exists(binary):
+        binary = oracle.REF_BIN
+        popcnt = False
+    if os.path.exists(binary):
+        os.makedirs(CACHE, exist_ok=True)
         q = os.path.join(CACHE, f"cpu_sample_{os.getpid()}.fna")
-        write_sample_fasta(q, sample)
+        write_sample_fasta(q, reads)
         try:
-            res = oracle.ref_run("timed", "-i", index_path, "-q", q, "-t", str(threads), "-r", str(reps))
+            res = subprocess.run([binary, "timed", "-i", index_path, "-q", q, "-t", str(threads), "-r", str(reps)], capture_output=True, check=True)
         finally:
             os.remove(q)
         r = json.loads(res.stdout.decode().strip().splitlines()[-1])
-        return {"value": r["lookups"] / r["seconds"], "unit": "lookups/s", "cores": threads, "kind": "reference",
-                "sample": f"first {n} reads ({r['lookups']} lookups, {r['hits']} hits) of the workload, {threads} threads over "
-                          f"SBWT::{'streaming_search' if streaming else 'search'} compiled from the reference sources",
-                "seconds": r["seconds"], "checksum": r["checksum"], "hits": r["hits"], "lookups": r["lookups"]}
-    a, off = synth.matrix_to_batch(sample[: max(20_000, n // max(1, threads))])
+        r.update(kind="reference", cores=threads,
+                 build="hardware popcount (-march=x86-64-v3 on the driver TU)" if popcnt else "default (the reference's CMakeLists.txt passes no -march: software popcount)",
+                 value=r["lookups"] / r["seconds"],
+                 sample=f"first {n} reads ({r['lookups']} lookups, {r['hits']} hits) of the workload, {threads} thread(s) over "
+                        f"SBWT::{'streaming_search' if streaming else 'search'} compiled from the reference sources, queries only")
+        return r
+    a, off = synth.matrix_to_batch(reads[: max(20_000, n // max(1, threads))])
     idx = oracle.OracleIndex(index_path)
     t0 = time.perf_counter()
     out = idx.query_batch(a, off, streaming=streaming)
     sec = time.perf_counter() - t0
-    return {"value": out.size / sec, "unit": "lookups/s", "cores": 1, "kind": "port",
-            "sample": f"first {off.size - 1} reads on 1 thread of the C oracle port (oracle/_ref not present)", "seconds": sec,
-            "checksum": int(out.sum()), "hits": int((out >= 0).sum()), "lookups": int(out.size)}
+    w = int((out.astype(np.uint64) * np.arange(1, out.size + 1, dtype=np.uint64)).sum(dtype=np.uint64))
+    return {"value": out.size / sec, "cores": 1, "kind": "port", "build": "C port of the oracle (oracle/_ref not present)",
+            "sample": f"first {off.size - 1} reads on 1 thread of the C oracle port", "seconds": sec,
+            "checksum": int(out.sum()), "weighted_checksum": w, "hits": int((out >= 0).sum()), "lookups": int(out.size)}
+
+
+def ref_processes(index_path: str, reads: np.ndarray, n_proc: int) -> dict:
+    """N single-threaded `search` processes (index load, parsing and output included), each on a 1/N
+    shard of the reads -- how the reference itself would be run on all cores (it has no threads)."""
+    import oracle
+    if not oracle.ref_available():
+        return {}
+    shards = []
+    n = reads.shape[0]
+    for i in range(n_proc):
+        q = os.path.join(CACHE, f"cpu_shard_{os.getpid()}_{i}.fna")
+        write_sample_fasta(q, reads[n * i // n_proc: n * (i + 1) // n_proc])
+        shards.append(q)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([oracle.REF_BIN, "search", "-i", index_path, "-q", q, "-o", "/dev/null"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE) for q in shards]
+    nq = 0
+    for p in procs:
+        err = p.communicate()[1].decode()
+        m = re.search(r"queries: (\d+)", err)
+        nq += int(m.group(1)) if m else 0
+    sec = time.perf_counter() - t0
+    for q in shards:
+        os.remove(q)
+    return {"value": nq / sec, "processes": n_proc, "seconds": sec, "lookups": nq,
+            "what": f"{n_proc} single-threaded reference processes, default build, wall time with index load, FASTA parsing and text output to /dev/null"}
+
+
+def host_widen_ceiling(threads: int) -> dict | None:
+    """tools/host_bw_probe: how many int32 -> int64 values per second `threads` host threads can write (stream stores):
+    the ceiling of any call that must hand back a dense int64 array of results."""
+    exe = os.path.join(ROOT, "tools", "host_bw_probe")
+    if not os.path.exists(exe) or threads < 1:
+        return None
+    try:
+        out = subprocess.run([exe, "200000000"], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    best = None
+    for line in out.splitlines():
+        m = re.match(r"threads=\s*(\d+) widen.*?: ([\d.]+) G values/s", line)
+        if m and int(m.group(1)) <= threads:
+            best = (int(m.group(1)), float(m.group(2)) * 1e9)
+    return None if best is None else {"threads": best[0], "values_per_s": best[1],
+                                      "how": "tools/host_bw_probe.cpp: int32 -> int64 with non-temporal stores, 2e8 values, best of 3"}
+
+
+# ---------------------------------------------------------------------------------------------- one workload on one GPU
+
+def gpu_digest(torch, d_out, n: int) -> dict:
+    """hits, sum and position-weighted checksum (sum of (i+1) * value modulo 2^64) of the first n results, on the device."""
+    hits, s, ws = 0, 0, 0
+    step = 1 << 27
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        x = d_out[a:b]
+        hits += int((x >= 0).sum().item())
+        s += int(x.sum().item())
+        ws += int((x * torch.arange(a + 1, b + 1, device=x.device, dtype=torch.int64)).sum().item())  # (int64 wraps like uint64)
+    return {"hits": hits, "checksum": s, "weighted_checksum": ws & MASK64}
+
+
+def measure(name: str, args, env: dict, headline: bool) -> dict:
+    """Index, reads, counted run, parity against the reference, timed steps. Returns the workload's record; for the headline
+    workload the device / host objects needed by the e2e legs are kept in env['keep']."""
+    import torch
+
+    import sbwt_b200 as S
+    rank, local_rank, world, dist, barrier = env["rank"], env["local_rank"], env["world"], env["dist"], env["barrier"]
+    w = WORKLOADS[name]
+    n_reads = args.reads or w["reads"]
+    L, k = args.read_len, w["k"]
+    steps = args.steps if headline else max(3, min(args.steps, 5))
+    if rank == 0:
+        path, ref = ensure_index(name, w)
+    barrier()
+    if rank != 0:
+        path, ref = ensure_index(name, w)
+    t0 = time.time()
+    rkey = (w["ref"], n_reads, L, w["rc"], rank)
+    if env.get("reads_key") != rkey:  # (c3 reuses c2's reads, c5s those of c4s)
+        env["reads"], env["reads_key"] = synth.sample_reads(ref, n_reads, L, 0.5, seed=43 + rank, both_strands=w["rc"]), rkey
+        log(f"rank {rank}: {name}: {n_reads} reads generated in {time.time() - t0:.1f}s")
+    reads = env["reads"]
+    a, off = synth.matrix_to_batch(reads)
+    mode = S.MODE_STREAMING if w["streaming"] else S.MODE_SEARCH
+    idx = S.Index(path, device=local_rank)
+    ses = S.Session(idx, a.size, n_reads)
+    n_out = ses.count_outputs(off)
+    d_a, d_off = torch.from_numpy(a).cuda(), torch.from_numpy(off).cuda()
+    d_out = torch.empty(n_out, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ses.query_device(d_a.data_ptr(), d_off.data_ptr(), n_reads, a.size, mode, d_out.data_ptr(), n_out, stream)
+
+    stats = ses.query_device_counted(d_a.data_ptr(), d_off.data_ptr(), n_reads, a.size, mode, d_out.data_ptr(), n_out, stream)
+    hits_gpu = int((d_out >= 0).sum().item())
+    assert stats.lookups == n_out and stats.hits == hits_gpu
+
+    # ---- parity: the reference's own classes on the same reads (rank 0; outside every timed region)
+    parity, cpu_run = None, None
+    if rank == 0 and not args.no_parity:
+        full = world == 1 and name in ("c2", "c3") and not args.quick_parity
+        n_par = n_reads if full else min(n_reads, 2_000_000)
+        threads = os.cpu_count() or 1
+        cpu_run = ref_timed(path, reads[:n_par], w["streaming"], threads, popcnt=True)
+        m_out = n_par * max(0, L - k + 1)
+        dg = gpu_digest(torch, d_out, m_out)
+        ok = {key: int(cpu_run[key]) & MASK64 == int(dg[key]) & MASK64 for key in ("hits", "checksum", "weighted_checksum")}
+        ok["lookups"] = int(cpu_run["lookups"]) == m_out
+        parity = {"reads": n_par, "lookups": m_out, "hits": dg["hits"], "checksum": dg["checksum"], "weighted_checksum": dg["weighted_checksum"],
+                  "lookups_match": ok["lookups"], "hits_match": ok["hits"], "checksum_match": ok["checksum"], "weighted_checksum_match": ok["weighted_checksum"],
+                  "checker": "sbwt_ref" if cpu_run["kind"] == "reference" else "oracle port",
+                  "what": "hits, sum and position-weighted checksum (sum of (i+1) x value mod 2^64) of the GPU results of the FIRST `reads` reads against "
+                          "the reference's own SBWT::" + ("streaming_search" if w["streaming"] else "search") + " on the same reads and index"}
+        if not all(ok.values()):
+            raise SystemExit(f"PARITY FAILURE on {name}: {parity} vs reference {cpu_run}")
+        log(f"{name}: parity with {parity['checker']} on {n_par} reads ({m_out} lookups): OK ({cpu_run['value'] / 1e6:.1f} M lookups/s on {threads} host threads)")
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    ses.set_timing(True)
+    walk_ms, prep_ms = [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    S.launch_count(reset=True)
+    barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(steps):
+            step()
+            p_ms, w_ms = ses.last_timing()
+            prep_ms.append(p_ms)
+            walk_ms.append(w_ms)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+    gpu_launches = S.launch_count()
+    ses.set_timing(False)
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / steps
+    value = world * n_out / (ms_per_step * 1e-3)
+
+    peak, peak_src = peaks()
+    w_ms = float(np.mean(walk_ms))
+    compact = bool(idx.compact_layout[0] and w["streaming"])
+    hot = int(32 * (idx.n_nodes // 64 + 1)) if compact else int(128 * (idx.n_nodes // 224 + 1))
+    level = "l2" if hot <= L2_RESIDENT_BYTES else "dram"
+    achieved = stats.index_sectors * 32 / (w_ms * 1e-3) / 1e9
+    sectors_per_s = stats.index_sectors / (w_ms * 1e-3)
+    ceil = env.get("ceilings") or {}
+    tr = env["traffic"].get(name)
+    roofline = {"bound": "l2-latency" if level == "l2" else "hbm",
+                "bound_note": ("the rank structure is L2-resident: the walk is bound by the latency of dependent random sector reads (and by the SM's rate of "
+                               "divergent 32-byte requests), not by HBM bandwidth; `frac` against the HBM copy peak is kept for the contract, the figure that "
+                               "matters is frac_of_level_ceiling") if level == "l2" else
+                              "every missing sector moves one 128-byte line from HBM: bound by the DRAM random-line rate (random_sector_ceiling.dram)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel": "walk_kernel",
+                "kernel_ms": w_ms, "kernel_share_of_step": w_ms / ms_per_step, "prep_ms": float(np.mean(prep_ms)),
+                "algorithmic_sectors_per_step": int(stats.index_sectors), "sectors_per_s": sectors_per_s,
+                "rank_ops_per_step": int(stats.rank_ops), "rank_ops_per_s": stats.rank_ops / (w_ms * 1e-3),
+                "nominal_frac": stats.rank_ops * 32 / (w_ms * 1e-3) / 1e9 / peak, "table_length": int(idx.table_length),
+                "index_level": level, "hot_bytes": hot,
+                "level_ceiling_sectors_per_s": ceil.get(level), "frac_of_level_ceiling": (sectors_per_s / ceil[level]) if ceil.get(level) else None,
+                "traffic": tr["bytes"] if tr else None,
+                "traffic_source": (f"profile constant, NOT measured in this run: dram__bytes_read + dram__bytes_write of one launch from {tr['source']} "
+                                   f"(library sha256 {tr.get('lib_sha256_12')}; this run's library {env['lib_sha']}"
+                                   + ("" if tr.get("lib_sha256_12") == env["lib_sha"] else ": DIFFERENT BINARY") + ")") if tr else None,
+                "traffic_over_algorithmic": (tr["bytes"] / (stats.index_sectors * 32)) if tr else None}
+    rec = {"workload": f"{name}: {w['desc']}", "value": value, "unit": "lookups/s", "ms_per_step": ms_per_step, "steps": steps,
+           "lookups_per_step_per_gpu": int(n_out), "hit_rate": hits_gpu / max(1, n_out), "n_nodes": int(idx.n_nodes), "k": k,
+           "index_device_bytes": int(idx.device_bytes), "l2_set_aside_bytes": int(idx.l2_set_aside),
+           "index_layout": ("csector64: one-hot, 64 columns x 4 characters + absolute counts per 32-byte sector" if compact else
+                            "classic sectors: 224 columns x 1 character + count per 32-byte sector") + f" (flagged csector fraction {idx.compact_layout[1]:.4f})",
+           "path": "streaming_search" if w["streaming"] else "search", "clocks": clk.summary(), "gpu_launches": int(gpu_launches),
+           "launches_per_step": int(stats.kernel_launches), "roofline": roofline, "parity": parity,
+           "cpu_reference": None if cpu_run is None else {key: cpu_run[key] for key in ("value", "cores", "kind", "build", "sample")}}
+    if headline:
+        env["keep"] = dict(idx=idx, ses=ses, d_out=d_out, a=a, off=off, n_out=n_out, n_reads=n_reads, mode=mode, path=path, reads=reads,
+                           hits=hits_gpu, cpu_run=cpu_run, w=w)
+    else:
+        ses.close()
+        idx.close()
+        del d_a, d_off, d_out
+        torch.cuda.empty_cache()
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------- e2e legs of the headline workload
+
+def e2e_legs(args, env: dict) -> dict:
+    import torch
+
+    import sbwt_b200 as S
+    K = env["keep"]
+    world, dist, barrier = env["world"], env["dist"], env["barrier"]
+    idx, a, off, n_out, mode, d_out, L = K["idx"], K["a"], K["off"], K["n_out"], K["mode"], K["d_out"], args.read_len
+    chunk_bases = min(args.e2e_chunk_bases, a.size)
+    chunk_reads = chunk_bases // max(1, L - 2) + 16
+    ses_h = S.Session(idx, chunk_bases, chunk_reads)
+    h_a, h_off, h_out = S.pinned_empty(a.size, np.uint8), S.pinned_empty(off.size, np.int64), S.pinned_empty(n_out, np.int64)
+    h_a[:], h_off[:] = a, off
+    head = d_out[: 120 * 50].cpu().numpy()
+    n_rep = max(1, min(args.steps, 3))
+
+    def timed(fn):
+        fn()  # warm-up (allocates the pipeline slots)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_rep):
+            fn()
+        sec = (time.perf_counter() - t0) / n_rep
+        if dist is not None:
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec
+
+    sec = timed(lambda: ses_h.query_host(h_a, h_off, mode, out=h_out))
+    assert np.array_equal(h_out[: head.size], head)
+    narrow32 = idx.n_nodes < (1 << 31)
+    sparse_wire = narrow32 and ses_h.widen_threads() > 0 and os.environ.get("SBWT_B200_WIRE", "sparse") != "dense"
+    sparse_bytes = int(n_out // 8 + 4 * K["hits"] + n_out // 1024)
+    e2e = {"value": world * n_out / sec, "unit": "lookups/s", "h2d_bytes_per_step": int(a.nbytes + off.nbytes),
+           "d2h_bytes_per_step": sparse_bytes if sparse_wire else int(n_out * (4 if (narrow32 and ses_h.widen_threads() > 0) else 8)),
+           "ms_per_step": sec * 1e3, "steps": n_rep,
+           "api": "sbwt_gpu_query_host (pinned host buffers, dense int64 results: what SBWT::streaming_search returns)",
+           "result_wire_format": ("sparse: one hit bit per result + the hits (int32) cross PCIe; host threads rebuild the caller's int64 array" if sparse_wire
+                                  else ("int32 over PCIe, sign-extended by host threads" if (narrow32 and ses_h.widen_threads() > 0) else "int64 over PCIe")),
+           "widen_threads": ses_h.widen_threads(), "host_threads": os.cpu_count()}
+    if env["rank"] == 0:
+        c = host_widen_ceiling(max(1, ses_h.widen_threads()))
+        if c:
+            e2e["host_ceiling"] = c  # (for the threads ONE rank uses; the ranks of a multi-GPU job share the host's memory system)
+            e2e["host_bw_frac"] = (n_out / sec) / c["values_per_s"]
+    pm = S.pinned_empty((n_out + 31) // 32, np.uint32)
+    if narrow32:
+        h32 = S.pinned_empty(n_out, np.int32)
+        s32 = timed(lambda: ses_h.query_host_i32(h_a, h_off, mode, out=h32))
+        assert np.array_equal(h32[: head.size].astype(np.int64), head)
+        e2e["int32_results"] = {"value": world * n_out / s32, "unit": "lookups/s", "ms_per_step": s32 * 1e3, "api": "sbwt_gpu_query_host_i32",
+                                "d2h_bytes_per_step": sparse_bytes if sparse_wire else int(n_out * 4)}
+        ph = h32  # (reused as the hits buffer)
+        res = {}
+        sh = timed(lambda: res.update(r=ses_h.query_host_hits(h_a, h_off, mode, mask=pm, hits=ph)))
+        mask, hits, nh = res["r"]
+        assert nh == K["hits"]
+        bits = np.unpackbits(mask[: (head.size + 31) // 32].view(np.uint8), bitorder="little")[: head.size].astype(bool)
+        assert np.array_equal(bits, head >= 0) and np.array_equal(hits[: int(bits.sum())], head[head >= 0])
+        e2e["hits_only"] = {"value": world * n_out / sh, "unit": "lookups/s", "ms_per_step": sh * 1e3, "d2h_bytes_per_step": int(n_out // 8 + 4 * nh),
+                            "api": "sbwt_gpu_query_host_hits: membership bitmap + the found values (int32) in order, DMA'd into the caller's pinned buffers; "
+                                   "no host thread touches results"}
+        del ph, h32
+    res = {}
+    sb = timed(lambda: res.update(r=ses_h.query_host_hits(h_a, h_off, mode, want_hits=False, mask=pm)))
+    assert res["r"][2] == K["hits"]
+    e2e["bitmap_only"] = {"value": world * n_out / sb, "unit": "lookups/s", "ms_per_step": sb * 1e3, "d2h_bytes_per_step": int(n_out // 8),
+                          "api": "sbwt_gpu_query_host_hits(hits = NULL): one membership bit per k-mer"}
+    ses_h.close()
+
+    # one process driving every visible GPU (sbwt_gpu_query_host_sharded): what a single `sbwt search --devices` gets
+    ndev = S.device_count()
+    if world == 1 and ndev > 1 and not args.no_sharded:
+        try:
+            idxs = [idx] + [S.Index(K["path"], device=d) for d in range(1, ndev)]
+            sess = [S.Session(ix, chunk_bases, chunk_reads) for ix in idxs]
+            s_sh = timed(lambda: S.query_host_sharded(sess, h_a, h_off, mode, out=h_out))
+            assert np.array_equal(h_out[: head.size], head)
+            e2e["sharded_e2e"] = {"value": n_out / s_sh, "unit": "lookups/s", "ms_per_step": s_sh * 1e3, "devices": ndev,
+                                  "api": "sbwt_gpu_query_host_sharded: one process, one host thread + session per device, dense int64 results"}
+            for x in sess:
+                x.close()
+            for ix in idxs[1:]:
+                ix.close()
+        except Exception as e:  # informational leg
+            e2e["sharded_e2e"] = {"error": str(e)}
+    return e2e
+
+
+def cli_e2e(args, env: dict) -> dict | None:
+    """Steady-state figure of the `sbwt search` command line on the full read file: parse + query + format + write, index load
+    excluded (the CLI reports it), output to /dev/null (1.2e9 results are 8 GB of text)."""
+    K = env["keep"]
+    exe = os.path.join(ROOT, "sbwt_b200", "csrc", "sbwt_search")
+    if not os.path.exists(exe):
+        return None
+    q = os.path.join(CACHE, f"cli_reads_{os.getpid()}.fna")
+    write_sample_fasta(q, K["reads"])
+    out = {"reads": int(K["reads"].shape[0]), "output": "/dev/null", "threads": min(16, os.cpu_count() or 8)}
+    try:
+        for key, extra in (("plain", []), ("gzip_output", ["-z"])):
+            r = subprocess.run([exe, "search", "-i", K["path"], "-q", q, "-o", "/dev/null", "--threads", str(out["threads"]), *extra],
+                               capture_output=True, text=True, timeout=600)
+            m = re.search(r"queries: (\d+) in ([\d.]+) s .*?: ([\d.]+) lookups/s", r.stderr)
+            out[key] = ({"lookups_per_s": float(m.group(3)), "seconds": float(m.group(2)), "lookups": int(m.group(1))} if (r.returncode == 0 and m)
+                        else {"error": r.stderr[-300:]})
+    finally:
+        os.remove(q)
+    return out
+
+
+def cpu_baseline_record(args, env: dict) -> dict | None:
+    """The reference on the host cores, as SURVEY.md section 8(d) specifies: default and hardware-popcount builds, one core and
+    all cores, in memory (queries only) and as N single-threaded processes with I/O; one headline number = the fastest."""
+    K = env["keep"]
+    if K["cpu_run"] is None:
+        return None
+    threads = os.cpu_count() or 1
+    path, reads, streaming = K["path"], K["reads"], K["w"]["streaming"]
+    best = K["cpu_run"]  # all threads, popcnt build, on the parity sample
+    variants = {"popcnt_all_cores": {key: best[key] for key in ("value", "cores", "seconds", "lookups")}}
+    if best["kind"] == "reference" and not args.quick_cpu:
+        n_all, n_one = min(reads.shape[0], 2_000_000), min(reads.shape[0], 150_000)
+        r = ref_timed(path, reads[:n_all], streaming, threads, popcnt=False)
+        variants["default_all_cores"] = {key: r[key] for key in ("value", "cores", "seconds", "lookups")}
+        for key, pc in (("default_1_core", False), ("popcnt_1_core", True)):
+            r = ref_timed(path, reads[:n_one], streaming, 1, popcnt=pc)
+            variants[key] = {k_: r[k_] for k_ in ("value", "cores", "seconds", "lookups")}
+        variants["processes_all_cores_with_io"] = ref_processes(path, reads[: min(reads.shape[0], 1_000_000)], threads)
+    return {"value": best["value"], "unit": "lookups/s", "cores": best["cores"], "kind": best["kind"], "sample": best["sample"],
+            "build": best["build"], "cpu_model": cpu_model(), "host_threads": threads, "variants": variants}
 
 
 def main() -> None:
@@ -185,11 +548,17 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--legs", default=None, help="other workloads measured in the same run, comma separated ('none' = only --workload); default: c3,c4s,c5s next to c2")
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's)")
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-cli", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--quick-parity", action="store_true", help="parity on 2 M reads instead of the whole batch (c2 / c3)")
+    ap.add_argument("--quick-cpu", action="store_true", help="only the all-core hardware-popcount CPU figure")
     ap.add_argument("--e2e-chunk-bases", type=int, default=48_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -200,8 +569,7 @@ def main() -> None:
     w = WORKLOADS[args.workload]
     n_reads = args.reads or w["reads"]
     L = args.read_len
-    k = w["k"]
-    config = {"workload": f"{args.workload}: {w['desc']}", "reads_per_gpu": n_reads, "read_len": L, "k": k, "precalc_k": 8,
+    config = {"workload": f"{args.workload}: {w['desc']}", "reads_per_gpu": n_reads, "read_len": L, "k": w["k"], "precalc_k": 8,
               "path": "streaming_search" if w["streaming"] else "search", "index": "replicated per GPU",
               "l2_policy": "inputs+outputs (>= 11 GB per step at full size) exceed L2; the index itself stays L2/HBM resident across steps as in production"}
 
@@ -216,13 +584,14 @@ def main() -> None:
         reads = synth.sample_reads(ref, n_s, L, 0.5, seed=43, both_strands=w["rc"])
         best = None
         for i in range(max(1, args.warmup) + max(1, args.steps)):
-            r = cpu_reference(path, reads, w["streaming"], threads)
+            r = ref_timed(path, reads, w["streaming"], threads, popcnt=True)  # (the faster of the two builds: favours the reference)
             if i >= max(1, args.warmup) and (best is None or r["value"] > best["value"]):
                 best = r
         line = {"impl": "reference", "metric": "kmer_lookups_per_s", "value": best["value"], "unit": "lookups/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["seconds"] * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
-                "cpu_baseline": {k_: best[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {"value": best["value"], "unit": "lookups/s", "cores": best["cores"], "kind": best["kind"], "sample": best["sample"],
+                                 "build": best["build"], "cpu_model": cpu_model()},
                 "e2e": {"value": best["value"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -245,238 +614,65 @@ def main() -> None:
         if dist is not None:
             dist.barrier()
 
-    if rank == 0:
-        path, ref = ensure_index(args.workload, w)
-    barrier()
-    if rank != 0:
-        path, ref = ensure_index(args.workload, w)
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    env = {"rank": rank, "local_rank": local_rank, "world": world, "dist": dist, "barrier": barrier,
+           "traffic": {k_: v for k_, v in (json.load(open(tp)) if os.path.exists(tp) else {}).items() if isinstance(v, dict) and "bytes" in v},
+           "lib_sha": hashlib.sha256(open(S.LIB_PATH, "rb").read()).hexdigest()[:12]}
+    if not args.no_probe:
+        try:  # the measured random-32-byte-gather ceilings the sector rates are quoted against
+            env["ceilings"] = {"dram": S.sector_probe(local_rank, 8 << 30, 1 << 28, 32), "l2": S.sector_probe(local_rank, 48 << 20, 1 << 28, 32)}
+        except Exception as e:
+            log(f"sector probe failed: {e}")
 
-    t0 = time.time()
-    reads = synth.sample_reads(ref, n_reads, L, 0.5, seed=43 + rank, both_strands=w["rc"])
-    a, off = synth.matrix_to_batch(reads)
-    log(f"rank {rank}: {n_reads} reads generated in {time.time() - t0:.1f}s")
-    mode = S.MODE_STREAMING if w["streaming"] else S.MODE_SEARCH
-    idx = S.Index(path, device=local_rank)
-    ses = S.Session(idx, a.size, n_reads)
-    n_out = ses.count_outputs(off)
-    d_a, d_off = torch.from_numpy(a).cuda(), torch.from_numpy(off).cuda()
-    d_out = torch.empty(n_out, dtype=torch.int64, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    head = measure(args.workload, args, env, headline=True)
+    e2e = None if args.no_e2e else e2e_legs(args, env)
+    cpu = None
+    cli = None
+    if rank == 0 and world == 1:
+        if not args.no_cpu:
+            cpu = cpu_baseline_record(args, env)
+        if not args.no_cli:
+            cli = cli_e2e(args, env)
+    K = env.pop("keep")
+    K["ses"].close()
+    K["idx"].close()
+    del K
+    torch.cuda.empty_cache()
 
-    def step():
-        ses.query_device(d_a.data_ptr(), d_off.data_ptr(), n_reads, a.size, mode, d_out.data_ptr(), n_out, stream)
-
-    stats = ses.query_device_counted(d_a.data_ptr(), d_off.data_ptr(), n_reads, a.size, mode, d_out.data_ptr(), n_out, stream)
-    launches_per_step = stats.kernel_launches
-    hits_gpu = int((d_out >= 0).sum().item())
-    assert stats.lookups == n_out and stats.hits == hits_gpu
-    # spot parity inside the bench: first reads against the oracle (checker only, outside any timed region)
-    if rank == 0:
-        import oracle
-        m = min(2000, n_reads)
-        want = oracle.OracleIndex(path).query_batch(a[: m * L], off[: m + 1], streaming=w["streaming"])
-        got = d_out[: want.size].cpu().numpy()
-        assert np.array_equal(got, want), "GPU output differs from the oracle"
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    ses.set_timing(True)
-    walk_ms, prep_ms = [], []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    S.launch_count(reset=True)
-    barrier()
-    torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            step()
-            p_ms, w_ms = ses.last_timing()
-            prep_ms.append(p_ms)
-            walk_ms.append(w_ms)
-        e1.record()
-        torch.cuda.synchronize()
-        barrier()
-    gpu_launches = S.launch_count()
-    ses.set_timing(False)
-    ms_total = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = world * n_out / (ms_per_step * 1e-3)
-
-    # ------------------------------------------------------------------ e2e through the host-buffer C-ABI call
-    e2e = None
-    if not args.no_e2e:
-        chunk_bases = min(args.e2e_chunk_bases, a.size)
-        ses_h = S.Session(idx, chunk_bases, chunk_bases // max(1, L - 2) + 16)
-        h_a, h_off, h_out = S.pinned_empty(a.size, np.uint8), S.pinned_empty(off.size, np.int64), S.pinned_empty(n_out, np.int64)
-        h_a[:], h_off[:] = a, off
-        ses_h.query_host(h_a, h_off, mode, out=h_out)  # warm-up (allocates the pipeline slots)
-        assert np.array_equal(h_out[: 120 * 50], d_out[: 120 * 50].cpu().numpy())
-        barrier()
-        n_e2e = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            ses_h.query_host(h_a, h_off, mode, out=h_out)
-        sec = (time.perf_counter() - t0) / n_e2e
-        if dist is not None:
-            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sec = float(t.item())
-        e2e = {"value": world * n_out / sec, "unit": "lookups/s", "h2d_bytes_per_step": int(a.nbytes + off.nbytes),
-               "d2h_bytes_per_step": int(n_out * 8), "ms_per_step": sec * 1e3, "steps": n_e2e,
-               "api": "sbwt_gpu_query_host (pinned host buffers, int64 results: what SBWT::streaming_search returns)",
-               "widen_threads": ses_h.widen_threads(), "host_threads": os.cpu_count()}
-        sparse_wire = ses_h.widen_threads() > 0 and os.environ.get("SBWT_B200_WIRE", "sparse") != "dense"
-        sparse_bytes = int(n_out // 8 + 4 * hits_gpu + n_out // 1024)  # hit masks + the hits + block bases
-        if sparse_wire:
-            e2e["result_wire_format"] = ("sparse: one hit bit per result + the hits only (int32) cross PCIe; host threads rebuild the caller's "
-                                         "int64 array (host_widen.hpp; SBWT_B200_WIRE=dense sends every result as int32 instead)")
-            e2e["d2h_bytes_per_step"] = sparse_bytes
-        elif ses_h.widen_threads() > 0:
-            e2e["result_wire_format"] = ("dense: int32 over PCIe, sign-extended into the caller's int64 array by host threads "
-                                         "(host_widen.hpp; SBWT_B200_WIDEN_THREADS, default = hardware threads / visible GPUs, <= 8)")
-            e2e["d2h_bytes_per_step"] = int(n_out * 4)
-        else:
-            e2e["result_wire_format"] = "int64 over PCIe"
-
-        def timed_leg(session, fn_name, out_buf):
-            getattr(session, fn_name)(h_a, h_off, mode, out=out_buf)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(n_e2e):
-                getattr(session, fn_name)(h_a, h_off, mode, out=out_buf)
-            s_ = (time.perf_counter() - t0) / n_e2e
-            if dist is not None:
-                t_ = torch.tensor([s_], device="cuda", dtype=torch.float64)
-                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-                s_ = float(t_.item())
-            return s_
-
-        if ses_h.widen_threads() > 0 and world == 1:
-            # the same call with the int64 values themselves crossing PCIe (no host threads involved)
-            prev_env = os.environ.get("SBWT_B200_WIDEN_THREADS")
-            os.environ["SBWT_B200_WIDEN_THREADS"] = "0"
-            ses_d = S.Session(idx, chunk_bases, chunk_bases // max(1, L - 2) + 16)
-            h_out[:4096] = -7
-            sec_d = timed_leg(ses_d, "query_host", h_out)
-            os.environ.pop("SBWT_B200_WIDEN_THREADS")
-            if prev_env is not None:
-                os.environ["SBWT_B200_WIDEN_THREADS"] = prev_env
-            assert np.array_equal(h_out[: 120 * 50], d_out[: 120 * 50].cpu().numpy())
-            e2e["int64_over_pcie"] = {"value": world * n_out / sec_d, "unit": "lookups/s", "d2h_bytes_per_step": int(n_out * 8),
-                                      "ms_per_step": sec_d * 1e3, "api": "sbwt_gpu_query_host with SBWT_B200_WIDEN_THREADS=0"}
-            ses_d.close()
-        if idx.n_nodes < (1 << 31) and world == 1:
-            # the same call with int32 results (same values; half the PCIe bytes of the result copy, which bounds e2e)
-            h_out32 = S.pinned_empty(n_out, np.int32)
-            ses_h.query_host_i32(h_a, h_off, mode, out=h_out32)
-            assert np.array_equal(h_out32[: 120 * 50].astype(np.int64), h_out[: 120 * 50])
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(n_e2e):
-                ses_h.query_host_i32(h_a, h_off, mode, out=h_out32)
-            sec32 = (time.perf_counter() - t0) / n_e2e
-            if dist is not None:
-                t = torch.tensor([sec32], device="cuda", dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                sec32 = float(t.item())
-            e2e["int32_results"] = {"value": world * n_out / sec32, "unit": "lookups/s", "d2h_bytes_per_step": sparse_bytes if sparse_wire else int(n_out * 4),
-                                    "ms_per_step": sec32 * 1e3, "api": "sbwt_gpu_query_host_i32"}
-            del h_out32
-        ses_h.close()
-
-    # the same kernel with the search table of round r01a..r01m (10 characters): more dependent sector reads per lookup,
-    # slower per lookup, but a higher sector rate -- reported next to the headline so the two can be told apart
-    alt = None
-    if world == 1 and idx.table_length > 10 and idx.precalc_k <= 10:
-        tp_default = idx.table_length
+    legs = DEFAULT_LEGS.get(args.workload, []) if args.legs is None else ([] if args.legs in ("none", "") else args.legs.split(","))
+    others = {}
+    for name in legs:
+        if name == args.workload:
+            continue
         try:
-            idx.set_table_length(10)
-            st10 = ses.query_device_counted(d_a.data_ptr(), d_off.data_ptr(), n_reads, a.size, mode, d_out.data_ptr(), n_out, stream)
-            ses.set_timing(True)
-            t10 = []
-            for _ in range(3 + min(args.steps, 10)):
-                step()
-                t10.append(ses.last_timing()[1])
-            alt = {"table_length": 10, "kernel_ms": float(np.mean(t10[3:])), "algorithmic_sectors_per_step": int(st10.index_sectors),
-                   "rank_ops_per_step": int(st10.rank_ops)}
-        except Exception as e:  # informational leg: never let it take the bench line down
-            log(f"shorter-table leg skipped: {e}")
-            alt = None
-        finally:
-            ses.set_timing(False)
-            idx.set_table_length(tp_default)
+            others[name] = measure(name, args, env, headline=False)
+        except SystemExit:
+            raise
+        except Exception as e:  # an attached leg never takes the headline line down
+            log(f"workload {name} failed: {e}")
+            others[name] = {"error": str(e)}
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
-    w_ms = float(np.mean(walk_ms))
-    sector_bytes = stats.index_sectors * 32
-    achieved = sector_bytes / (w_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                # DRAM bytes actually moved per launch (ncu) / this run's kernel time / peak: how much of HBM the kernel uses
-                "traffic_frac": (traffic / (w_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "kernel": "walk2_kernel",
-                "kernel_ms": w_ms, "kernel_share_of_step": w_ms / ms_per_step, "prep_ms": float(np.mean(prep_ms)),
-                "algorithmic_sectors_per_step": stats.index_sectors, "sectors_per_s": stats.index_sectors / (w_ms * 1e-3),
-                "rank_ops_per_step": stats.rank_ops, "rank_ops_per_s": stats.rank_ops / (w_ms * 1e-3),
-                "nominal_frac": stats.rank_ops * 32 / (w_ms * 1e-3) / 1e9 / peak,
-                "table_length": int(idx.table_length),
-                # sector bytes + the bytes the walk must also move: 8 B per result written, the packed reads and work items read
-                "io_bytes_per_step": int(n_out * 8 + a.size * 3 // 8 + n_reads * 16),
-                "frac_with_io": (sector_bytes + n_out * 8 + a.size * 3 // 8 + n_reads * 16) / (w_ms * 1e-3) / 1e9 / peak}
-    if alt:
-        alt["achieved"] = alt["algorithmic_sectors_per_step"] * 32 / (alt["kernel_ms"] * 1e-3) / 1e9
-        alt["frac"] = alt["achieved"] / peak
-        alt["lookups_per_s_kernel"] = n_out / (alt["kernel_ms"] * 1e-3)
-        alt["note"] = ("same kernel, shorter search table: each from-scratch search does 3 more dependent interval steps (more sector reads, "
-                       "higher sector rate, fewer lookups/s); the default table trades sector rate for lookups/s")
-        roofline["shorter_table"] = alt
-    if not args.no_probe:
-        try:
-            dram = S.sector_probe(local_rank, 8 << 30, 1 << 28, 32)
-            l2 = S.sector_probe(local_rank, 48 << 20, 1 << 28, 32)
-            # the structure the walk reads at random on every step: the rank sectors in use (a row of the search table is read
-            # once per from-scratch search and is not part of this buffer)
-            hot = 32 * (idx.n_nodes // 96 + 1) if (idx.compact_layout[0] and w["streaming"]) else 128 * (idx.n_nodes // 224 + 1)
-            same = S.sector_probe(local_rank, max(1 << 20, hot), 1 << 28, 32)
-            roofline["random_sector_ceiling"] = {"dram_sectors_per_s": dram, "l2_sectors_per_s": l2, "index_sized_buffer_sectors_per_s": same,
-                                                 "frac_of_index_sized_ceiling": roofline["sectors_per_s"] / same,
-                                                 "index_sized_buffer_bytes": int(hot),
-                                                 "how": "sbwt_gpu_sector_probe: 2^28 independent uniformly random 32-byte loads over 8 GiB / 48 MiB / a buffer the size of the rank sectors in use",
-                                                 "note": "an L2 miss moves a whole 128-byte line (4 sectors) from HBM whatever cudaLimitMaxL2FetchGranularity says, so "
-                                                         "the DRAM figure x 128 B is ~94 % of the HBM copy peak; ~62 MB of L2 are usable for randomly read data "
-                                                         "(profiles/r01g_l2_capacity.txt)"}
-        except Exception as e:  # the probe is informational
-            roofline["random_sector_ceiling"] = {"error": str(e)}
-
-    cpu = None
-    if not args.no_cpu and world == 1:
-        r = cpu_reference(path, reads, w["streaming"])
-        cpu = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
-
-    line = {"metric": "kmer_lookups_per_s", "value": value, "unit": "lookups/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int64", "data": "synthetic", "config": config, "clocks": clk.summary(), "e2e": e2e,
-            "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step), "roofline": roofline, "cpu_baseline": cpu,
-            "lookups_per_step_per_gpu": int(n_out), "hit_rate": hits_gpu / n_out, "index_device_bytes": int(idx.device_bytes),
-            "n_nodes": int(idx.n_nodes),
-            "index_layout": ({"kind": "compact one-hot csectors (96 columns x 4 characters per 32-byte sector) + classic sectors for flagged blocks",
-                              "flagged_block_fraction": idx.compact_layout[1], "hot_bytes": int(32 * (idx.n_nodes // 96 + 1))}
-                             if (idx.compact_layout[0] and w["streaming"]) else
-                             {"kind": "classic sectors (224 columns x 1 character per 32-byte sector)",
-                              "flagged_block_fraction": idx.compact_layout[1], "hot_bytes": int(128 * (idx.n_nodes // 224 + 1))})}
+    rf = head["roofline"]
+    if env.get("ceilings"):
+        rf["random_sector_ceiling"] = {"dram_sectors_per_s": env["ceilings"]["dram"], "l2_sectors_per_s": env["ceilings"]["l2"],
+                                       "how": "sbwt_gpu_sector_probe: 2^28 independent uniformly random 32-byte loads over 8 GiB / 48 MiB",
+                                       "note": "an L2 miss moves a whole 128-byte line from HBM, so the DRAM figure x 128 B is ~92 % of the HBM copy peak; the L2 figure is one "
+                                               "divergent 32-byte request per SM and clock (148 SMs x 1.965 GHz = 291 G/s): the SM's request rate, not L2 bandwidth"}
+    line = {"metric": "kmer_lookups_per_s", "value": head["value"], "unit": "lookups/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic", "config": config, "clocks": head["clocks"], "e2e": e2e,
+            "gpu_launches": head["gpu_launches"], "launches_per_step": head["launches_per_step"], "roofline": rf, "cpu_baseline": cpu,
+            "parity": head["parity"], "cli_e2e": cli,
+            "lookups_per_step_per_gpu": head["lookups_per_step_per_gpu"], "hit_rate": head["hit_rate"], "index_device_bytes": head["index_device_bytes"],
+            "n_nodes": head["n_nodes"], "index_layout": head["index_layout"], "l2_set_aside_bytes": head["l2_set_aside_bytes"],
+            "library_sha256_12": env["lib_sha"], "workloads": others}
+    if cpu is None and world == 1 and head.get("cpu_reference"):
+        line["cpu_baseline"] = dict(head["cpu_reference"], unit="lookups/s", cpu_model=cpu_model())
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

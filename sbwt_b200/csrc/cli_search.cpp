@@ -15,6 +15,9 @@
 //   sbwt_search [search] -o <out | list.txt> -i <index.sbwt> -q <reads.(fa|fq)[.gz] | list.txt> [-z]
 #include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <deque>
+#include <condition_variable>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -164,14 +167,31 @@ struct Options {
 };
 
 // run_file (sbwt_search.cpp:93-105): streaming search when the index supports it, else search() per k-mer.
-static int string_sink(void* user, const char* text, int64_t n_bytes) {
-    static_cast<string*>(user)->append(text, (size_t)n_bytes);
+// One batch over several devices (--devices): the reads are cut into contiguous ranges of (almost) equal total bases,
+// one host thread per replica produces the text of its range, and the ranges are written in order. Nothing is exchanged
+// between the devices. The text is STREAMED: every replica hands its pieces to a bounded
+// queue, the calling thread writes the queue of range 0 while it fills, then range 1, ...; a replica whose queue is full
+// waits (its pipeline stalls), so the memory held is bounded whatever the batch size.
+struct PieceQueue {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<string> pieces;
+    size_t bytes = 0;
+    bool done = false, abandoned = false;
+    static constexpr size_t kCap = (size_t)256 << 20;
+};
+
+static int queue_sink(void* user, const char* text, int64_t n_bytes) {
+    PieceQueue* q = static_cast<PieceQueue*>(user);
+    std::unique_lock<std::mutex> g(q->mu);
+    q->cv.wait(g, [&] { return q->bytes < PieceQueue::kCap || q->abandoned; });
+    if (q->abandoned) return 1;
+    q->pieces.emplace_back(text, (size_t)n_bytes);
+    q->bytes += (size_t)n_bytes;
+    q->cv.notify_all();
     return 0;
 }
 
-// One batch over several devices (--devices): the reads are cut into contiguous ranges of (almost) equal total bases,
-// one host thread per replica produces the text of its range, and the ranges are written in order. Nothing is exchanged
-// between the devices.
 static int64_t query_batch_multi(const vector<const sbwt::plain_matrix_sbwt_t*>& replicas, const vector<char>& ascii,
                                  const vector<int64_t>& offsets, int64_t n, int mode, Writer& writer) {
     const size_t D = replicas.size();
@@ -183,26 +203,51 @@ static int64_t query_batch_multi(const vector<const sbwt::plain_matrix_sbwt_t*>&
         const int64_t c = std::lower_bound(offsets.begin(), offsets.begin() + n + 1, target) - offsets.begin();
         cuts[d] = std::min<int64_t>(n, std::max<int64_t>(cuts[d - 1], c));
     }
-    vector<string> text(D);
+    vector<PieceQueue> queues(D);
     vector<int64_t> lookups(D, 0);
     vector<std::exception_ptr> errors(D);
     auto work = [&](size_t d) {
         try {
             const int64_t r0 = cuts[d], nr = cuts[d + 1] - r0;
             if (nr > 0)
-                lookups[d] = replicas[d]->query_batch_text(ascii.data(), offsets.data() + r0, nr, mode, SBWT_GPU_CASE_UPPER, string_sink, &text[d]);
+                lookups[d] = replicas[d]->query_batch_text(ascii.data(), offsets.data() + r0, nr, mode, SBWT_GPU_CASE_UPPER, queue_sink, &queues[d]);
         } catch (...) { errors[d] = std::current_exception(); }
+        std::lock_guard<std::mutex> g(queues[d].mu);
+        queues[d].done = true;
+        queues[d].cv.notify_all();
     };
     vector<std::thread> th;
-    for (size_t d = 1; d < D; d++) th.emplace_back(work, d);
-    work(0);
-    for (auto& t : th) t.join();
-    int64_t n_lookups = 0;
-    for (size_t d = 0; d < D; d++) {
-        if (errors[d]) std::rethrow_exception(errors[d]);
-        writer.write(text[d].data(), text[d].size());
-        n_lookups += lookups[d];
+    for (size_t d = 0; d < D; d++) th.emplace_back(work, d);
+    std::exception_ptr write_error;
+    for (size_t d = 0; d < D; d++) { // in order: everything of range d before anything of range d + 1
+        PieceQueue& q = queues[d];
+        for (;;) {
+            string piece;
+            {
+                std::unique_lock<std::mutex> g(q.mu);
+                q.cv.wait(g, [&] { return !q.pieces.empty() || q.done; });
+                if (q.pieces.empty()) break;
+                piece.swap(q.pieces.front());
+                q.pieces.pop_front();
+                q.bytes -= piece.size();
+                q.cv.notify_all();
+            }
+            if (!write_error && !errors[d]) {
+                try { writer.write(piece.data(), piece.size()); }
+                catch (...) { write_error = std::current_exception(); }
+            }
+            if (write_error)
+                for (PieceQueue& x : queues) { std::lock_guard<std::mutex> g(x.mu); x.abandoned = true; x.cv.notify_all(); }
+        }
+        if (errors[d] && !write_error) { // a failed range: nothing after it is written (what was before it already is)
+            write_error = errors[d];
+            for (PieceQueue& x : queues) { std::lock_guard<std::mutex> g(x.mu); x.abandoned = true; x.cv.notify_all(); }
+        }
     }
+    for (auto& t : th) t.join();
+    if (write_error) std::rethrow_exception(write_error);
+    int64_t n_lookups = 0;
+    for (size_t d = 0; d < D; d++) n_lookups += lookups[d];
     return n_lookups;
 }
 

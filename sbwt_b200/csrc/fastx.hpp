@@ -12,6 +12,7 @@
 #pragma once
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -236,9 +237,83 @@ class ParallelFastxReader {
     std::vector<char> zbuf;
     bool z_eof = false;
     bool all_here = true; // everything up to the end of the input is in [data, data + size)
+    // BGZF input (bgzip, htslib: gzip members of at most 64 KiB whose header carries the member's size in a 'BC' extra
+    // field): member boundaries are known without inflating, so the members are inflated in parallel. A plain gzip
+    // stream has no such index and is inflated by one thread ahead of the parallel parser.
+    const unsigned char* zmap = nullptr;
+    size_t zmap_size = 0, zmap_pos = 0;
+    bool bgzf = false;
+
+    // size of the BGZF member at `at` (0 = not a BGZF member header)
+    size_t bgzf_member_size(size_t at) const {
+        if (at + 18 > zmap_size) return 0;
+        const unsigned char* h = zmap + at;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+        const size_t xlen = h[10] | (h[11] << 8);
+        if (at + 12 + xlen > zmap_size) return 0;
+        for (size_t x = 12; x + 4 <= 12 + xlen;) {
+            const size_t slen = h[x + 2] | (h[x + 3] << 8);
+            if (h[x] == 'B' && h[x + 1] == 'C' && slen == 2 && x + 6 <= 12 + xlen) {
+                const size_t bsize = (size_t)(h[x + 4] | (h[x + 5] << 8)) + 1;
+                return (bsize >= 12 + xlen + 8 && at + bsize <= zmap_size) ? bsize : 0;
+            }
+            x += 4 + slen;
+        }
+        return 0;
+    }
+
+    void bgzf_fill(size_t want) {
+        if (cur > 0 && cur == size) { size = 0; cur = 0; }
+        if (cur > ((size_t)64 << 20)) {
+            memmove(zbuf.data(), zbuf.data() + cur, size - cur);
+            size -= cur;
+            cur = 0;
+        }
+        while (!z_eof && size - cur < want) {
+            // the next members, up to ~64 MB of text: headers are hopped over, the sizes come from each member's ISIZE
+            struct Member { size_t at, len, out, out_len, hdr; };
+            std::vector<Member> ms;
+            size_t out_total = 0;
+            while (zmap_pos < zmap_size && out_total < ((size_t)64 << 20)) {
+                const size_t len = bgzf_member_size(zmap_pos);
+                if (!len) throw std::runtime_error("Error reading gzip file " + filename);
+                const unsigned char* h = zmap + zmap_pos;
+                const size_t isize = (size_t)h[len - 4] | ((size_t)h[len - 3] << 8) | ((size_t)h[len - 2] << 16) | ((size_t)h[len - 1] << 24);
+                ms.push_back(Member{zmap_pos, len, out_total, isize, 12 + (size_t)(h[10] | (h[11] << 8))});
+                out_total += isize;
+                zmap_pos += len;
+            }
+            if (zmap_pos >= zmap_size) z_eof = true;
+            if (zbuf.size() < size + out_total) zbuf.resize(std::max(zbuf.size() * 2, size + out_total));
+            char* base = zbuf.data() + size;
+            const unsigned char* zm = zmap;
+            std::atomic<bool> bad{false};
+            const Member* mp = ms.data();
+            parallel_for(ms.size(), [=, &bad](size_t a, size_t b, size_t) {
+                for (size_t i = a; i < b; i++) {
+                    if (mp[i].out_len == 0) continue; // (bgzip's end-of-file marker is an empty member)
+                    z_stream z;
+                    memset(&z, 0, sizeof z);
+                    if (inflateInit2(&z, -15) != Z_OK) { bad = true; return; } // raw deflate: the member's header was parsed above
+                    z.next_in = (Bytef*)(zm + mp[i].at + mp[i].hdr);
+                    z.avail_in = (uInt)(mp[i].len - mp[i].hdr - 8);
+                    z.next_out = (Bytef*)(base + mp[i].out);
+                    z.avail_out = (uInt)mp[i].out_len;
+                    const int rc = inflate(&z, Z_FINISH);
+                    if (rc != Z_STREAM_END || z.avail_out != 0) bad = true;
+                    inflateEnd(&z);
+                }
+            });
+            if (bad) throw std::runtime_error("Error reading gzip file " + filename);
+            size += out_total;
+        }
+        data = zbuf.data();
+        all_here = z_eof;
+    }
 
     // make at least `want` bytes after `cur` available (or reach the end of the stream)
     void z_fill(size_t want) {
+        if (bgzf) { bgzf_fill(want); return; }
         if (!gzf) return;
         if (cur > 0 && cur == size) { size = 0; cur = 0; }
         if (cur > ((size_t)64 << 20)) { // drop what has been consumed
@@ -321,9 +396,23 @@ public:
         const FileFormat ff = figure_out_file_format(filename);
         format = ff.format;
         if (ff.gzipped) {
-            gzf = gzopen(filename.c_str(), "rb");
-            if (!gzf) throw std::runtime_error("Error opening file " + filename);
-            gzbuffer(gzf, 1 << 20);
+            fd = open(filename.c_str(), O_RDONLY);
+            struct stat zst;
+            if (fd >= 0 && fstat(fd, &zst) == 0 && zst.st_size >= 28) {
+                void* p = mmap(nullptr, (size_t)zst.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (p != MAP_FAILED) {
+                    zmap = (const unsigned char*)p;
+                    zmap_size = (size_t)zst.st_size;
+                    bgzf = bgzf_member_size(0) != 0;
+                    if (!bgzf) { munmap(p, zmap_size); zmap = nullptr; }
+                }
+            }
+            if (!bgzf) {
+                if (fd >= 0) { close(fd); fd = -1; }
+                gzf = gzopen(filename.c_str(), "rb");
+                if (!gzf) throw std::runtime_error("Error opening file " + filename);
+                gzbuffer(gzf, 1 << 20);
+            }
             z_fill(1);
             const char c = size ? data[0] : 0; // read_first_char_and_sanity_check, SeqIO.hh:178-189
             if (format == SeqFormat::FASTA && c != '>') throw std::runtime_error("ERROR: FASTA file " + filename + " does not start with '>'");
@@ -356,6 +445,7 @@ public:
     ~ParallelFastxReader() {
         serial.reset();
         if (gzf) gzclose(gzf);
+        else if (zmap) munmap((void*)zmap, zmap_size);
         else if (data) munmap((void*)data, size);
         if (fd >= 0) close(fd);
     }
@@ -431,6 +521,7 @@ public:
             window *= 2; // the window ended before the batch was full
         }
         if (anomaly) {
+            if (bgzf) z_fill((size_t)1 << 62); // the serial parser continues in memory: inflate the rest of the members first
             serial.reset(new FastxReader(filename, format, data + cur, size - cur, gzf)); // (gzip: continues with the rest of the stream)
             return from_serial(max_bases, max_reads, ascii, offsets);
         }

@@ -26,6 +26,21 @@ def both(exe, path, max_bases, max_reads, threads):
     return a, b
 
 
+def write_bgzf(path, data, block=60_000):
+    """bgzip's container: gzip members of < 64 KiB whose header carries the member size in a 'BC' extra field, then the
+    empty end-of-file member."""
+    import struct
+    import zlib
+    with open(path, "wb") as f:
+        for a in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if a is None else data[a:a + block]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            body = c.compress(chunk) + c.flush()
+            bsize = 12 + 6 + len(body) + 8
+            f.write(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1))
+            f.write(body + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+
 def rand_seq(rng, n):
     return bytes(np.frombuffer(b"ACGTNacgt", dtype=np.uint8)[rng.integers(0, 9, size=n)])
 
@@ -65,12 +80,17 @@ def test_wellformed_files_give_identical_batches(exe, tmp_path, kind):
     open(path, "wb").write(data)
     with gzip.open(path + ".gz", "wb", compresslevel=1) as f:  # the same bytes through the inflate-ahead path
         f.write(data)
+    bg = str(tmp_path / ("b.fq.gz" if kind.startswith("fq") else "b.fna.gz"))  # ... and through the member-parallel BGZF path
+    write_bgzf(bg, data, block=7_000)
+    assert gzip.open(bg).read() == data
     for max_bases, max_reads, threads in [(1 << 30, 1 << 30, 4), (5000, 1 << 30, 3), (1, 1 << 30, 2), (1 << 30, 7, 8), (100_000, 100, 1), (333, 5, 5)]:
         a, b = both(exe, path, max_bases, max_reads, threads)
         assert not a.startswith("ERROR"), a
         assert a == b, (kind, max_bases, max_reads, threads)
         az, bz = both(exe, path + ".gz", max_bases, max_reads, threads)
         assert az == a and bz == a, (kind, "gz", max_bases, max_reads, threads)
+        ag, bg_ = both(exe, bg, max_bases, max_reads, threads)
+        assert ag == a and bg_ == a, (kind, "bgzf", max_bases, max_reads, threads)
 
 
 def test_long_reads_exceed_the_scan_window(exe, tmp_path):
@@ -126,6 +146,10 @@ def test_malformed_files_fail_or_parse_exactly_like_the_serial_reader(exe, tmp_p
             assert a == b, (name, a, b)
             az, bz = both(exe, path + ".gz", max_bases, max_reads, threads)
             assert az == bz == a.replace(name, name + ".gz"), (name, "gz", az, bz, a)
+            bgp = str(tmp_path / ("bg_" + name + ".gz"))
+            write_bgzf(bgp, prefix + BAD[name], block=25)
+            ag, bg_ = both(exe, bgp, max_bases, max_reads, threads)
+            assert ag == bg_ == a.replace(name, "bg_" + name + ".gz"), (name, "bgzf", ag, bg_, a)
 
 
 def test_gzip_input_large_enough_to_slide_the_buffer(exe, tmp_path):
