@@ -64,6 +64,8 @@ WORKLOADS = {
                ref=("pangenome", 400, 5_000_000, 44), k=63, streaming=True, rc=True, reads=10_000_000),
     "c2q": dict(desc="experiment: a quarter-size configs[1] reference (25 Mbp) -- the index certainly fits in L2", ref=("contigs", 25, 1_000_000, 42),
                 k=31, streaming=True, rc=False, reads=10_000_000),
+    "c2m": dict(desc="experiment: a 150 Mbp random reference -- csector64 (75 MB) no longer fits in L2, csector96 (50 MB) does", ref=("contigs", 150, 1_000_000, 42),
+                k=31, streaming=True, rc=False, reads=10_000_000),
     "tiny": dict(desc="smoke-sized: 2 Mbp random DNA, k=31, streaming", ref=("contigs", 2, 1_000_000, 42), k=31, streaming=True,
                  rc=False, reads=200_000),
 }
@@ -531,14 +533,17 @@ def cpu_baseline_record(args, env: dict) -> dict | None:
     variants = {"popcnt_all_cores": {key: best[key] for key in ("value", "cores", "seconds", "lookups")}}
     if best["kind"] == "reference" and not args.quick_cpu:
         n_all, n_one = min(reads.shape[0], 2_000_000), min(reads.shape[0], 150_000)
-        r = ref_timed(path, reads[:n_all], streaming, threads, popcnt=False)
-        variants["default_all_cores"] = {key: r[key] for key in ("value", "cores", "seconds", "lookups")}
+        r_all = ref_timed(path, reads[:n_all], streaming, threads, popcnt=False)
+        variants["default_all_cores"] = {key: r_all[key] for key in ("value", "cores", "seconds", "lookups")}
         for key, pc in (("default_1_core", False), ("popcnt_1_core", True)):
             r = ref_timed(path, reads[:n_one], streaming, 1, popcnt=pc)
             variants[key] = {k_: r[k_] for k_ in ("value", "cores", "seconds", "lookups")}
         variants["processes_all_cores_with_io"] = ref_processes(path, reads[: min(reads.shape[0], 1_000_000)], threads)
-    return {"value": best["value"], "unit": "lookups/s", "cores": best["cores"], "kind": best["kind"], "sample": best["sample"],
-            "build": best["build"], "cpu_model": cpu_model(), "host_threads": threads, "variants": variants}
+    head = best
+    if "default_all_cores" in variants:  # the headline figure is the STOCK build's (what `--impl reference` times); the faster popcount build is a variant
+        head = dict(r_all)
+    return {"value": head["value"], "unit": "lookups/s", "cores": head["cores"], "kind": head["kind"], "sample": head["sample"],
+            "build": head["build"], "cpu_model": cpu_model(), "host_threads": threads, "variants": variants}
 
 
 def main() -> None:
@@ -584,7 +589,7 @@ def main() -> None:
         reads = synth.sample_reads(ref, n_s, L, 0.5, seed=43, both_strands=w["rc"])
         best = None
         for i in range(max(1, args.warmup) + max(1, args.steps)):
-            r = ref_timed(path, reads, w["streaming"], threads, popcnt=True)  # (the faster of the two builds: favours the reference)
+            r = ref_timed(path, reads, w["streaming"], threads, popcnt=False)  # (the stock build: the reference's CMakeLists.txt passes no -march flag)
             if i >= max(1, args.warmup) and (best is None or r["value"] > best["value"]):
                 best = r
         line = {"impl": "reference", "metric": "kmer_lookups_per_s", "value": best["value"], "unit": "lookups/s", "n_gpus": args.gpus,
