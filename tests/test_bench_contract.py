@@ -42,3 +42,31 @@ def test_our_arm_refuses_to_run_without_a_gpu():
         return
     r = run_bench("--workload", "tiny", "--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_our_arm_prints_the_contract_line_with_parity_and_legs():
+    """A small run of our arm on the GPU: the contract keys, the roofline / parity / e2e objects, and an attached workload."""
+    r = run_bench("--workload", "tiny", "--legs", "tiny,c2q", "--reads", "100000", "--steps", "3", "--warmup", "3", "--quick-cpu", "--no-sharded")
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity", "workloads"):
+        assert key in d, key
+    assert d["metric"] == "kmer_lookups_per_s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] > 0 and d["value"] > 0
+    rf = d["roofline"]
+    assert rf["bound"] in ("hbm", "l2-latency") and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["frac_of_level_ceiling"] > 0 and "frac_with_io" not in rf
+    p = d["parity"]
+    assert p["checker"] == "sbwt_ref" and p["reads"] == 100000 and all(p[k_] for k_ in ("lookups_match", "hits_match", "checksum_match", "weighted_checksum_match"))
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["hits_only"]["value"] > 0 and e["bitmap_only"]["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["cpu_model"]
+    assert d["cli_e2e"]["plain"]["lookups"] == d["lookups_per_step_per_gpu"]
+    w = d["workloads"]["c2q"]
+    assert w["value"] > 0 and w["parity"]["weighted_checksum_match"] and w["roofline"]["kernel_ms"] > 0
