@@ -128,8 +128,11 @@ private:
         if (!session || bases > session_bases || reads > session_reads) {
             if (session) sbwt_gpu_session_destroy(session);
             session = nullptr;
-            session_bases = std::max<int64_t>(std::max<int64_t>(bases, session_bases), 1 << 20);
-            session_reads = std::max<int64_t>(std::max<int64_t>(reads, session_reads), 1 << 14);
+            // capacities grow in powers of two: batches of slightly different sizes (variable-length reads, --devices slices)
+            // must not free and reallocate several GB of device and pinned buffers inside the query path
+            auto pow2 = [](int64_t x) { int64_t p = 1; while (p < x) p <<= 1; return p; };
+            session_bases = std::min<int64_t>(std::max<int64_t>(pow2(std::max<int64_t>(bases, session_bases)), 1 << 20), (int64_t)0xFFFF0000ll);
+            session_reads = std::min<int64_t>(std::max<int64_t>(pow2(std::max<int64_t>(reads, session_reads)), 1 << 14), (int64_t)0x7FFF0000ll);
             gpu_check(sbwt_gpu_session_create(dev, session_bases, session_reads, &session));
         }
         return session;

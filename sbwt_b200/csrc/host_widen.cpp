@@ -2,6 +2,9 @@
 // runs inside a cudaLaunchHostFunc callback, where CUDA API calls are not allowed.
 #include "host_widen.hpp"
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -165,8 +168,15 @@ void expand_sparse_i32(const uint32_t* masks, const uint32_t* block_base, const 
     expand_sparse_t<int32_t>(masks, block_base, packed, n, b0, b1, dst);
 }
 
-WidenPool::WidenPool(int threads) {
+WidenPool::WidenPool(int threads, const std::vector<int>& cpus) {
     for (int t = 0; t < threads; t++) workers_.emplace_back([this] { run(); });
+    if (!cpus.empty()) { // keep the pool on the NUMA node of its GPU: the pinned buffers it reads were allocated from there
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        for (int c : cpus)
+            if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
+        for (std::thread& w : workers_) pthread_setaffinity_np(w.native_handle(), sizeof set, &set); // (best effort)
+    }
 }
 
 WidenPool::~WidenPool() {

@@ -27,7 +27,8 @@ struct WidenTicket {
 
 class WidenPool {
 public:
-    explicit WidenPool(int threads);
+    // cpus: logical CPUs the workers may run on (empty = anywhere)
+    explicit WidenPool(int threads, const std::vector<int>& cpus = std::vector<int>());
     ~WidenPool();
     int threads() const { return (int)workers_.size(); }
     // dst[i] = src[i] for i < n, split over the pool; returns at once. `t->pending` reaches 0 when done.

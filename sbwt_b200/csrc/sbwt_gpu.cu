@@ -2,6 +2,7 @@
 // kernel launches and the host<->device pipeline. No torch types, no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -231,6 +232,24 @@ extern "C" int64_t sbwt_gpu_count_outputs(const int64_t* off, int64_t n_reads, i
 
 extern "C" int sbwt_gpu_index_set_table_length(sbwt_gpu_index* ix, int tp);
 
+// The persisting-L2 limit is per device: it follows the largest request among the indexes alive on the device and is given
+// back (with the persisting lines) when the last of them goes.
+static std::mutex g_l2_mutex;
+static std::vector<sbwt_gpu_index*> g_l2_indexes;
+static void l2_set_aside_update(int device) { // (device is current)
+    std::lock_guard<std::mutex> lock(g_l2_mutex);
+    int64_t want = 0;
+    for (const sbwt_gpu_index* x : g_l2_indexes)
+        if (x->device == device) want = std::max(want, x->l2_set_aside);
+    size_t have = 0;
+    cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+    if ((int64_t)have != want) {
+        if (want == 0) cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want);
+    }
+    cudaGetLastError();
+}
+
 static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs, int64_t n_nodes, int64_t n_kmers,
                              int64_t k, const int64_t C[4], const int64_t* precalc, int64_t p, int device,
                              sbwt_gpu_index** out) {
@@ -242,6 +261,7 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     if (p < 0 || p > k || p > 14) return set_error("precalc length %lld is not supported (0 <= p <= min(k,14))", (long long)p);
     DeviceGuard guard(device);
     sbwt_gpu_index* ix = new sbwt_gpu_index();
+    { std::lock_guard<std::mutex> lock(g_l2_mutex); g_l2_indexes.push_back(ix); }
     auto fail = [&](int rc) { sbwt_gpu_index_destroy(ix); return rc; };
     ix->device = device;
     ix->n_nodes = n_nodes; ix->n_kmers = n_kmers; ix->k = k; ix->precalc_k = p;
@@ -417,11 +437,8 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
         const char* e = getenv("SBWT_B200_L2_SET_ASIDE_MB"); // 0 = never
         int64_t want = e ? (int64_t)atoi(e) << 20 : (cbytes <= ((int64_t)56 << 20) ? cbytes + ((int64_t)2 << 20) : 0);
-        want = std::min<int64_t>(want, max_persist);
-        size_t have = 0;
-        cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
-        if (want > (int64_t)have && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want) == cudaSuccess) ix->l2_set_aside = want;
-        cudaGetLastError();
+        ix->l2_set_aside = std::min<int64_t>(want, max_persist);
+        l2_set_aside_update(device);
     }
     if (ix->table_from_bits) { // (see launch_walk)
         int log4n = 0;
@@ -496,6 +513,11 @@ extern "C" void sbwt_gpu_index_destroy(sbwt_gpu_index* ix) {
     DeviceGuard guard(ix->device);
     cudaFree(ix->d_sectors); cudaFree(ix->d_sbbase); cudaFree(ix->d_precalc); cudaFree(ix->d_sgs); cudaFree(ix->d_table);
     cudaFree(ix->d_compact); cudaFree(ix->d_cbase); cudaFree(ix->d_scratch);
+    {
+        std::lock_guard<std::mutex> lock(g_l2_mutex);
+        g_l2_indexes.erase(std::remove(g_l2_indexes.begin(), g_l2_indexes.end(), ix), g_l2_indexes.end());
+    }
+    if (ix->l2_set_aside) l2_set_aside_update(ix->device);
     delete ix;
 }
 
@@ -1024,6 +1046,37 @@ static int widen_thread_count() {
     return t >= 4 ? t : 0;
 }
 
+// logical CPUs of the NUMA node the device hangs off (empty when the host has one node or the topology is not exposed):
+// /sys/bus/pci/devices/<bus id>/numa_node -> /sys/devices/system/node/node<N>/cpulist
+static std::vector<int> device_numa_cpus(int device) {
+    std::vector<int> cpus;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return cpus; }
+    for (char* p = bus; *p; p++) *p = (char)tolower(*p);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return cpus;
+    f = fopen("/sys/devices/system/node/node1/cpulist", "r"); // a single-node host needs no binding
+    if (!f) return cpus;
+    fclose(f);
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return cpus;
+    int a = 0, b = 0;
+    while (fscanf(f, "%d", &a) == 1) { // "0-15,32-47"
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') { if (fscanf(f, "%d", &b) != 1) b = a; ch = fgetc(f); }
+        for (int c = a; c <= b; c++) cpus.push_back(c);
+        if (ch != ',') break;
+    }
+    fclose(f);
+    return cpus;
+}
+
 // values per D2H piece of the 32-bit wire format (SBWT_B200_D2H_PIECE, in values). Default 64 Mi: a chunk of the
 // default size goes in one piece -- smaller pieces only added per-piece overhead on the measured host
 // (profiles/r01g_e2e_sweep.txt)
@@ -1092,7 +1145,7 @@ static int query_host_body(sbwt_gpu_session* s, const char* ascii, const int64_t
     bool sparse = false; // sparse wire format: hit masks + hits only (SBWT_B200_WIRE=dense turns it off)
     if (!ix->view.wide && ix->n_nodes < (1ll << 31)) {
         if (s->widen_threads < 0) s->widen_threads = widen_thread_count();
-        if (s->widen_threads > 0 && !s->widen_pool) s->widen_pool = new WidenPool(s->widen_threads);
+        if (s->widen_threads > 0 && !s->widen_pool) s->widen_pool = new WidenPool(s->widen_threads, device_numa_cpus(ix->device));
         widen = !out32 && s->widen_pool != nullptr;
         const char* we = getenv("SBWT_B200_WIRE");
         sparse = s->widen_pool != nullptr && !(we && strcmp(we, "dense") == 0);
