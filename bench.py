@@ -386,8 +386,8 @@ def measure(name: str, args, env: dict, headline: bool) -> dict:
                 "level_ceiling_sectors_per_s": ceil.get(level), "frac_of_level_ceiling": (sectors_per_s / ceil[level]) if ceil.get(level) else None,
                 "traffic": tr["bytes"] if tr else None,
                 "traffic_source": (f"profile constant, NOT measured in this run: dram__bytes_read + dram__bytes_write of one launch from {tr['source']} "
-                                   f"(library sha256 {tr.get('lib_sha256_12')}; this run's library {env['lib_sha']}"
-                                   + ("" if tr.get("lib_sha256_12") == env["lib_sha"] else ": DIFFERENT BINARY") + ")") if tr else None,
+                                   f"(kernel sources sha256 {tr.get('kernel_src_sha256_12')}; this run's {env['kernel_src_sha']}"
+                                   + ("" if tr.get("kernel_src_sha256_12") == env["kernel_src_sha"] else ": DIFFERENT KERNEL SOURCES") + ")") if tr else None,
                 "traffic_over_algorithmic": (tr["bytes"] / (stats.index_sectors * 32)) if tr else None}
     rec = {"workload": f"{name}: {w['desc']}", "value": value, "unit": "lookups/s", "ms_per_step": ms_per_step, "steps": steps,
            "lookups_per_step_per_gpu": int(n_out), "hit_rate": hits_gpu / max(1, n_out), "n_nodes": int(idx.n_nodes), "k": k,
@@ -622,7 +622,8 @@ def main() -> None:
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     env = {"rank": rank, "local_rank": local_rank, "world": world, "dist": dist, "barrier": barrier,
            "traffic": {k_: v for k_, v in (json.load(open(tp)) if os.path.exists(tp) else {}).items() if isinstance(v, dict) and "bytes" in v},
-           "lib_sha": hashlib.sha256(open(S.LIB_PATH, "rb").read()).hexdigest()[:12]}
+           "lib_sha": hashlib.sha256(open(S.LIB_PATH, "rb").read()).hexdigest()[:12],
+           "kernel_src_sha": hashlib.sha256(b"".join(open(os.path.join(ROOT, "sbwt_b200", "csrc", f), "rb").read() for f in ("walk_kernel.cuh", "device_index.cuh"))).hexdigest()[:12]}
     if not args.no_probe:
         try:  # the measured random-32-byte-gather ceilings the sector rates are quoted against
             env["ceilings"] = {"dram": S.sector_probe(local_rank, 8 << 30, 1 << 28, 32), "l2": S.sector_probe(local_rank, 48 << 20, 1 << 28, 32)}
