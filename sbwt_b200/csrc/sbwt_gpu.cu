@@ -23,7 +23,6 @@
 #include "query_kernels.cuh"
 #include "sbwt_file.hpp"
 #include "walk_kernel.cuh"
-#include "walk_passes.cuh"
 
 using namespace sbwt_b200;
 
@@ -86,7 +85,6 @@ struct sbwt_gpu_index {
     void* d_table = nullptr;
     int64_t table_bytes = 0;
     bool table_from_bits = true; // the file's table equals what the bit vectors imply, so any table length is admissible
-    bool use_passes = true;         // streaming batches run as passes over global work lists (walk_passes.cuh; SBWT_B200_PASSES=0: one persistent kernel)
     bool compact_in_search = false; // the per-k-mer search path also walks the compact layout (default: classic sectors)
     int64_t l2_set_aside = 0;       // bytes of L2 set aside for persisting (evict_last) lines by this index, 0 = none
     uint32_t probe_stride = 0;      // streaming walk: distance between the probes of a range of presumed misses (0 = none)
@@ -108,13 +106,6 @@ struct Scratch {
     WalkItem* items = nullptr;
     int64_t n_words = 0;        // u64 words allocated for codes (u32 words for invalid)
     unsigned long long* stats = nullptr;
-    // work lists of the multi-pass streaming walk (walk_passes.cuh), allocated by the first batch that uses them
-    int64_t list_cap = 0;
-    void* l_surv = nullptr;
-    uint4* l_ranges = nullptr;
-    WalkItem* l_fresh[2] = {nullptr, nullptr};
-    WalkItem* l_left = nullptr;
-    unsigned long long* l_n = nullptr;
 };
 
 struct HostSlot {
@@ -339,7 +330,6 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     int layout = kDefaultCompactLayout;
     if (const char* e = getenv("SBWT_B200_LAYOUT")) layout = strcmp(e, "c64") == 0 ? LAY_C64 : (strcmp(e, "c96") == 0 ? LAY_C96 : layout);
     if (const char* e = getenv("SBWT_B200_COMPACT_SEARCH")) ix->compact_in_search = atoi(e) > 0;
-    if (const char* e = getenv("SBWT_B200_PASSES")) ix->use_passes = atoi(e) > 0;
     if (compact_mode >= 2) ix->compact_in_search = true;
     const int ccols = layout == LAY_C64 ? kC64Cols : kCBlockCols;
     const int64_t n_cblocks = n_nodes / ccols + 1;
@@ -735,7 +725,6 @@ static void session_count(int delta); // sessions alive in this process (see wid
 static void scratch_free(Scratch& sc) {
     cudaFree(sc.codes); cudaFree(sc.invalid); cudaFree(sc.n_out); cudaFree(sc.n_win); cudaFree(sc.partials);
     cudaFree(sc.totals); cudaFree(sc.items); cudaFree(sc.stats);
-    cudaFree(sc.l_surv); cudaFree(sc.l_ranges); cudaFree(sc.l_fresh[0]); cudaFree(sc.l_fresh[1]); cudaFree(sc.l_left); cudaFree(sc.l_n);
     sc = Scratch();
 }
 
@@ -873,87 +862,8 @@ static cudaError_t launch_walk_t(const WalkParams& P, bool count, int sm_count, 
                  : launch_walk_tt<STREAMING, WIDE, false, false, KW>(P, sm_count, st);
 }
 
-// ---- the multi-pass streaming walk (walk_passes.cuh)
-constexpr int kPassRounds = 3; // first -> chain -> probe, this many times; what is left goes through walk_kernel
-
-template <typename K>
-static cudaError_t pass_grid(K kernel, size_t smem, int sm_count, int* occ_cache, unsigned* grid) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
-    if (occ_cache[dev] == 0) {
-        int o = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, kPassThreads, smem);
-        if (e != cudaSuccess) return e;
-        occ_cache[dev] = o < 1 ? 1 : o;
-    }
-    *grid = (unsigned)(sm_count * occ_cache[dev]);
-    return cudaSuccess;
-}
-
-template <bool WIDE, bool COUNT, bool OUT32, int KW, int LAY>
-static cudaError_t launch_passes_t(const WalkParams& P, Scratch& sc, int sm_count, cudaStream_t st) {
-    static int occ_first[64] = {0}, occ_chain[64] = {0}, occ_probe[64] = {0};
-    unsigned g_first = 0, g_chain = 0, g_probe = 0;
-    constexpr size_t chain_smem = sizeof(ChainShared<WIDE>);
-    cudaError_t e;
-    if ((e = pass_grid(first_pass_kernel<WIDE, COUNT, OUT32, KW, LAY>, 0, sm_count, occ_first, &g_first)) != cudaSuccess) return e;
-    if ((e = pass_grid(chain_pass_kernel<WIDE, COUNT, OUT32, LAY>, chain_smem, sm_count, occ_chain, &g_chain)) != cudaSuccess) return e;
-    if ((e = pass_grid(probe_pass_kernel<WIDE, COUNT, OUT32, KW, LAY>, 0, sm_count, occ_probe, &g_probe)) != cudaSuccess) return e;
-    PassLists LS;
-    LS.surv = sc.l_surv; LS.ranges = sc.l_ranges; LS.left = sc.l_left; LS.n = sc.l_n;
-    LS.cap = (uint32_t)sc.list_cap; LS.cap_left = (uint32_t)(2 * sc.list_cap);
-    if ((e = cudaMemsetAsync(sc.l_n, 0, 8 * 8, st)) != cudaSuccess) return e;
-    const WalkItem* items = P.items;
-    const unsigned long long* n_items = reinterpret_cast<const unsigned long long*>(P.n_items);
-    for (int r = 0; r < kPassRounds; r++) {
-        const int last = r == kPassRounds - 1;
-        LS.fresh = sc.l_fresh[r & 1];
-        LS.n_fresh = sc.l_n + ((r & 1) ? 5 : 2);
-        if (r > 0) { // S, P and the F buffer this round's probes fill start empty (its other half is this round's input)
-            if ((e = cudaMemsetAsync(sc.l_n, 0, 16, st)) != cudaSuccess) return e;
-            if ((e = cudaMemsetAsync(LS.n_fresh, 0, 8, st)) != cudaSuccess) return e;
-        }
-        first_pass_kernel<WIDE, COUNT, OUT32, KW, LAY><<<g_first, kPassThreads, 0, st>>>(P, items, n_items, LS, last);
-        if ((e = cudaMemsetAsync(sc.l_n + 4, 0, 8, st)) != cudaSuccess) return e;
-        chain_pass_kernel<WIDE, COUNT, OUT32, LAY><<<g_chain, kPassThreads, chain_smem, st>>>(P, LS);
-        if ((e = cudaMemsetAsync(sc.l_n + 4, 0, 8, st)) != cudaSuccess) return e;
-        probe_pass_kernel<WIDE, COUNT, OUT32, KW, LAY><<<g_probe, kPassThreads, 0, st>>>(P, LS, last);
-        g_launches += 3;
-        items = LS.fresh;
-        n_items = LS.n_fresh;
-    }
-    return cudaGetLastError();
-}
-
-template <bool WIDE, int KW>
-static cudaError_t launch_passes(const WalkParams& P, Scratch& sc, bool count, int sm_count, cudaStream_t st) {
-#define PASSES(C_, O_) (P.ix.compact ? (P.ix.layout == LAY_C64 ? launch_passes_t<WIDE, C_, O_, KW, WIDE ? LAY_CLASSIC : LAY_C64>(P, sc, sm_count, st)   \
-                                                                : launch_passes_t<WIDE, C_, O_, KW, WIDE ? LAY_CLASSIC : LAY_C96>(P, sc, sm_count, st)) \
-                                     : launch_passes_t<WIDE, C_, O_, KW, LAY_CLASSIC>(P, sc, sm_count, st))
-    if (P.out32) {
-        if (WIDE || count) return cudaErrorInvalidValue;
-        return PASSES(false, !WIDE);
-    }
-    return count ? PASSES(true, false) : PASSES(false, false);
-#undef PASSES
-}
-
-static int pass_lists_alloc(Scratch& sc, int window) {
-    if (sc.l_n) return 0;
-    sc.list_cap = sc.max_reads + sc.max_bases / std::max(1, window) + 64;
-    const size_t cap = (size_t)sc.list_cap;
-    CU(cudaMalloc(&sc.l_surv, cap * 32));
-    CU(cudaMalloc(&sc.l_ranges, cap * sizeof(uint4)));
-    CU(cudaMalloc(&sc.l_fresh[0], cap * sizeof(WalkItem)));
-    CU(cudaMalloc(&sc.l_fresh[1], cap * sizeof(WalkItem)));
-    CU(cudaMalloc(&sc.l_left, 2 * cap * sizeof(WalkItem)));
-    CU(cudaMalloc(&sc.l_n, 8 * 8));
-    return 0;
-}
-
 // One persistent wave: grid = SM count x resident blocks per SM (occupancy query); work is handed out through a global cursor.
-static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, Scratch& sc, int window, bool streaming, bool count, cudaStream_t st) {
+static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, bool count, cudaStream_t st) {
     // The compact layouts pay in streaming mode, whose 8 B-per-k-mer result stream competes with the index for L2.
     // The per-k-mer search path re-reads the wide top of the tree, is bound by L2 sector throughput and issue slots,
     // and is faster on the 224-column classic sectors (fewer two-sector steps): profiles/r01h_compact_ab.txt.
@@ -965,18 +875,8 @@ static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, Scratch& sc, int
     P.probe_stride = streaming ? ix->probe_stride : 0u;
     const bool wide = ix->view.wide;
     cudaError_t e;
-    const bool k64 = ix->k > 32;
-    if (streaming && ix->use_passes && ix->view.edges_at_starts && P.probe_stride > 0) {
-        // passes over global lists; walk_kernel then answers what they leave (k-mers over invalid bases, reads with more
-        // stretches of found k-mers than there are rounds)
-        if (pass_lists_alloc(sc, window)) return 1;
-        if (wide) e = k64 ? launch_passes<true, 2>(P, sc, count, ix->sm_count, st) : launch_passes<true, 1>(P, sc, count, ix->sm_count, st);
-        else e = k64 ? launch_passes<false, 2>(P, sc, count, ix->sm_count, st) : launch_passes<false, 1>(P, sc, count, ix->sm_count, st);
-        CU(e);
-        P.items = sc.l_left;
-        P.n_items = reinterpret_cast<const int64_t*>(sc.l_n + 3);
-    }
     CU(cudaMemsetAsync(P.cursor, 0, 8, st));
+    const bool k64 = ix->k > 32;
 #define WALK(S_, W_) e = k64 ? launch_walk_t<S_, W_, 2>(P, count, ix->sm_count, st) : launch_walk_t<S_, W_, 1>(P, count, ix->sm_count, st)
     if (streaming) { if (wide) WALK(true, true); else WALK(true, false); }
     else { if (wide) WALK(false, true); else WALK(false, false); }
@@ -1026,7 +926,7 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
     if (count) CU(cudaMemsetAsync(sc.stats, 0, 64, st));
     const bool timed = s->timing && &sc == &s->sc;
     if (timed) CU(cudaEventRecord(s->ev_walk0, st));
-    if (launch_walk(ix, P, sc, window, mode == SBWT_GPU_MODE_STREAMING, count, st)) return 1;
+    if (launch_walk(ix, P, mode == SBWT_GPU_MODE_STREAMING, count, st)) return 1;
     if (timed) CU(cudaEventRecord(s->ev_walk1, st));
     return 0;
 }
