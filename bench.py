@@ -364,8 +364,8 @@ def measure(name: str, args, env: dict, headline: bool) -> dict:
 
     peak, peak_src = peaks()
     w_ms = float(np.mean(walk_ms))
-    compact = bool(idx.compact_layout[0] and w["streaming"])
-    hot = int(32 * (idx.n_nodes // 64 + 1)) if compact else int(128 * (idx.n_nodes // 224 + 1))
+    compact = idx.csector_format if w["streaming"] else None
+    hot = int(32 * (idx.n_nodes // (64 if compact == "c64" else 96) + 1)) if compact else int(128 * (idx.n_nodes // 224 + 1))
     level = "l2" if hot <= L2_RESIDENT_BYTES else "dram"
     achieved = stats.index_sectors * 32 / (w_ms * 1e-3) / 1e9
     sectors_per_s = stats.index_sectors / (w_ms * 1e-3)
@@ -392,7 +392,8 @@ def measure(name: str, args, env: dict, headline: bool) -> dict:
     rec = {"workload": f"{name}: {w['desc']}", "value": value, "unit": "lookups/s", "ms_per_step": ms_per_step, "steps": steps,
            "lookups_per_step_per_gpu": int(n_out), "hit_rate": hits_gpu / max(1, n_out), "n_nodes": int(idx.n_nodes), "k": k,
            "index_device_bytes": int(idx.device_bytes), "l2_set_aside_bytes": int(idx.l2_set_aside),
-           "index_layout": ("csector64: one-hot, 64 columns x 4 characters + absolute counts per 32-byte sector" if compact else
+           "index_layout": ("csector64: one-hot, 64 columns x 4 characters + absolute counts per 32-byte sector" if compact == "c64" else
+                            "csector96: one-hot, 96 columns x 4 characters + relative counts per 32-byte sector" if compact == "c96" else
                             "classic sectors: 224 columns x 1 character + count per 32-byte sector") + f" (flagged csector fraction {idx.compact_layout[1]:.4f})",
            "path": "streaming_search" if w["streaming"] else "search", "clocks": clk.summary(), "gpu_launches": int(gpu_launches),
            "launches_per_step": int(stats.kernel_launches), "roofline": roofline, "parity": parity,

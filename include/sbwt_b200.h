@@ -83,12 +83,13 @@ int64_t sbwt_gpu_index_device_bytes(const sbwt_gpu_index *idx);
 /* 1 if every non-suffix-group-start column has an empty subset (true for every index the
  * reference builds; lets the streaming step use one sector instead of a walk-back). */
 int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index *idx);
-/* 1 if the walk kernels answer ranks from the compact one-hot layout (two bits per column: used for
- * narrow indexes in which at most 5 % of the 96-column blocks hold a column with no outgoing edge or
- * several; SBWT_B200_COMPACT=0 disables it, =2 forces it). *flagged_fraction (may be NULL) receives
- * the fraction of blocks that are answered from the classic sectors, -1 if the layout was not built.
- * Results never depend on the layout. Replaces nothing in the reference: it is the device-side
- * counterpart of choosing the SubsetMatrixRank bit-vector representation (SubsetMatrixRank.hh:19-37). */
+/* Nonzero if the walk kernels answer ranks from a compact one-hot layout (two bits per column; for narrow indexes in
+ * which at most 5 % of the blocks hold a column with no outgoing edge or several; SBWT_B200_COMPACT=0 disables it, =2
+ * forces it): 2 = csector64 (64 columns per sector, absolute counts inline), 1 = csector96 (96 columns, relative counts;
+ * chosen when only the denser format keeps the structure on chip; SBWT_B200_LAYOUT=c64|c96 overrides). *flagged_fraction
+ * (may be NULL) receives the fraction of blocks that are answered from the classic sectors, -1 if the layout was not
+ * built. Results never depend on the layout. Replaces nothing in the reference: it is the device-side counterpart of
+ * choosing the SubsetMatrixRank bit-vector representation (SubsetMatrixRank.hh:19-37). */
 int sbwt_gpu_index_compact_layout(const sbwt_gpu_index *idx, double *flagged_fraction);
 /* Bytes of L2 this index asked the device to set aside for its persisting (evict_last) lines: done for a one-hot
  * index whose csectors fit on chip (cudaLimitPersistingL2CacheSize; SBWT_B200_L2_SET_ASIDE_MB overrides, 0 = never). */

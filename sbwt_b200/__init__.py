@@ -211,6 +211,11 @@ class Index:
         return bool(used), float(f.value)
 
     @property
+    def csector_format(self) -> str | None:
+        """'c64' / 'c96' when a compact one-hot layout is in use, else None."""
+        return {0: None, 1: "c96", 2: "c64"}[lib().sbwt_gpu_index_compact_layout(self._h, None)]
+
+    @property
     def C_array(self):
         out = np.zeros(4, dtype=np.int64)
         lib().sbwt_gpu_index_C(self._h, out.ctypes.data)

@@ -231,6 +231,7 @@ extern "C" int64_t sbwt_gpu_count_outputs(const int64_t* off, int64_t n_reads, i
 // ------------------------------------------------------------------ API: index
 
 extern "C" int sbwt_gpu_index_set_table_length(sbwt_gpu_index* ix, int tp);
+constexpr int kMaxTableLength = 16; // the table index is the first word of the k-mer window: 16 characters
 
 // The persisting-L2 limit is per device: it follows the largest request among the indexes alive on the device and is given
 // back (with the persisting lines) when the last of them goes.
@@ -327,7 +328,11 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     // SBWT_B200_LAYOUT = c96 | c64 picks the csector format (device_index.cuh). Read here, once per index.
     int compact_mode = 1;
     if (const char* e = getenv("SBWT_B200_COMPACT")) compact_mode = atoi(e);
+    // csector format: csector64 (one request per rank) unless only the denser csector96 keeps the structure on chip
+    // (measured, profiles/r02m_c2m_csector_format.txt: 150 M columns = 75 MB / 50 MB: 11.04 ms vs 9.72 ms per 1.2e9 lookups;
+    // 100 M columns = 50 MB / 33 MB: 7.93 ms vs 8.27 ms)
     int layout = kDefaultCompactLayout;
+    if (n_nodes / 2 > ((int64_t)56 << 20) && n_nodes / 3 <= ((int64_t)60 << 20)) layout = LAY_C96;
     if (const char* e = getenv("SBWT_B200_LAYOUT")) layout = strcmp(e, "c64") == 0 ? LAY_C64 : (strcmp(e, "c96") == 0 ? LAY_C96 : layout);
     if (const char* e = getenv("SBWT_B200_COMPACT_SEARCH")) ix->compact_in_search = atoi(e) > 0;
     if (compact_mode >= 2) ix->compact_in_search = true;
@@ -417,13 +422,18 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
         const char* e = getenv("SBWT_B200_TABLE_P");
         if (e) tp = atoi(e);
         else {
-            // longest table (<= 14 characters: 2.1 GB of 8-byte rows) with at most 4 rows per column of the index. A row
-            // is read once per from-scratch search and replaces one dependent interval step per extra character; every
-            // workload measured faster with each character up to 14 although the table then dwarfs the sector array and
-            // lives in HBM (profiles/r01n_table_length.txt: c2 10.86 -> 9.73 -> 8.86 ms for 10 / 13 / 14 characters,
-            // c4s 20.4 -> 18.8 -> 17.8 ms)
-            tp = (int)std::min<int64_t>(std::max<int64_t>(p, 14), k);
-            while (tp > p && (1ll << (2 * tp)) > std::max<int64_t>(4 * n_nodes, 1 << 16)) tp--;
+            // longest table (<= 16 characters) with at most 64 rows per column of the index that takes at most a fifth of the
+            // device memory free right now. A row is read once per from-scratch search and replaces one dependent
+            // interval step per extra character -- the steps right after the table jump are the expensive ones (wide
+            // intervals, two sectors, lanes dying at different depths) -- and every workload measured faster with each
+            // character although the table then dwarfs the rank structure and lives in HBM: c2 10.63 / 9.31 / 7.94 / 7.22 /
+            // 6.93 ms for 10 / 12 / 14 / 15 / 16 characters (2.1 / 8.6 / 34 GB of 8-byte rows), c4s 21.8 / 19.7 / 17.6 /
+            // 16.4 / 15.7 ms (profiles/r02q_table_length.txt). HBM is what a B200 has plenty of.
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+            const int64_t row_bytes = wide ? 16 : 8;
+            tp = (int)std::min<int64_t>(std::max<int64_t>(p, kMaxTableLength), k);
+            while (tp > p && ((1ll << (2 * tp)) > std::max<int64_t>(64 * n_nodes, 1 << 16) || (row_bytes << (2 * tp)) > (int64_t)(free_b / 5))) tp--;
         }
     }
     if (int rc = sbwt_gpu_index_set_table_length(ix, tp)) { sbwt_gpu_index_destroy(ix); return rc; }
@@ -455,7 +465,7 @@ extern "C" int sbwt_gpu_index_set_table_length(sbwt_gpu_index* ix, int tp) {
     if (!ix) return set_error("null index");
     if (tp < 0) return set_error("negative table length");
     if (tp > ix->k) tp = (int)ix->k;
-    if (tp > 14) tp = 14;
+    if (tp > kMaxTableLength) tp = kMaxTableLength;
     if (!ix->table_from_bits && tp != ix->precalc_k)
         return set_error("the file's precalc table does not follow from its bit vectors; only its own length (%lld) can be used", (long long)ix->precalc_k);
     DeviceGuard guard(ix->device);
@@ -531,7 +541,7 @@ extern "C" void sbwt_gpu_index_C(const sbwt_gpu_index* ix, int64_t C[4]) { for (
 extern "C" int64_t sbwt_gpu_index_device_bytes(const sbwt_gpu_index* ix) { return ix->device_bytes; }
 extern "C" int sbwt_gpu_index_compact_layout(const sbwt_gpu_index* ix, double* flagged_fraction) {
     if (flagged_fraction) *flagged_fraction = ix->flagged_fraction;
-    return ix->d_compact ? 1 : 0;
+    return ix->d_compact ? ix->view.layout : 0; // LAY_C96 = 1, LAY_C64 = 2
 }
 extern "C" int64_t sbwt_gpu_index_l2_set_aside(const sbwt_gpu_index* ix) { return ix ? ix->l2_set_aside : 0; }
 extern "C" int sbwt_gpu_index_edges_only_at_group_starts(const sbwt_gpu_index* ix) { return ix->view.edges_at_starts; }

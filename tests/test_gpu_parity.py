@@ -264,7 +264,7 @@ def test_search_table_lengths(tmp_path):
         assert idx.table_length >= file_p
         np.testing.assert_array_equal(idx.precalc().reshape(-1), read_sbwt(golden(name, "index.sbwt"))["precalc"].reshape(-1))
         ses = S.Session(idx, a.size, len(reads))
-        for tp in (0, 1, file_p, 5, 8, 9, 11, 12) + ((13, 14) if name == "small_k31" else ()):
+        for tp in (0, 1, file_p, 5, 8, 9, 11, 12) + ((13, 14, 15, 16) if name == "small_k31" else ()):  # (16 characters: 34 GB of rows)
             idx.set_table_length(tp)
             assert idx.table_length == min(tp, idx.k)
             for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
