@@ -563,16 +563,30 @@ __global__ void __launch_bounds__(kWalkThreads, WalkBlocks<STREAMING, WIDE, LAY>
                     if (D) nP += __popc(pm); else nT += __popc(pm);
                 }
             };
-            auto advance = [&](int i) { // one base consumed
-                pos[i]++;
-                const uint32_t ph = pos[i] & 15u;
+            // The next code word, every 16 bases, is loaded IN PLACE under a predicate, and by the step BEFORE the one that
+            // moves to a new word, right behind that step's sector load: the two loads are in flight together and the step's
+            // one wait covers both. (Issued after the step -- as round 1 and the first round-2 kernels did -- the load is
+            // still in flight at the top of the next step, and ptxas, which tracks it on the scoreboard of the sector load,
+            // waits for it BEFORE issuing the next sector load: 11 % of the kernel's stall samples, profiles/r02t.)
+            auto refill = [&](int i) { // (after the step's character has been taken from cw)
+                const uint32_t np = pos[i] + 1u, ph = np & 15u;
                 if (ph == 0) cw[i] = nx[i];
-                // the next code word, every 16 bases, loaded IN PLACE under a predicate: nothing reads nx for the next 16
-                // steps, so no step waits for this load (a plain conditional load went through a temporary register and a
-                // move that stalled every iteration on some lane's refill: 15 % of the round-1 kernel's stall samples)
                 asm volatile("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
-                             : "+r"(nx[i]) : "l"(P.codes + (pos[i] >> 4) + 1), "r"(ph));
+                             : "+r"(nx[i]) : "l"(P.codes + (np >> 4) + 1), "r"(ph));
             };
+            // a chain's row of the stage as a shared-space address held in a register (left to itself the compiler rebuilds
+            // the generic address from %tid and the shared window in every step: 11 of the step's 75 instructions)
+            uint32_t row_sa[NCH];
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                row_sa[i] = (uint32_t)__cvta_generic_to_shared(&STG.v[i][lane][0]);
+                asm volatile("mov.u32 %0, %0;" : "+r"(row_sa[i]));
+            }
+            auto stage_put = [&](int i, uint32_t sl, pos_t v) {
+                if (WIDE) asm volatile("st.shared.b64 [%0], %1;" ::"r"(row_sa[i] + sl * 8u), "l"((int64_t)v) : "memory");
+                else asm volatile("st.shared.b32 [%0], %1;" ::"r"(row_sa[i] + sl * 4u), "r"((uint32_t)v) : "memory");
+            };
+            auto advance = [&](int i) { pos[i]++; }; // one base consumed (a step that fails ends its chain: cw may be one ahead)
 
             while (true) {
                 // ---- own k-mers: steps without a result. A miss here is the item's first k-mer being absent.
@@ -586,7 +600,7 @@ __global__ void __launch_bounds__(kWalkThreads, WalkBlocks<STREAMING, WIDE, LAY>
 #pragma unroll
                     for (int i = 0; i < NCH; i++) {
                         c[i] = (int)((cw[i] >> ((pos[i] & 15u) * 2u)) & 3u);
-                        if (run[i]) ST.issue(L[i], col[i], c[i]);
+                        if (run[i]) { ST.issue(L[i], col[i], c[i]); refill(i); }
                     }
                     uint32_t wantm = 0; // bit i: chain i ended in a miss and leaves k-mers behind
                     uint32_t kstart[NCH];
@@ -644,7 +658,7 @@ __global__ void __launch_bounds__(kWalkThreads, WalkBlocks<STREAMING, WIDE, LAY>
                     for (int i = 0; i < NCH; i++) {
                         run[i] = (sl - lo[i]) < width[i]; // (unsigned: also false below lo; width is 0 for a chain that is not running)
                         c[i] = (int)((cw[i] >> ((pos[i] & 15u) * 2u)) & 3u);
-                        if (run[i]) ST.issue(L[i], col[i], c[i]);
+                        if (run[i]) { ST.issue(L[i], col[i], c[i]); refill(i); }
                     }
                     pos_t ncol[NCH];
                     bool ok[NCH], okall = true;
@@ -662,7 +676,7 @@ __global__ void __launch_bounds__(kWalkThreads, WalkBlocks<STREAMING, WIDE, LAY>
 #pragma unroll
                         for (int i = 0; i < NCH; i++) {
                             if (run[i]) {
-                                STG.v[i][lane][sl] = ncol[i];
+                                stage_put(i, sl, ncol[i]);
                                 col[i] = ncol[i];
                                 advance(i);
                             }
@@ -678,11 +692,11 @@ __global__ void __launch_bounds__(kWalkThreads, WalkBlocks<STREAMING, WIDE, LAY>
                                 // (a chain's first result may be its own k-mer's: that step is not a streaming step)
                                 if (!hit) resolve(col[i], c[i], fs[i] || sl > lo[i], ncol[i], hit);
                                 if (hit) {
-                                    STG.v[i][lane][sl] = ncol[i];
+                                    stage_put(i, sl, ncol[i]);
                                     col[i] = ncol[i];
                                     advance(i);
                                 } else { // the k-mer is absent: [col, col] -> empty (SBWT.hh:433) / l != r (SBWT.hh:574); the chain ends
-                                    STG.v[i][lane][sl] = (pos_t)-1;
+                                    stage_put(i, sl, (pos_t)-1);
                                     kstart[i] = pos[i] - (k - 1u);
                                     width[i] = sl + 1u - lo[i];
                                     endm |= 1u << i;
