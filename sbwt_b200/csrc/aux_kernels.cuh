@@ -15,60 +15,74 @@ namespace sbwt_b200 {
 // ------------------------------------------------------------------ K1: packer
 
 // 4 ASCII bytes in a word -> 4 two-bit codes in the low byte and 4 invalid flags in the low nibble.
-// code = ((ch >> 1) ^ (ch >> 2)) & 3 maps A,C,G,T -> 0,1,2,3 (and a,c,g,t likewise).
+// code = ((ch >> 1) ^ (ch >> 2)) & 3 maps A,C,G,T -> 0,1,2,3 (and a,c,g,t likewise). A byte is valid when it IS the
+// character its code stands for: the four codes of the word, as selector nibbles, look that character up in
+// 0x54474341 ("ACGT") with one byte permute. (The packer is bound by instruction issue, not by HBM: the first version's
+// arithmetic look-up and __vcmpeq4 cost 9 instructions per base; this one about half, profiles/r02y.)
 __device__ __forceinline__ void pack4(uint32_t x, uint32_t fold, uint32_t& codes, uint32_t& inval) {
     const uint32_t u = x & fold; // fold = 0xDFDFDFDF folds a-z onto A-Z; 0xFFFFFFFF keeps the byte exact
     const uint32_t c = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
-    // the character each code stands for: A=0x41, C=0x43, G=0x47, T=0x54
-    const uint32_t lo = c & 0x01010101u, hi = (c >> 1) & 0x01010101u;
-    const uint32_t expect = 0x41414141u + lo * 2u + hi * 6u + (lo & hi) * 11u;
-    const uint32_t ok = __vcmpeq4(u, expect); // 0xFF per valid byte
-    inval = (((~ok) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
+    const uint32_t t = c | (c >> 4);                          // byte 0: c0 | c1 << 4, byte 2: c2 | c3 << 4
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420u);         // nibbles c0, c1, c2, c3
+    const uint32_t d = u ^ __byte_perm(0x54474341u, 0u, sel); // zero byte = valid
+    const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u; // bit 7 of every non-zero byte
+    inval = (nz * 0x00204081u) >> 28;                         // bits 7, 15, 23, 31 -> 28, 29, 30, 31
     codes = (c * 0x01041040u) >> 24;
 }
 
-// One thread packs 32 bases: two 16-byte loads, one u64 + one u32 store. n_words covers the
-// padding words as well (they are written as "all invalid").
+// One lane packs 16 bases per unit, kPackUnits units per lane, a warp's lanes side by side: every load instruction of a
+// warp covers 512 contiguous bytes and every store 128 (round 1 gave each lane 32 contiguous bytes: half-used sectors in
+// both of its loads, 3.9 TB/s; profiles/r02y). The codes of a unit are one u32 (16 x 2 bits), its flags 16 bits; two
+// neighbouring lanes' flags make one word of the invalid mask. n_units (even) covers the padding words as well (they
+// are written as "all invalid").
+constexpr int kPackUnits = 4;
+
+__device__ __forceinline__ void pack16(const uint32_t (&x)[4], uint32_t fold, uint32_t& codes, uint32_t& inval) {
+    codes = 0; inval = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t c, v;
+        pack4(x[i], fold, c, v);
+        codes |= c << (8 * i);
+        inval |= v << (4 * i);
+    }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ ascii, int64_t n_bases, uint32_t fold,
-                                                   uint64_t* __restrict__ codes, uint32_t* __restrict__ invalid,
-                                                   int64_t n_words) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_words) return;
-    const int64_t g = t << 5;
-    uint64_t cw = 0;
-    uint32_t iw = 0;
-    if (VEC && g + 32 <= n_bases) {
-        const uint4* src = reinterpret_cast<const uint4*>(ascii + g);
-        uint4 q[2];
-        q[0] = __ldcs(src);
-        q[1] = __ldcs(src + 1);
-        const uint32_t* x = reinterpret_cast<const uint32_t*>(q);
+                                                   uint32_t* __restrict__ codes, uint32_t* __restrict__ invalid, int64_t n_units) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t u0 = warp * (32 * kPackUnits) + lane;
+    uint4 q[kPackUnits];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            uint32_t c, v;
-            pack4(x[i], fold, c, v);
-            cw |= (uint64_t)c << (8 * i);
-            iw |= v << (4 * i);
-        }
-    } else {
+    for (int u = 0; u < kPackUnits; u++) {
+        const int64_t unit = u0 + u * 32;
+        q[u] = make_uint4(0, 0, 0, 0);
+        if (VEC && unit * 16 + 16 <= n_bases) q[u] = __ldcs(reinterpret_cast<const uint4*>(ascii) + unit);
+    }
+#pragma unroll
+    for (int u = 0; u < kPackUnits; u++) {
+        const int64_t unit = u0 + u * 32, g = unit * 16;
+        uint32_t x[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        if (!(VEC && g + 16 <= n_bases) && unit < n_units) { // the ragged end, the padding, an unaligned buffer: byte by byte
 #pragma unroll 1
-        for (int i = 0; i < 8; i++) {
-            uint32_t x = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int64_t pos = g + 4 * i + b;
-                const uint32_t ch = pos < n_bases ? ascii[pos] : 0u; // beyond the end: invalid
-                x |= ch << (8 * b);
+            for (int i = 0; i < 4; i++) {
+                x[i] = 0;
+                for (int b = 0; b < 4; b++) {
+                    const int64_t pos = g + 4 * i + b;
+                    x[i] |= (pos < n_bases ? (uint32_t)ascii[pos] : 0u) << (8 * b); // beyond the end: invalid
+                }
             }
-            uint32_t c, v;
-            pack4(x, fold, c, v);
-            cw |= (uint64_t)c << (8 * i);
-            iw |= v << (4 * i);
+        }
+        uint32_t c, v;
+        pack16(x, fold, c, v);
+        const uint32_t vn = __shfl_down_sync(0xFFFFFFFFu, v, 1);
+        if (unit < n_units) {
+            codes[unit] = c;
+            if (!(lane & 1)) invalid[unit >> 1] = v | (vn << 16);
         }
     }
-    codes[t] = cw;
-    invalid[t] = iw;
 }
 
 // ------------------------------------------------------------------ scans
@@ -164,24 +178,61 @@ __global__ void __launch_bounds__(256) plan_count_kernel(const int64_t* __restri
     n_win[r] = (nk + window - 1) / window;
 }
 
-// per read: emit its work items. out_off / win_off are the exclusive scans of the counts. item.vfrom holds `nvalid`,
-// the number of leading k-mers of the item that cover no invalid base (0 = already the first k-mer does).
-__global__ void __launch_bounds__(256) plan_emit_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k,
-                                                         int window, const int64_t* __restrict__ out_off,
-                                                         const int64_t* __restrict__ win_off,
-                                                         const uint32_t* __restrict__ invalid, WalkItem* __restrict__ items) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const int64_t start = offsets[r] - offsets[0];
+// The walk's plan in three launches instead of eight (count, 2 x {reduce, partials, apply}, emit): the per-read counts are
+// recomputed from the offsets where they are needed rather than written, scanned in place and read back
+// (1.1 GB of traffic for 10 M reads became 0.45 GB; profiles/r02y).
+//   plan_reduce_kernel    per tile of kScanTile reads: sum of results, sum of work items
+//   plan_partials_kernel  one block: exclusive scan of both tile sums, the two totals
+//   plan_fused_emit_kernel per tile: the reads' result offsets (written to out_off, which the formatter and the hits
+//                         kernels use) and their work items
+__device__ __forceinline__ void plan_counts(const int64_t* __restrict__ offsets, int64_t r, int k, int window, int64_t& nk, int64_t& nw) {
     const int64_t len = offsets[r + 1] - offsets[r];
-    const int64_t nk = len >= k ? len - k + 1 : 0;
-    int64_t it = win_off[r];
+    nk = len >= k ? len - k + 1 : 0;
+    nw = (nk + window - 1) / window;
+}
+
+__global__ void __launch_bounds__(kScanThreads) plan_reduce_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k, int window,
+                                                                   int64_t* __restrict__ part_out, int64_t* __restrict__ part_win) {
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t so = 0, sw = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++)
+        if (base + i < n_reads) {
+            int64_t nk, nw;
+            plan_counts(offsets, base + i, k, window, nk, nw);
+            so += nk;
+            sw += nw;
+        }
+    int64_t to, tw;
+    block_exclusive_scan(so, &to);
+    block_exclusive_scan(sw, &tw);
+    if (threadIdx.x == 0) { part_out[blockIdx.x] = to; part_win[blockIdx.x] = tw; }
+}
+
+__global__ void __launch_bounds__(kScanThreads) plan_partials_kernel(int64_t* __restrict__ part_out, int64_t* __restrict__ part_win, int64_t n,
+                                                                     int64_t* __restrict__ totals) {
+    int64_t co = 0, cw = 0;
+    for (int64_t base = 0; base < n; base += kScanThreads) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t vo = i < n ? part_out[i] : 0, vw = i < n ? part_win[i] : 0;
+        int64_t to, tw;
+        const int64_t eo = block_exclusive_scan(vo, &to), ew = block_exclusive_scan(vw, &tw);
+        if (i < n) { part_out[i] = co + eo; part_win[i] = cw + ew; }
+        co += to;
+        cw += tw;
+    }
+    if (threadIdx.x == 0) { totals[0] = co; totals[1] = cw; }
+}
+
+// one read's work items (item.vfrom holds `nvalid`, the number of leading k-mers of the item that cover no invalid base)
+__device__ __forceinline__ void plan_emit_read(int64_t start, int64_t nk, int k, int window, int64_t out_off, int64_t it,
+                                               const uint32_t* __restrict__ invalid, WalkItem* __restrict__ items) {
     for (int64_t done = 0; done < nk; done += window, it++) {
         WalkItem w;
         const int64_t cnt = nk - done < window ? nk - done : window;
         const int64_t lo = start + done, hi = lo + cnt + k - 1; // bases covered by the item's k-mers: [lo, hi)
         w.base = (uint32_t)lo;
-        w.out = (uint32_t)(out_off[r] + done);
+        w.out = (uint32_t)(out_off + done);
         w.cnt = (uint32_t)cnt;
         int64_t first_bad = hi; // first invalid base in [lo, hi)
         for (int64_t wi = lo >> 5; wi <= (hi - 1) >> 5; wi++) {
@@ -193,6 +244,28 @@ __global__ void __launch_bounds__(256) plan_emit_kernel(const int64_t* __restric
         const int64_t nv = first_bad - lo - k + 1; // k-mer t covers [lo + t, lo + t + k)
         w.vfrom = (uint32_t)(nv < 0 ? 0 : (nv > cnt ? cnt : nv));
         items[it] = w;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) plan_fused_emit_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k, int window,
+                                                                       const int64_t* __restrict__ part_out, const int64_t* __restrict__ part_win,
+                                                                       const uint32_t* __restrict__ invalid, int64_t* __restrict__ out_off,
+                                                                       WalkItem* __restrict__ items) {
+    // the tile in kScanItems rounds of one read per thread (neighbouring threads, neighbouring reads: coalesced), a block scan per round
+    int64_t co = part_out[blockIdx.x], cw = part_win[blockIdx.x];
+    const int64_t o0 = offsets[0];
+    for (int round = 0; round < kScanItems; round++) {
+        const int64_t r = (int64_t)blockIdx.x * kScanTile + (int64_t)round * kScanThreads + threadIdx.x;
+        int64_t nk = 0, nw = 0;
+        if (r < n_reads) plan_counts(offsets, r, k, window, nk, nw);
+        int64_t to, tw;
+        const int64_t eo = block_exclusive_scan(nk, &to), ew = block_exclusive_scan(nw, &tw);
+        if (r < n_reads) {
+            out_off[r] = co + eo;
+            plan_emit_read(offsets[r] - o0, nk, k, window, co + eo, cw + ew, invalid, items);
+        }
+        co += to;
+        cw += tw;
     }
 }
 

@@ -749,7 +749,7 @@ static int scratch_alloc(Scratch& sc, int64_t max_bases, int64_t max_reads, int 
     CU(cudaMemset(sc.invalid, 0xFF, words * 4));
     CU(cudaMalloc(&sc.n_out, (max_reads + 1) * 8));
     CU(cudaMalloc(&sc.n_win, (max_reads + 1) * 8));
-    CU(cudaMalloc(&sc.partials, scan_partials_needed(max_reads + 1) * 8));
+    CU(cudaMalloc(&sc.partials, 2 * scan_partials_needed(max_reads + 1) * 8)); // (two channels: plan_reduce_kernel)
     CU(cudaMalloc(&sc.totals, 4 * 8));
     CU(cudaMalloc(&sc.items, sc.max_items * sizeof(WalkItem)));
     CU(cudaMalloc(&sc.stats, 8 * 8));
@@ -822,11 +822,12 @@ extern "C" void sbwt_gpu_session_destroy(sbwt_gpu_session* s) {
 // ------------------------------------------------------------------ launches
 
 static int launch_pack(const char* d_ascii, int64_t n_bases, int case_mode, uint64_t* codes, uint32_t* invalid, cudaStream_t st) {
-    const int64_t n_words = n_bases / 32 + 4;
+    const int64_t n_units = 2 * (n_bases / 32 + 4); // 16-base units, padding words included
     const uint32_t fold = case_mode == SBWT_GPU_CASE_EXACT ? 0xFFFFFFFFu : 0xDFDFDFDFu;
     const bool vec = ((uintptr_t)d_ascii & 15) == 0;
-    if (vec) pack_kernel<true><<<grid_for(n_words, 256), 256, 0, st>>>((const uint8_t*)d_ascii, n_bases, fold, codes, invalid, n_words);
-    else pack_kernel<false><<<grid_for(n_words, 256), 256, 0, st>>>((const uint8_t*)d_ascii, n_bases, fold, codes, invalid, n_words);
+    const unsigned grid = grid_for(n_units, 256 * kPackUnits);
+    if (vec) pack_kernel<true><<<grid, 256, 0, st>>>((const uint8_t*)d_ascii, n_bases, fold, reinterpret_cast<uint32_t*>(codes), invalid, n_units);
+    else pack_kernel<false><<<grid, 256, 0, st>>>((const uint8_t*)d_ascii, n_bases, fold, reinterpret_cast<uint32_t*>(codes), invalid, n_units);
     LAUNCHED();
     CU(cudaGetLastError());
     return 0;
@@ -918,10 +919,12 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
     // is walked read by read, as SBWT.hh:556-576 does
     const bool windows_ok = ix->view.edges_at_starts && ix->table_from_bits;
     const int window = mode == SBWT_GPU_MODE_SEARCH ? 32 : (windows_ok ? std::min(s->window, 1 << 23) : (1 << 23));
-    plan_count_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win); LAUNCHED();
-    if (exclusive_scan_inplace(sc.n_out, n_reads, sc.partials, sc.totals + 0, st)) return 1;
-    if (exclusive_scan_inplace(sc.n_win, n_reads, sc.partials, sc.totals + 1, st)) return 1;
-    plan_emit_kernel<<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.n_out, sc.n_win, sc.invalid, sc.items);
+    // (sc.n_out becomes the reads' result offsets, sc.totals[0..1] the number of results and of work items)
+    const unsigned n_tiles = grid_for(n_reads, kScanTile);
+    int64_t* part_win = sc.partials + scan_partials_needed(sc.max_reads + 1);
+    plan_reduce_kernel<<<n_tiles, kScanThreads, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.partials, part_win); LAUNCHED();
+    plan_partials_kernel<<<1, kScanThreads, 0, st>>>(sc.partials, part_win, n_tiles, sc.totals); LAUNCHED();
+    plan_fused_emit_kernel<<<n_tiles, kScanThreads, 0, st>>>(d_offsets, n_reads, (int)ix->k, window, sc.partials, part_win, sc.invalid, sc.n_out, sc.items);
     LAUNCHED();
     CU(cudaGetLastError());
     WalkParams P;
