@@ -115,25 +115,40 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu: int):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.rows, self.proc, self.t0, self.t1 = gpu, [], None, None, None
 
     def __enter__(self):
+        """Starts nvidia-smi and waits for its first row (its start-up is longer than a short timed region)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_wait = time.time()
+            while not self.rows and time.time() - t_wait < 5.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def start(self):  # the timed region begins
+        self.t0 = time.time()
+
+    def stop(self):  # ... and ends
+        self.t1 = time.time()
+
+    def in_region(self) -> int:
+        return sum(1 for t, _ in self.rows if self.t0 is not None and t >= self.t0 and (self.t1 is None or t <= self.t1 + 0.05))
+
+    def under_load(self) -> int:
+        return sum(1 for t, _ in self.rows if self.t0 is not None and t >= self.t0)
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -141,16 +156,19 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self) -> dict:
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        """Rows sampled from the start of the timed region on (the region itself, and -- when it is shorter than a few
+        sampling periods -- the identical steps run right behind it to keep the load up; both counts are reported)."""
+        rows = [r for t, r in self.rows if self.t0 is not None and t >= self.t0]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 7:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": self.in_region()}
 
 
 def peaks() -> tuple[float, str]:
@@ -343,6 +361,9 @@ def measure(name: str, args, env: dict, headline: bool) -> dict:
     barrier()
     torch.cuda.synchronize()
     with ClockSampler(local_rank) as clk:
+        barrier()
+        torch.cuda.synchronize()
+        clk.start()
         e0.record()
         for _ in range(steps):
             step()
@@ -352,7 +373,14 @@ def measure(name: str, args, env: dict, headline: bool) -> dict:
         e1.record()
         torch.cuda.synchronize()
         barrier()
-    gpu_launches = S.launch_count()
+        clk.stop()
+        gpu_launches = S.launch_count()  # (kernels launched inside the timed region only)
+        # a timed region shorter than a few sampling periods: the same steps go on (untimed) until the sampler has seen the load
+        t_more = time.time()
+        while clk.proc and clk.under_load() < 4 and time.time() - t_more < 2.0:
+            step()
+            torch.cuda.synchronize()
+        barrier()
     ses.set_timing(False)
     ms_total = e0.elapsed_time(e1)
     if dist is not None:
@@ -439,7 +467,7 @@ def e2e_legs(args, env: dict) -> dict:
             sec = float(t.item())
         return sec
 
-    sec = timed(lambda: ses_h.query_host(h_a, h_off, mode, out=h_out))
+    sec = timed(lambda: ses_h.query_host(h_a, h_off, mode, out=h_out, n_out=n_out))
     assert np.array_equal(h_out[: head.size], head)
     narrow32 = idx.n_nodes < (1 << 31)
     sparse_wire = narrow32 and ses_h.widen_threads() > 0 and os.environ.get("SBWT_B200_WIRE", "sparse") != "dense"
@@ -459,13 +487,13 @@ def e2e_legs(args, env: dict) -> dict:
     pm = S.pinned_empty((n_out + 31) // 32, np.uint32)
     if narrow32:
         h32 = S.pinned_empty(n_out, np.int32)
-        s32 = timed(lambda: ses_h.query_host_i32(h_a, h_off, mode, out=h32))
+        s32 = timed(lambda: ses_h.query_host_i32(h_a, h_off, mode, out=h32, n_out=n_out))
         assert np.array_equal(h32[: head.size].astype(np.int64), head)
         e2e["int32_results"] = {"value": world * n_out / s32, "unit": "lookups/s", "ms_per_step": s32 * 1e3, "api": "sbwt_gpu_query_host_i32",
                                 "d2h_bytes_per_step": sparse_bytes if sparse_wire else int(n_out * 4)}
         ph = h32  # (reused as the hits buffer)
         res = {}
-        sh = timed(lambda: res.update(r=ses_h.query_host_hits(h_a, h_off, mode, mask=pm, hits=ph)))
+        sh = timed(lambda: res.update(r=ses_h.query_host_hits(h_a, h_off, mode, mask=pm, hits=ph, n_out=n_out)))
         mask, hits, nh = res["r"]
         assert nh == K["hits"]
         bits = np.unpackbits(mask[: (head.size + 31) // 32].view(np.uint8), bitorder="little")[: head.size].astype(bool)
@@ -475,11 +503,35 @@ def e2e_legs(args, env: dict) -> dict:
                                    "no host thread touches results"}
         del ph, h32
     res = {}
-    sb = timed(lambda: res.update(r=ses_h.query_host_hits(h_a, h_off, mode, want_hits=False, mask=pm)))
+    sb = timed(lambda: res.update(r=ses_h.query_host_hits(h_a, h_off, mode, want_hits=False, mask=pm, n_out=n_out)))
     assert res["r"][2] == K["hits"]
     e2e["bitmap_only"] = {"value": world * n_out / sb, "unit": "lookups/s", "ms_per_step": sb * 1e3, "d2h_bytes_per_step": int(n_out // 8),
                           "api": "sbwt_gpu_query_host_hits(hits = NULL): one membership bit per k-mer"}
     ses_h.close()
+
+    # what the link itself gives: the reads' buffer copied up, a result-sized slice copied down (pinned memory, torch's copy engine
+    # calls, best of 3) -- the bound of the hits-only and bitmap-only calls, which move one byte per base up and little down
+    try:
+        ta = torch.from_numpy(h_a)
+        d_buf = torch.empty(ta.numel(), dtype=torch.uint8, device="cuda")
+        best = {"h2d": 0.0, "d2h": 0.0}
+        for _ in range(3):
+            for kind in ("h2d", "d2h"):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if kind == "h2d":
+                    d_buf.copy_(ta, non_blocking=True)
+                else:
+                    ta.copy_(d_buf, non_blocking=True)
+                e1.record()
+                e1.synchronize()
+                best[kind] = max(best[kind], ta.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        e2e["pcie"] = {"h2d_GBps": round(best["h2d"], 2), "d2h_GBps": round(best["d2h"], 2), "bytes": int(ta.numel()),
+                       "how": "one cudaMemcpyAsync of the reads' pinned buffer each way, CUDA events, best of 3"}
+        e2e["bitmap_only"]["h2d_frac"] = round((a.nbytes + off.nbytes) / sb / 1e9 / best["h2d"], 3)
+        del d_buf
+    except Exception as e:  # informational
+        e2e["pcie"] = {"error": str(e)}
 
     # one process driving every visible GPU (sbwt_gpu_query_host_sharded): what a single `sbwt search --devices` gets
     ndev = S.device_count()

@@ -153,7 +153,11 @@ int64_t sbwt_gpu_count_outputs(const int64_t *read_offsets, int64_t n_reads, int
  * sbwt_gpu_count_outputs() int64 values to `out`, read after read -- the concatenation of the
  * vectors SBWT::streaming_search / the search() loop return. Copies H2D, packs, walks and copies
  * D2H through pinned staging buffers in a double-buffered pipeline. MODE_STREAMING on an index
- * without streaming support fails like the reference ("streaming search support not built"). */
+ * without streaming support fails like the reference ("streaming search support not built").
+ * Every read must fit the session (max_bases) and the offsets must not decrease: both are checked chunk by
+ * chunk as the batch is cut, so such a read is reported when its chunk is reached; after ANY non-zero return
+ * nothing is in flight any more (the call drains its pipeline) and the contents of the result buffers are
+ * unspecified. The same holds for the _i32, _hits, _text and _sharded forms below. */
 int sbwt_gpu_query_host(sbwt_gpu_session *s, const char *ascii, const int64_t *read_offsets,
                         int64_t n_reads, int mode, int case_mode, int64_t *out);
 

@@ -311,11 +311,13 @@ class Session:
         return lib().sbwt_gpu_count_outputs(offsets.ctypes.data, offsets.size - 1, self.index.k)
 
     def query_host(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER,
-                   out: np.ndarray | None = None) -> np.ndarray:
-        """sbwt_gpu_query_host: host buffers in, int64 results out (H2D + pack + walk + D2H)."""
+                   out: np.ndarray | None = None, n_out: int | None = None) -> np.ndarray:
+        """sbwt_gpu_query_host: host buffers in, int64 results out (H2D + pack + walk + D2H). `n_out`: the number of results,
+        when the caller already knows it (count_outputs is a pass over the offsets)."""
         assert ascii_.dtype == np.uint8 and ascii_.flags.c_contiguous
         assert offsets.dtype == np.int64 and offsets.flags.c_contiguous
-        n_out = self.count_outputs(offsets)
+        if n_out is None:
+            n_out = self.count_outputs(offsets)
         if out is None:
             out = np.empty(n_out, dtype=np.int64)
         assert out.dtype == np.int64 and out.size >= n_out
@@ -328,10 +330,12 @@ class Session:
         return lib().sbwt_gpu_session_widen_threads(self._h)
 
     def query_host_hits(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER, *, want_hits: bool = True,
-                        mask: np.ndarray | None = None, hits: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray | None, int]:
+                        mask: np.ndarray | None = None, hits: np.ndarray | None = None,
+                        n_out: int | None = None) -> tuple[np.ndarray, np.ndarray | None, int]:
         """sbwt_gpu_query_host_hits: (membership bitmap as uint32 words, found values in order or None, number of hits)."""
         assert ascii_.dtype == np.uint8 and ascii_.flags.c_contiguous and offsets.dtype == np.int64 and offsets.flags.c_contiguous
-        n_out = self.count_outputs(offsets)
+        if n_out is None:
+            n_out = self.count_outputs(offsets)
         if mask is None:
             mask = np.empty((n_out + 31) // 32, dtype=np.uint32)
         if want_hits and hits is None:
@@ -342,11 +346,12 @@ class Session:
         return mask, (hits[: n.value] if want_hits else None), n.value
 
     def query_host_i32(self, ascii_: np.ndarray, offsets: np.ndarray, mode: int, case_mode: int = CASE_UPPER,
-                       out: np.ndarray | None = None) -> np.ndarray:
+                       out: np.ndarray | None = None, n_out: int | None = None) -> np.ndarray:
         """sbwt_gpu_query_host_i32: the same values as int32 (indexes with fewer than 2^31 columns)."""
         assert ascii_.dtype == np.uint8 and ascii_.flags.c_contiguous
         assert offsets.dtype == np.int64 and offsets.flags.c_contiguous
-        n_out = self.count_outputs(offsets)
+        if n_out is None:
+            n_out = self.count_outputs(offsets)
         if out is None:
             out = np.empty(n_out, dtype=np.int32)
         assert out.dtype == np.int32 and out.size >= n_out

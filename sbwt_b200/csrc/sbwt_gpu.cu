@@ -219,13 +219,25 @@ extern "C" int64_t sbwt_gpu_launch_count(int reset) {
     return v;
 }
 
-extern "C" int64_t sbwt_gpu_count_outputs(const int64_t* off, int64_t n_reads, int64_t k) {
+static int64_t count_outputs_range(const int64_t* off, int64_t i0, int64_t i1, int64_t k) {
     int64_t t = 0;
-    for (int64_t i = 0; i < n_reads; i++) {
-        const int64_t len = off[i + 1] - off[i];
-        if (len >= k) t += len - k + 1;
+    for (int64_t i = i0; i < i1; i++) { // (branch-free: the compiler unrolls and vectorises it)
+        const int64_t v = off[i + 1] - off[i] - (k - 1);
+        t += v > 0 ? v : 0;
     }
     return t;
+}
+
+extern "C" int64_t sbwt_gpu_count_outputs(const int64_t* off, int64_t n_reads, int64_t k) {
+    if (n_reads < (1 << 20)) return count_outputs_range(off, 0, n_reads, k);
+    // a pass over tens of MB of offsets is bound by one core's memory bandwidth: four threads for large batches
+    constexpr int T = 4;
+    int64_t part[T] = {0, 0, 0, 0};
+    std::thread th[T - 1];
+    for (int j = 1; j < T; j++) th[j - 1] = std::thread([&, j] { part[j] = count_outputs_range(off, n_reads * j / T, n_reads * (j + 1) / T, k); });
+    part[0] = count_outputs_range(off, 0, n_reads / T, k);
+    for (std::thread& x : th) x.join();
+    return part[0] + part[1] + part[2] + part[3];
 }
 
 // ------------------------------------------------------------------ API: index
@@ -1118,13 +1130,29 @@ static void drain_slots(sbwt_gpu_session* s) {
     g_last_error = keep;
 }
 
-// every read must fit a device-side batch: checked before anything is queued
-static int validate_reads(const sbwt_gpu_session* s, const int64_t* off, int64_t n_reads) {
-    for (int64_t i = 0; i < n_reads; i++) {
-        const int64_t len = off[i + 1] - off[i];
+// The next chunk [r0, r1) of a host batch: as many reads as the session capacity takes, found by bisection on the
+// offsets; one pass over the chunk's reads then checks them and counts their results. (Round 1 walked every read three
+// times on the calling thread -- one validation pass over the whole batch before anything was queued, one to cut the
+// chunk, one to count -- 80 MB of offsets each for 10 M reads: ~10 ms of a 130 ms call before the first copy started.)
+// A malformed or over-long read is therefore reported when its chunk is reached; the chunks before it have been
+// queued and are drained by the caller (drain_slots): the contents of the result buffers are unspecified after an error.
+static int next_chunk(const sbwt_gpu_session* s, const int64_t* off, int64_t n_reads, int64_t k, int64_t r0, int64_t* r1_out, int64_t* bases_out,
+                      int64_t* n_out_out) {
+    const int64_t hi = std::min(n_reads, r0 + s->max_reads);
+    int64_t r1 = (std::upper_bound(off + r0 + 1, off + hi + 1, off[r0] + s->max_bases) - off) - 1; // off[r1] - off[r0] <= max_bases
+    if (r1 <= r0) {
+        const int64_t len = off[r0 + 1] - off[r0];
         if (len < 0) return set_error("read offsets must be non-decreasing");
-        if (len > s->max_bases) return set_error("read %lld (%lld bases) is longer than the session capacity (%lld bases)", (long long)i, (long long)len, (long long)s->max_bases);
+        return set_error("read %lld (%lld bases) is longer than the session capacity (%lld bases)", (long long)r0, (long long)len, (long long)s->max_bases);
     }
+    int64_t t = 0, mn = 0;
+    for (int64_t i = r0; i < r1; i++) {
+        const int64_t len = off[i + 1] - off[i], v = len - (k - 1);
+        mn = len < mn ? len : mn;
+        t += v > 0 ? v : 0;
+    }
+    if (mn < 0 || off[r1] - off[r0] > s->max_bases) return set_error("read offsets must be non-decreasing");
+    *r1_out = r1; *bases_out = off[r1] - off[r0]; *n_out_out = t;
     return 0;
 }
 
@@ -1140,7 +1168,6 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
     if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
     if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
     if (mode == SBWT_GPU_MODE_STREAMING && !s->idx->has_sgs) return set_error("Error: streaming search support not built");
-    if (validate_reads(s, off, n_reads)) return 1;
     DeviceGuard guard(s->idx->device);
     const int rc = query_host_body(s, ascii, off, n_reads, mode, case_mode, out, out32);
     if (rc) drain_slots(s); // a CUDA or internal error in the middle of the pipeline
@@ -1168,15 +1195,9 @@ static int query_host_body(sbwt_gpu_session* s, const char* ascii, const int64_t
     HostSlot* prev = nullptr; // the slot of the previous chunk, whose second half (sparse format) is still to be issued
     while (r0 < n_reads) {
         // largest chunk [r0, r1) that fits the session capacity
-        int64_t r1 = r0, bases = 0;
-        while (r1 < n_reads && r1 - r0 < s->max_reads) {
-            const int64_t len = off[r1 + 1] - off[r1];
-            if (bases + len > s->max_bases) break;
-            bases += len;
-            r1++;
-        }
+        int64_t r1 = r0, bases = 0, n_out = 0;
+        if (next_chunk(s, off, n_reads, k, r0, &r1, &bases, &n_out)) return 1;
         const int64_t nr = r1 - r0;
-        const int64_t n_out = sbwt_gpu_count_outputs(off + r0, nr, k);
         HostSlot& h = s->slots[turn % sbwt_gpu_session::kSlots];
         turn++;
         if (slot_finish(h)) return 1;
@@ -1338,8 +1359,9 @@ static int query_host_hits_body(sbwt_gpu_session* s, const char* ascii, const in
             CU(cudaMemcpyAsync(pin_hits ? hits + n_hits : h.h_out32, d_packed, (size_t)total * 4, cudaMemcpyDeviceToHost, h.stream));
         }
         const int64_t w0 = p.bit0 >> 5, nw = ((p.bit0 & 31) + p.n_out + 31) / 32;
-        if (nw) {
-            hit_mask[w0] |= h.h_masks[0];
+        if (p.n_out) { // (every word of the bitmap is written here: no clearing pass over the caller's buffer; a chunk without results brought no masks)
+            if (p.bit0 & 31) hit_mask[w0] |= h.h_masks[0]; // the previous chunk wrote the low bits of this word
+            else hit_mask[w0] = h.h_masks[0];
             if (nw > 1) memcpy(hit_mask + w0 + 1, h.h_masks + 1, (size_t)(nw - 1) * 4);
         }
         if (hits && total && !pin_hits) {
@@ -1354,15 +1376,9 @@ static int query_host_hits_body(sbwt_gpu_session* s, const char* ascii, const in
     int64_t r0 = 0, out_pos = 0;
     int turn = 0;
     while (r0 < n_reads) {
-        int64_t r1 = r0, bases = 0;
-        while (r1 < n_reads && r1 - r0 < s->max_reads) {
-            const int64_t len = off[r1 + 1] - off[r1];
-            if (bases + len > s->max_bases) break;
-            bases += len;
-            r1++;
-        }
+        int64_t r1 = r0, bases = 0, n_out = 0;
+        if (next_chunk(s, off, n_reads, k, r0, &r1, &bases, &n_out)) return 1;
         const int64_t nr = r1 - r0;
-        const int64_t n_out = sbwt_gpu_count_outputs(off + r0, nr, k);
         HostSlot& h = s->slots[turn & 1];
         turn++;
         const char* src = ascii + off[r0];
@@ -1421,9 +1437,6 @@ extern "C" int sbwt_gpu_query_host_hits(sbwt_gpu_session* s, const char* ascii, 
     if (hits && (s->idx->n_nodes >= (1ll << 31) || s->idx->view.wide))
         return set_error("32-bit hit values need an index with fewer than 2^31 columns (this one has %lld); pass hits = NULL for the membership bitmap alone",
                          (long long)s->idx->n_nodes);
-    if (validate_reads(s, off, n_reads)) return 1;
-    const int64_t n_out = sbwt_gpu_count_outputs(off, n_reads, s->idx->k);
-    memset(hit_mask, 0, (size_t)((n_out + 31) / 32) * 4);
     DeviceGuard guard(s->idx->device);
     const int rc = query_host_hits_body(s, ascii, off, n_reads, mode, case_mode, hit_mask, hits, n_hits);
     if (rc) drain_slots(s);
@@ -1606,7 +1619,6 @@ extern "C" int sbwt_gpu_query_host_text(sbwt_gpu_session* s, const char* ascii, 
     if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
     if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
     if (mode == SBWT_GPU_MODE_STREAMING && !s->idx->has_sgs) return set_error("Error: streaming search support not built");
-    if (validate_reads(s, off, n_reads)) return 1;
     DeviceGuard guard(s->idx->device);
     const int rc = query_host_text_body(s, ascii, off, n_reads, mode, case_mode, sink, user, n_lookups);
     if (rc) drain_slots(s); // also after a sink error: queued kernels still read the caller's (pinned) input buffers
@@ -1633,13 +1645,8 @@ static int query_host_text_body(sbwt_gpu_session* s, const char* ascii, const in
     int turn = 0;
     HostSlot* prev = nullptr;
     while (r0 < n_reads) {
-        int64_t r1 = r0, bases = 0;
-        while (r1 < n_reads && r1 - r0 < s->max_reads) {
-            const int64_t len = off[r1 + 1] - off[r1];
-            if (bases + len > s->max_bases) break;
-            bases += len;
-            r1++;
-        }
+        int64_t r1 = r0, bases = 0, n_out_chunk = 0;
+        if (next_chunk(s, off, n_reads, ix->k, r0, &r1, &bases, &n_out_chunk)) return 1;
         const int64_t nr = r1 - r0;
         HostSlot& h = s->slots[turn & 1]; // free: its previous batch was delivered one iteration ago
         turn++;

@@ -59,6 +59,7 @@ def test_our_arm_prints_the_contract_line_with_parity_and_legs():
                 "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity", "workloads"):
         assert key in d, key
     assert d["metric"] == "kmer_lookups_per_s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] > 0 and d["value"] > 0
+    assert d["clocks"]["samples"] >= 1 and d["clocks"]["sm_mhz"] > 0 and d["clocks"]["sm_max_mhz"] >= d["clocks"]["sm_mhz"]
     rf = d["roofline"]
     assert rf["bound"] in ("hbm", "l2-latency") and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert rf["frac_of_level_ceiling"] > 0 and "frac_with_io" not in rf

@@ -680,6 +680,43 @@ def test_hits_only_results():
     idx.close()
 
 
+def test_chunks_without_results_and_late_errors():
+    """Host batches cut into chunks by a small session: a chunk made of reads shorter than k only (no results, and its
+    predecessor ends inside a bitmap word), then reads again; and a read that does not fit the session in a LATER chunk:
+    the call fails with the reference-style message, the session stays usable."""
+    reads = c1_reads()
+    long_reads = [r for r in reads if len(r) >= 60][:11]
+    mixed = long_reads[:5] + [b"ACGTACGTAC"] * 5 + [b""] * 2 + long_reads[5:]
+    a, off = synth.ragged_to_batch(mixed)
+    want = oracle.OracleIndex(golden("c1", "index.sbwt")).query_batch(a, off, streaming=True)
+    idx = S.Index(golden("c1", "index.sbwt"))
+    ses = S.Session(idx, max(len(r) for r in mixed) * 5, 5)
+    n_out = want.size
+    assert ses.count_outputs(off[:6]) % 32 != 0
+    for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+        np.testing.assert_array_equal(ses.query_host(a, off, mode), want)
+        pm = S.pinned_empty((n_out + 31) // 32, np.uint32)
+        pm[:] = 0xFFFFFFFF
+        mask, hits, n = ses.query_host_hits(a, off, mode, mask=pm)
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[:n_out].astype(bool)
+        got = np.full(n_out, -1, dtype=np.int64)
+        got[bits] = hits
+        np.testing.assert_array_equal(got, want)
+        assert n == int((want >= 0).sum())
+    too_long = long_reads[:7] + [b"ACGT" * 2000] + long_reads[7:]
+    ba, bo = synth.ragged_to_batch(too_long)
+    for call in (lambda: ses.query_host(ba, bo, S.MODE_STREAMING), lambda: ses.query_host_hits(ba, bo, S.MODE_STREAMING)):
+        with pytest.raises(S.SbwtGpuError, match=r"read 7 \(8000 bases\) is longer than the session capacity"):
+            call()
+    bad = off.copy()
+    bad[8] = bad[7] - 3
+    with pytest.raises(S.SbwtGpuError, match="non-decreasing"):
+        ses.query_host(a, bad, S.MODE_STREAMING)
+    np.testing.assert_array_equal(ses.query_host(a, off, S.MODE_STREAMING), want)
+    ses.close()
+    idx.close()
+
+
 def test_hits_only_bitmap_on_wide_index(monkeypatch):
     monkeypatch.setenv("SBWT_B200_FORCE_WIDE", "3")
     name = "small_k31"
