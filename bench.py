@@ -266,13 +266,13 @@ def host_widen_ceiling(threads: int) -> dict | None:
     if not os.path.exists(exe) or threads < 1:
         return None
     try:
-        out = subprocess.run([exe, "200000000"], capture_output=True, text=True, timeout=120).stdout
+        out = subprocess.run([exe, "200000000", str(threads)], capture_output=True, text=True, timeout=120).stdout
     except Exception:
         return None
     best = None
     for line in out.splitlines():
         m = re.match(r"threads=\s*(\d+) widen.*?: ([\d.]+) G values/s", line)
-        if m and int(m.group(1)) <= threads:
+        if m and int(m.group(1)) == threads:
             best = (int(m.group(1)), float(m.group(2)) * 1e9)
     return None if best is None else {"threads": best[0], "values_per_s": best[1],
                                       "how": "tools/host_bw_probe.cpp: int32 -> int64 with non-temporal stores, 2e8 values, best of 3"}

@@ -1067,7 +1067,7 @@ static int widen_thread_count() {
     int share = std::max(1, g_live_sessions.load());
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = std::max(share, atoi(e));
     const int hw = (int)std::thread::hardware_concurrency();
-    const int t = std::min(8, hw / share); // 8 threads saturate the host's memory system (profiles/r01g_e2e_sweep.txt)
+    const int t = std::min(10, hw / share); // 10 threads: best dense-result rate on the 16-core box (profiles/r03b_widen_threads.txt; 8: -5 %, 16: -3 %)
     return t >= 4 ? t : 0;
 }
 

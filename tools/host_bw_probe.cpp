@@ -24,12 +24,15 @@ static void widen(const int32_t* src, int64_t* dst, size_t n) {
 
 int main(int argc, char** argv) {
     const size_t n = argc > 1 ? strtoull(argv[1], 0, 10) : (size_t)400'000'000;
+    const int only = argc > 2 ? atoi(argv[2]) : 0; // one thread count instead of the sweep
     int32_t* src = (int32_t*)aligned_alloc(64, n * 4);
     int64_t* dst = (int64_t*)aligned_alloc(64, n * 8);
     memset(src, 1, n * 4);
     memset(dst, 0, n * 8);
-    for (int T : {1, 2, 4, 8, 12, 16, 24, 32}) {
-        if (T > (int)std::thread::hardware_concurrency() * 2) break;
+    std::vector<int> counts = {1, 2, 4, 8, 10, 12, 16, 24, 32};
+    if (only > 0) counts = {only};
+    for (int T : counts) {
+        if (!only && T > (int)std::thread::hardware_concurrency() * 2) break;
         for (int what = 0; what < 2; what++) {
             double best = 1e30;
             for (int rep = 0; rep < 3; rep++) {
