@@ -9,8 +9,9 @@ e = d["e2e"]
 print("e2e dense %.2f G/s (%.1f ms, host_bw_frac %.3f) | int32 %.2f | hits-only %.2f | bitmap %.2f | pcie %s" % (
     e["value"] / 1e9, e["ms_per_step"], e.get("host_bw_frac", 0), e.get("int32_results", {}).get("value", 0) / 1e9,
     e.get("hits_only", {}).get("value", 0) / 1e9, e.get("bitmap_only", {}).get("value", 0) / 1e9, e.get("pcie")))
-cb = d["cpu_baseline"]
-print("cpu_baseline %.1f M/s on %s cores (%s); variants: %s" % (cb["value"] / 1e6, cb["cores"], cb.get("cpu_model"),
+cb = d.get("cpu_baseline")
+if cb:
+  print("cpu_baseline %.1f M/s on %s cores (%s); variants: %s" % (cb["value"] / 1e6, cb["cores"], cb.get("cpu_model"),
       {k: round(v["value"] / 1e6, 1) for k, v in cb.get("variants", {}).items() if isinstance(v, dict) and "value" in v}))
 c = d.get("cli_e2e") or {}
 print("cli:", {k: round(v["lookups_per_s"] / 1e6, 1) for k, v in c.items() if isinstance(v, dict) and "lookups_per_s" in v}, "M lookups/s")
