@@ -479,8 +479,8 @@ def e2e_legs(args, env: dict) -> dict:
            "result_wire_format": ("sparse: one hit bit per result + the hits (int32) cross PCIe; host threads rebuild the caller's int64 array" if sparse_wire
                                   else ("int32 over PCIe, sign-extended by host threads" if (narrow32 and ses_h.widen_threads() > 0) else "int64 over PCIe")),
            "widen_threads": ses_h.widen_threads(), "host_threads": os.cpu_count()}
-    if env["rank"] == 0:
-        c = host_widen_ceiling(max(1, ses_h.widen_threads()))
+    if env["rank"] == 0 and narrow32 and ses_h.widen_threads() > 0:  # (int64 results over PCIe involve no host rebuild: no host ceiling)
+        c = host_widen_ceiling(ses_h.widen_threads())
         if c:
             e2e["host_ceiling"] = c  # (for the threads ONE rank uses; the ranks of a multi-GPU job share the host's memory system)
             e2e["host_bw_frac"] = (n_out / sec) / c["values_per_s"]

@@ -42,6 +42,11 @@ extern "C" {
                                  where seq_io::Reader upper-cases every base (SeqIO.hh:294-297,330-333) */
 #define SBWT_GPU_CASE_EXACT 1 /* only the bytes 'A','C','G','T' are valid: SBWT::search() called
                                  directly on a caller's buffer (SBWT.hh:427, globals.hh:38-47)         */
+#define SBWT_GPU_CASE_API 2   /* the direct API on raw bytes, to the letter: MODE_SEARCH = CASE_EXACT; MODE_STREAMING =
+                                 SBWT::streaming_search(const char*, len), whose from-scratch searches take the bytes
+                                 as they are while a streaming step upper-cases its new character (SBWT.hh:565): a k-mer
+                                 covering a lower-case base is a miss unless the k-mer before it was found. On an index
+                                 that violates the edge invariant (hand-made files only) it is CASE_EXACT.        */
 
 typedef struct sbwt_gpu_index sbwt_gpu_index;     /* one device-resident index (index, device)         */
 typedef struct sbwt_gpu_session sbwt_gpu_session; /* scratch + streams for batches against one index   */

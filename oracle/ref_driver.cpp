@@ -221,6 +221,7 @@ static int cmd_ranks(int argc, char** argv) {
 //   forward  (stdin: "node c" per line)  one result per line                        (SBWT::forward, SBWT.hh:369-381)
 //   getkmer  (stdin: colex rank per line) one k-mer label per line                  (SBWT::get_kmer, SBWT.hh:701-725)
 //   export   -o file         SBWT::ascii_export_sets (SBWT.hh:750-773)
+//   api      [--no-streaming] (stdin: one raw sequence per line) streaming_search / search on the bytes as given
 static int cmd_partial(int argc, char** argv) {
     plain_matrix_t idx;
     load_index(arg(argc, argv, "-i"), idx);
@@ -230,6 +231,27 @@ static int cmd_partial(int argc, char** argv) {
         if (len == 0) break;
         auto res = idx.partial_search(reader.read_buf, len);
         std::cout << res.first.first << " " << res.first.second << " " << res.second << "\n";
+    }
+    return 0;
+}
+
+// The direct API on the caller's raw bytes (no SeqIO upper-casing in front): one sequence per line on stdin,
+// SBWT::streaming_search(const char*, len) (SBWT.hh:545-581) -- or the search() loop with --no-streaming -- per line,
+// the result vector printed as numbers separated by blanks. Pins the mixed-case behaviour: a from-scratch search
+// takes the bytes as they are (SBWT.hh:427), a streaming step upper-cases its new character (SBWT.hh:565).
+static int cmd_api(int argc, char** argv) {
+    plain_matrix_t idx;
+    load_index(arg(argc, argv, "-i"), idx);
+    const bool streaming = !flag(argc, argv, "--no-streaming");
+    const int64_t k = idx.get_k();
+    string line;
+    while (std::getline(std::cin, line)) {
+        vector<int64_t> res;
+        if (streaming) res = idx.streaming_search(line.c_str(), (int64_t)line.size());
+        else
+            for (int64_t i = 0; i + k <= (int64_t)line.size(); i++) res.push_back(idx.search(line.c_str() + i));
+        for (size_t i = 0; i < res.size(); i++) std::cout << (i ? " " : "") << res[i];
+        std::cout << "\n";
     }
     return 0;
 }
@@ -287,6 +309,7 @@ int main(int argc, char** argv) {
         if (cmd == "ranks") return cmd_ranks(argc, argv);
         if (cmd == "dump") return cmd_dump(argc, argv);
         if (cmd == "partial") return cmd_partial(argc, argv);
+        if (cmd == "api") return cmd_api(argc, argv);
         if (cmd == "forward") return cmd_forward(argc, argv);
         if (cmd == "getkmer") return cmd_getkmer(argc, argv);
         if (cmd == "export") return cmd_export(argc, argv);

@@ -20,6 +20,7 @@ MODE_SEARCH = 0
 MODE_STREAMING = 1
 CASE_UPPER = 0
 CASE_EXACT = 1
+CASE_API = 2  # the direct API on raw bytes: streaming_search's mixed-case rule (include/sbwt_b200.h)
 
 EXPORTS = [
     "sbwt_gpu_last_error", "sbwt_gpu_device_count", "sbwt_gpu_abi_version",

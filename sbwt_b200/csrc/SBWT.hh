@@ -9,11 +9,11 @@
 // on the CPU. Construction from reads (KMC) and the select-support methods are out of
 // scope.
 //
-// Differences a caller can observe, all on the direct-API path only (the `sbwt search` command
-// line upper-cases every base before the index sees it, SeqIO.hh:294-297, so it is unaffected):
-//   * streaming_search(const char*, len) treats lower-case bases like search() does (a miss);
-//     the reference's single streaming step upper-cases the new character (SBWT.hh:565) while
-//     its from-scratch search does not (SBWT.hh:427).
+// Differences a caller can observe:
+//   * k <= 64 (the reference's search has no limit); a larger k is refused when the index is created.
+//   * streaming_search(const char*, len) gives the reference's answer, mixed case included (SBWT_GPU_CASE_API;
+//     tests/golden/*/mixed_case.*, written by the reference's own method) -- except on an index that violates the
+//     edge invariant (only hand-made files do), where a lower-case base is a miss everywhere (CASE_EXACT).
 //   * the batch methods (search_batch / streaming_search_batch) are additions: one call per
 //     k-mer through a GPU is correct but slow, the batch forms are what `sbwt search` uses.
 #pragma once
@@ -199,12 +199,14 @@ public:
         return out;
     }
 
-    // SBWT.hh:545-586. Throws if the index has no streaming support; empty result if len < k.
+    // SBWT.hh:545-586. Throws if the index has no streaming support; empty result if len < k. Raw bytes as in the
+    // reference: from-scratch searches are case-sensitive (SBWT.hh:427), a streaming step upper-cases its new
+    // character (SBWT.hh:565) -- SBWT_GPU_CASE_API.
     std::vector<int64_t> streaming_search(const std::string& input) const { return streaming_search(input.c_str(), (int64_t)input.size()); }
     std::vector<int64_t> streaming_search(const char* input, int64_t len) const {
         if (suffix_group_starts.empty()) throw std::runtime_error("Error: streaming search support not built");
         const int64_t off[2] = {0, len};
-        return streaming_search_batch(input, off, 1, SBWT_GPU_CASE_EXACT);
+        return streaming_search_batch(input, off, 1, SBWT_GPU_CASE_API);
     }
 
     // All k-mers of all reads; reads are ascii[offsets[i], offsets[i+1]). Results concatenated read after read.

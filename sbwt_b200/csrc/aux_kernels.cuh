@@ -85,6 +85,65 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ a
     }
 }
 
+// ------------------------------------------------------------------ CASE_API: the direct API's mixed-case behaviour
+//
+// SBWT::streaming_search(const char*, len) on raw bytes treats lower case in two ways (SBWT.hh:545-581): the first
+// k-mer of a read and every k-mer after a miss are searched from scratch on the bytes as they are (a lower-case base
+// makes the k-mer a miss, SBWT.hh:427 / globals.hh:38-47), while a streaming step upper-cases the one new character
+// it consumes (SBWT.hh:565). The batch is therefore walked with every base folded to upper case, and this pass
+// replays the reference's rule over each read's results: a k-mer that covers a lower-case base is a miss unless the
+// k-mer before it was found.
+
+// one bit per base: the byte is one of a, c, g, t
+__global__ void __launch_bounds__(256) lower_mask_kernel(const uint8_t* __restrict__ ascii, int64_t n_bases, uint32_t* __restrict__ lower,
+                                                         int64_t n_words) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; b++) {
+        const int64_t pos = w * 32 + b;
+        const uint8_t ch = pos < n_bases ? ascii[pos] : 0;
+        if (ch == 'a' || ch == 'c' || ch == 'g' || ch == 't') m |= 1u << b;
+    }
+    lower[w] = m;
+}
+
+// first position in [from, end) whose bit is set, or `end`
+__device__ __forceinline__ int64_t next_set_bit(const uint32_t* __restrict__ bits, int64_t from, int64_t end) {
+    int64_t p = from;
+    while (p < end) {
+        const uint32_t w = bits[p >> 5] >> (p & 31);
+        if (w) {
+            p += __ffs(w) - 1;
+            return p < end ? p : end;
+        }
+        p = (p | 31) + 1;
+    }
+    return end;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) case_fixup_kernel(const int64_t* __restrict__ offsets, int64_t n_reads, int k,
+                                                         const int64_t* __restrict__ out_off, const uint32_t* __restrict__ lower,
+                                                         T* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int64_t start = offsets[r] - offsets[0], len = offsets[r + 1] - offsets[r], nk = len - k + 1;
+    if (nk <= 0) return;
+    const int64_t end = start + len;
+    int64_t nl = next_set_bit(lower, start, end);
+    if (nl == end) return; // no lower-case base in the read
+    T* o = out + out_off[r];
+    bool prev_missing = true; // (the first k-mer is searched from scratch)
+    for (int64_t i = 0; i < nk; i++) {
+        const int64_t pos = start + i;
+        if (nl < pos) nl = next_set_bit(lower, pos, end);
+        T v = o[i];
+        if (prev_missing && nl < pos + k && v >= 0) { v = (T)-1; o[i] = v; }
+        prev_missing = v < 0;
+    }
+}
+
 // ------------------------------------------------------------------ scans
 
 constexpr int kScanThreads = 256;

@@ -99,6 +99,7 @@ struct Scratch {
     int64_t max_bases = 0, max_reads = 0, max_items = 0;
     uint64_t* codes = nullptr;
     uint32_t* invalid = nullptr;
+    uint32_t* lower = nullptr;  // CASE_API only: one bit per base, the byte is a lower-case a/c/g/t (allocated on first use)
     int64_t* n_out = nullptr;   // per read; becomes the exclusive scan
     int64_t* n_win = nullptr;   // per read; becomes the exclusive scan
     int64_t* partials = nullptr;
@@ -745,7 +746,7 @@ extern "C" int sbwt_gpu_ascii_export_sets(sbwt_gpu_index* ix, char* out, int64_t
 static void session_count(int delta); // sessions alive in this process (see widen_thread_count)
 
 static void scratch_free(Scratch& sc) {
-    cudaFree(sc.codes); cudaFree(sc.invalid); cudaFree(sc.n_out); cudaFree(sc.n_win); cudaFree(sc.partials);
+    cudaFree(sc.codes); cudaFree(sc.invalid); cudaFree(sc.lower); cudaFree(sc.n_out); cudaFree(sc.n_win); cudaFree(sc.partials);
     cudaFree(sc.totals); cudaFree(sc.items); cudaFree(sc.stats);
     sc = Scratch();
 }
@@ -835,7 +836,7 @@ extern "C" void sbwt_gpu_session_destroy(sbwt_gpu_session* s) {
 
 static int launch_pack(const char* d_ascii, int64_t n_bases, int case_mode, uint64_t* codes, uint32_t* invalid, cudaStream_t st) {
     const int64_t n_units = 2 * (n_bases / 32 + 4); // 16-base units, padding words included
-    const uint32_t fold = case_mode == SBWT_GPU_CASE_EXACT ? 0xFFFFFFFFu : 0xDFDFDFDFu;
+    const uint32_t fold = case_mode == SBWT_GPU_CASE_EXACT ? 0xFFFFFFFFu : 0xDFDFDFDFu; // (CASE_API arrives here as EXACT or UPPER)
     const bool vec = ((uintptr_t)d_ascii & 15) == 0;
     const unsigned grid = grid_for(n_units, 256 * kPackUnits);
     if (vec) pack_kernel<true><<<grid, 256, 0, st>>>((const uint8_t*)d_ascii, n_bases, fold, reinterpret_cast<uint32_t*>(codes), invalid, n_units);
@@ -914,7 +915,7 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
                             int64_t n_bases, int mode, int case_mode, void* d_out, bool out32, bool count, cudaStream_t st) {
     sbwt_gpu_index* ix = s->idx;
     if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
-    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
+    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT && case_mode != SBWT_GPU_CASE_API) return set_error("unknown case mode %d", case_mode);
     if (mode == SBWT_GPU_MODE_STREAMING && !ix->has_sgs) return set_error("Error: streaming search support not built"); // SBWT.hh:546-547
     if (n_reads < 0 || n_bases < 0) return set_error("negative batch size");
     if (out32 && (ix->n_nodes >= (1ll << 31) || ix->view.wide))
@@ -924,7 +925,12 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
                          (long long)n_bases, (long long)sc.max_reads, (long long)sc.max_bases);
     if (n_reads == 0) return 0;
     if (s->timing && &sc == &s->sc) CU(cudaEventRecord(s->ev_start, st));
-    if (launch_pack(d_ascii, n_bases, case_mode, sc.codes, sc.invalid, st)) return 1;
+    // CASE_API: per-k-mer search is CASE_EXACT; streaming is walked upper-cased and corrected afterwards (case_fixup_kernel)
+    // (an index that violates the edge invariant -- hand-made files only -- is walked with CASE_EXACT instead: there a streaming
+    // step and a from-scratch search may disagree, which the correction pass relies on not happening)
+    const bool api_fixup = case_mode == SBWT_GPU_CASE_API && mode == SBWT_GPU_MODE_STREAMING && ix->view.edges_at_starts && ix->table_from_bits;
+    const int pack_case = case_mode == SBWT_GPU_CASE_API ? (api_fixup ? SBWT_GPU_CASE_UPPER : SBWT_GPU_CASE_EXACT) : case_mode;
+    if (launch_pack(d_ascii, n_bases, pack_case, sc.codes, sc.invalid, st)) return 1;
     // search mode is planned as chunks of 32 k-mers (one lane per k-mer), streaming mode as windows of a read. The first
     // k-mer of a window is searched from scratch, which gives streaming_search's answers only where those equal search()'s:
     // an index that violates the edge invariant (LITERAL kernel) or whose table does not follow from its bit vectors
@@ -953,6 +959,15 @@ static int run_device_batch(sbwt_gpu_session* s, Scratch& sc, const char* d_asci
     if (timed) CU(cudaEventRecord(s->ev_walk0, st));
     if (launch_walk(ix, P, mode == SBWT_GPU_MODE_STREAMING, count, st)) return 1;
     if (timed) CU(cudaEventRecord(s->ev_walk1, st));
+    if (api_fixup) {
+        const int64_t n_words = n_bases / 32 + 1;
+        if (!sc.lower) CU(cudaMalloc(&sc.lower, (size_t)(sc.max_bases / 32 + 2) * 4));
+        lower_mask_kernel<<<grid_for(n_words, 256), 256, 0, st>>>((const uint8_t*)d_ascii, n_bases, sc.lower, n_words); LAUNCHED();
+        if (out32) case_fixup_kernel<int32_t><<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, sc.n_out, sc.lower, (int32_t*)d_out);
+        else case_fixup_kernel<int64_t><<<grid_for(n_reads, 256), 256, 0, st>>>(d_offsets, n_reads, (int)ix->k, sc.n_out, sc.lower, (int64_t*)d_out);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -1166,7 +1181,7 @@ static int query_host_impl(sbwt_gpu_session* s, const char* ascii, const int64_t
     if (n_reads == 0) return 0;
     if (!ascii || !off || !out) return set_error("null buffer");
     if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
-    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
+    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT && case_mode != SBWT_GPU_CASE_API) return set_error("unknown case mode %d", case_mode);
     if (mode == SBWT_GPU_MODE_STREAMING && !s->idx->has_sgs) return set_error("Error: streaming search support not built");
     DeviceGuard guard(s->idx->device);
     const int rc = query_host_body(s, ascii, off, n_reads, mode, case_mode, out, out32);
@@ -1432,7 +1447,7 @@ extern "C" int sbwt_gpu_query_host_hits(sbwt_gpu_session* s, const char* ascii, 
     if (n_reads == 0) return 0;
     if (!ascii || !off || !hit_mask) return set_error("null buffer");
     if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
-    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
+    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT && case_mode != SBWT_GPU_CASE_API) return set_error("unknown case mode %d", case_mode);
     if (mode == SBWT_GPU_MODE_STREAMING && !s->idx->has_sgs) return set_error("Error: streaming search support not built");
     if (hits && (s->idx->n_nodes >= (1ll << 31) || s->idx->view.wide))
         return set_error("32-bit hit values need an index with fewer than 2^31 columns (this one has %lld); pass hits = NULL for the membership bitmap alone",
@@ -1617,7 +1632,7 @@ extern "C" int sbwt_gpu_query_host_text(sbwt_gpu_session* s, const char* ascii, 
     if (n_reads == 0) return 0;
     if (!ascii || !off || !sink) return set_error("null argument");
     if (mode != SBWT_GPU_MODE_SEARCH && mode != SBWT_GPU_MODE_STREAMING) return set_error("unknown mode %d", mode);
-    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT) return set_error("unknown case mode %d", case_mode);
+    if (case_mode != SBWT_GPU_CASE_UPPER && case_mode != SBWT_GPU_CASE_EXACT && case_mode != SBWT_GPU_CASE_API) return set_error("unknown case mode %d", case_mode);
     if (mode == SBWT_GPU_MODE_STREAMING && !s->idx->has_sgs) return set_error("Error: streaming search support not built");
     DeviceGuard guard(s->idx->device);
     const int rc = query_host_text_body(s, ascii, off, n_reads, mode, case_mode, sink, user, n_lookups);

@@ -233,12 +233,66 @@ def case_f4(man, name, queries, seed):
     man.setdefault(name, {})["f4"] = {"partial": len(part), "forward": len(fwd), "get_kmer": len(kmers), "export_md5": out["export_md5"]}
 
 
+def case_mixed(man, name, queries, seed):
+    """The direct API on raw mixed-case bytes: `sbwt_ref api` = SBWT::streaming_search(const char*, len) and the search()
+    loop on reads in which bases and runs of bases were lower-cased (SBWT.hh:427 takes bytes as they are, SBWT.hh:565
+    upper-cases the new character of a streaming step). Written to <name>/mixed_case.txt (one read per line),
+    mixed_case.streaming.txt and mixed_case.search.txt (one result vector per line)."""
+    d = os.path.join(HERE, name)
+    idx = os.path.join(d, "index.sbwt")
+    rng = np.random.default_rng(seed)
+    reads = []
+    cur = []
+    for line in open(os.path.join(d, queries), "rb").read().split(b"\n"):
+        if line.startswith(b">"):
+            if cur:
+                reads.append(b"".join(cur))
+            cur = []
+        elif line:
+            cur.append(line)
+    if cur:
+        reads.append(b"".join(cur))
+    out = []
+    for r in reads[:200]:
+        a = np.frombuffer(r, np.uint8).copy()
+        mode = rng.integers(0, 4)
+        if mode == 0:      # single bases
+            m = rng.random(a.size) < 0.02
+        elif mode == 1:    # one run
+            m = np.zeros(a.size, bool)
+            if a.size > 10:
+                s0 = int(rng.integers(0, a.size - 5)); m[s0:s0 + int(rng.integers(1, 40))] = True
+        elif mode == 2:    # the first base(s) only: the first k-mer misses, the rest streams on or restarts
+            m = np.zeros(a.size, bool); m[: int(rng.integers(1, 3))] = True
+        else:              # all lower case
+            m = np.ones(a.size, bool)
+        up = (a >= 65) & (a <= 90)
+        a[m & up] += 32
+        out.append(a.tobytes())
+    text = b"\n".join(out) + b"\n"
+    open(os.path.join(d, "mixed_case.txt"), "wb").write(text)
+    st = oracle.ref_run("api", "-i", idx, stdin=text).stdout
+    se = oracle.ref_run("api", "-i", idx, "--no-streaming", stdin=text).stdout
+    open(os.path.join(d, "mixed_case.streaming.txt"), "wb").write(st)
+    open(os.path.join(d, "mixed_case.search.txt"), "wb").write(se)
+    man.setdefault(name, {})["mixed_case"] = {"reads": len(out), "streaming_md5": hashlib.md5(st).hexdigest(), "search_md5": hashlib.md5(se).hexdigest(),
+                                              "differ": st != se}
+
+
+MIXED_CASES = [("small_k31", "reads.fna", 31), ("small_k8_p0", "reads.fna", 32), ("small_k63_rc", "reads.fna", 33)]
 F4_CASES = [("cli_k6", "queries.fna", 21), ("small_k31", "reads.fna", 22), ("small_k63_rc", "reads.fna", 23), ("small_k8_p0", "reads.fna", 24)]
 
 
 def main():
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     oracle.build(with_ref=True)
+    if "--only-mixed" in sys.argv:  # add the mixed-case fixtures to an existing set
+        man = json.load(open(os.path.join(HERE, "MANIFEST.json")))
+        for name, q, seed in MIXED_CASES:
+            case_mixed(man, name, q, seed)
+        with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
+            json.dump(man, f, indent=1, sort_keys=True)
+        return
     if "--only-f4" in sys.argv:  # add the f4.json fixtures to an existing set
         man = json.load(open(os.path.join(HERE, "MANIFEST.json")))
         for name, q, seed in F4_CASES:
@@ -256,6 +310,8 @@ def main():
         case_c1(man, tmp)
         for name, q, seed in F4_CASES:
             case_f4(man, name, q, seed)
+        for name, q, seed in MIXED_CASES:
+            case_mixed(man, name, q, seed)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:

@@ -133,7 +133,8 @@ def test_cpp_mirror_surface(tmp_path):
     name = "small_k31"
     ref = open(golden(name, "input.fna"), "rb").read().split(b"\n")
     genome = b"".join(x for x in ref[1:400] if not x.startswith(b">"))
-    read = genome[1000:1100] + b"N" + genome[1101:1180]
+    # (mixed case on purpose: the mirror's streaming_search / search take raw bytes like the reference's, SBWT.hh:427,565)
+    read = genome[1000:1060] + genome[1060:1064].lower() + genome[1064:1100] + b"N" + genome[1101:1180]
     out = str(tmp_path / "re.sbwt")
     r = subprocess.run([exe, golden(name, "index.sbwt"), out, read.decode()], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -141,15 +142,18 @@ def test_cpp_mirror_surface(tmp_path):
     orc = oracle.OracleIndex(golden(name, "index.sbwt"))
     a, off = synth.ragged_to_batch([read])
     want = orc.query_batch(a, off, streaming=True)
+    want_search = orc.query_batch(a, off, streaming=False)
+    assert (want != want_search).any() and (want[30:34] >= 0).all() and (want_search[30:61] == -1).all()
     assert [int(x) for x in lines["streaming"].split()] == want.tolist()
-    assert [int(x) for x in lines["search"].split()] == want.tolist()
+    assert [int(x) for x in lines["search"].split()] == want_search.tolist()
     assert [int(x) for x in lines["rebuilt_streaming"].split()] == want.tolist()
     assert lines["header"].split() == [str(orc.n_nodes), str(orc.n_kmers), "31", "8", "1"] + [str(c) for c in orc.C_array]
     assert lines["interval"].split() == [str(want[0]), str(want[0])] and want[0] >= 0
     pl, pr, plen = (int(x) for x in lines["partial"].split())
     assert plen == 100 and pl <= pr  # the walk from the full interval stops at the N
     fw = [int(x) for x in lines["forward"].split()]
-    assert fw[-1] == -1 and fw[:-1] == [int(want[i + 1]) if want[i] >= 0 else -2 for i in range(len(fw) - 1)]
+    k = 31  # (forward() is case-sensitive like rank(): a lower-case character has no edge)
+    assert fw[-1] == -1 and fw[:-1] == [(-1 if read[i + k:i + k + 1].islower() else int(want[i + 1])) if want[i] >= 0 else -2 for i in range(len(fw) - 1)]
     assert [int(x) for x in lines["rank"].split()] == [orc.rank(orc.n_nodes, "A"), orc.rank(orc.n_nodes // 2, "G"), 0]
     assert lines["rebuilt_same_C"] == "1" and lines["rebuilt_same_precalc"] == "1"
     assert "incompatible version of SBWT" in lines["version_error"]

@@ -141,6 +141,34 @@ def test_case_exact_mode_matches_search_api():
     assert (want != parse_expected(open(golden(name, "expected.txt"), "rb").read())[0]).any()  # the fixture has lower case
 
 
+@pytest.mark.parametrize("name", ["small_k31", "small_k8_p0", "small_k63_rc"])
+def test_case_api_mode_matches_the_reference_on_mixed_case(name):
+    """CASE_API = the direct API on raw bytes: MODE_STREAMING reproduces SBWT::streaming_search(const char*, len) on
+    mixed-case reads (a lower-case base is a miss in a from-scratch search, accepted as the new character of a streaming
+    step), MODE_SEARCH the search() loop; expected vectors written by the reference's own methods (`sbwt_ref api`).
+    Dense, int32 and hits-only results, whole-batch and chunked sessions."""
+    reads = open(golden(name, "mixed_case.txt"), "rb").read().split(b"\n")[:-1]
+    want = {}
+    for kind in ("streaming", "search"):
+        rows = open(golden(name, f"mixed_case.{kind}.txt"), "rb").read().split(b"\n")[:-1]
+        want[kind] = np.array([int(x) for row in rows for x in row.split()], dtype=np.int64)
+    a, off = synth.ragged_to_batch(reads)
+    idx = S.Index(golden(name, "index.sbwt"))
+    for max_bases, max_reads in ((a.size, len(reads)), (max(len(r) for r in reads) * 3, 7)):
+        ses = S.Session(idx, max_bases, max_reads)
+        np.testing.assert_array_equal(ses.query_host(a, off, S.MODE_STREAMING, S.CASE_API), want["streaming"])
+        np.testing.assert_array_equal(ses.query_host(a, off, S.MODE_SEARCH, S.CASE_API), want["search"])
+        np.testing.assert_array_equal(ses.query_host(a, off, S.MODE_SEARCH, S.CASE_EXACT), want["search"])
+        np.testing.assert_array_equal(ses.query_host_i32(a, off, S.MODE_STREAMING, S.CASE_API).astype(np.int64), want["streaming"])
+        mask, hits, n = ses.query_host_hits(a, off, S.MODE_STREAMING, S.CASE_API)
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[: want["streaming"].size].astype(bool)
+        got = np.full(want["streaming"].size, -1, dtype=np.int64)
+        got[bits] = hits
+        np.testing.assert_array_equal(got, want["streaming"])
+        ses.close()
+    idx.close()
+
+
 def test_index_create_from_arrays_and_violated_invariant(tmp_path):
     """sbwt_gpu_index_create (the SBWT(A,C,G,T,...) constructor path) and the literal walk-back:
     clearing suffix-group marks makes columns with edges non-starts, so the one-sector shortcut

@@ -162,3 +162,26 @@ def test_other_queries_against_the_reference(name):
         members = cols[at:j + 1].upper().replace("$", "")
         assert [idx.contains(pos, c) for c in "ACGT"] == [c in members for c in "ACGT"]
         pos, at = pos + 1, j + 1
+
+
+def _mixed_case(name):
+    reads = open(golden(name, "mixed_case.txt"), "rb").read().split(b"\n")[:-1]
+    want = {}
+    for kind in ("streaming", "search"):
+        rows = open(golden(name, f"mixed_case.{kind}.txt"), "rb").read().split(b"\n")[:-1]
+        assert len(rows) == len(reads)
+        want[kind] = np.array([int(x) for row in rows for x in row.split()], dtype=np.int64)
+    return reads, want
+
+
+@pytest.mark.parametrize("name", ["small_k31", "small_k8_p0", "small_k63_rc"])
+def test_mixed_case_direct_api_against_the_reference(name):
+    """Raw mixed-case bytes through the direct API: the oracle's streaming_search upper-cases the new character of a
+    streaming step only (SBWT.hh:565), its search() takes bytes as they are (SBWT.hh:427) -- against the vectors the
+    reference's own methods returned (`sbwt_ref api`, tests/golden/make_golden.py --only-mixed)."""
+    reads, want = _mixed_case(name)
+    a, off = synth.ragged_to_batch(reads)
+    orc = oracle.OracleIndex(golden(name, "index.sbwt"))
+    np.testing.assert_array_equal(orc.query_batch(a, off, streaming=True), want["streaming"])
+    np.testing.assert_array_equal(orc.query_batch(a, off, streaming=False), want["search"])
+    assert (want["streaming"] != want["search"]).any()  # the fixture exercises the difference
