@@ -10,7 +10,7 @@
 // scope.
 //
 // Differences a caller can observe:
-//   * k <= 64 (the reference's search has no limit); a larger k is refused when the index is created.
+//   * none in the answers. (k > 64 is answered by the literal kernels of long_kmer_kernels.cuh: correct, not tuned.)
 //   * streaming_search(const char*, len) gives the reference's answer, mixed case included (SBWT_GPU_CASE_API;
 //     tests/golden/*/mixed_case.*, written by the reference's own method) -- except on an index that violates the
 //     edge invariant (only hand-made files do), where a lower-case base is a miss everywhere (CASE_EXACT).

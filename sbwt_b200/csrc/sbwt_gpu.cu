@@ -20,6 +20,7 @@
 #include "device_index.cuh"
 #include "format_kernels.cuh"
 #include "host_widen.hpp"
+#include "long_kmer_kernels.cuh"
 #include "query_kernels.cuh"
 #include "sbwt_file.hpp"
 #include "walk_kernel.cuh"
@@ -271,7 +272,6 @@ static int index_create_impl(const uint64_t* const bits[4], const uint64_t* sgs,
     if (sbwt_gpu_device_count() <= 0) return set_error("no CUDA device available: the SBWT GPU query path has no CPU fallback");
     if (device < 0 || device >= sbwt_gpu_device_count()) return set_error("invalid device %d", device);
     if (n_nodes < 1 || k < 1) return set_error("invalid index: n_nodes=%lld k=%lld", (long long)n_nodes, (long long)k);
-    if (k > 64) return set_error("k = %lld is not supported by this build (k <= 64)", (long long)k);
     if (p < 0 || p > k || p > 14) return set_error("precalc length %lld is not supported (0 <= p <= min(k,14))", (long long)p);
     DeviceGuard guard(device);
     sbwt_gpu_index* ix = new sbwt_gpu_index();
@@ -899,6 +899,18 @@ static int launch_walk(const sbwt_gpu_index* ix, WalkParams& P, bool streaming, 
     P.probe_stride = streaming ? ix->probe_stride : 0u;
     const bool wide = ix->view.wide;
     cudaError_t e;
+    if (ix->k > 64) { // no register-held k-mer window: the literal kernels of long_kmer_kernels.cuh
+        const bool o32 = P.out32 != nullptr;
+        const unsigned grid = (unsigned)ix->sm_count * 8u;
+        const uint32_t k = (uint32_t)ix->k;
+#define LONGK(W_, O_) do { if (streaming) long_streaming_kernel<W_, O_><<<grid * 2u, 128, 0, st>>>(P, k); else long_search_kernel<W_, O_><<<grid, 256, 0, st>>>(P, k); } while (0)
+        if (wide) { if (o32) LONGK(true, true); else LONGK(true, false); }
+        else { if (o32) LONGK(false, true); else LONGK(false, false); }
+#undef LONGK
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return 0;
+    }
     CU(cudaMemsetAsync(P.cursor, 0, 8, st));
     const bool k64 = ix->k > 32;
 #define WALK(S_, W_) e = k64 ? launch_walk_t<S_, W_, 2>(P, count, ix->sm_count, st) : launch_walk_t<S_, W_, 1>(P, count, ix->sm_count, st)

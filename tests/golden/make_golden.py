@@ -167,6 +167,37 @@ def case_small(man, tmp, name, ref, k, p, add_rc, n_reads, seed):
                  "expected_md5": md5(os.path.join(d, "expected.txt")), "builder_equals_reference_inmem": True}
 
 
+def case_long_k(man, tmp, name, ref, k, p, add_rc, n_reads, seed):
+    """k > 64: index built AND answered by the reference itself (the driver compiled with MAX_KMER_LENGTH=255,
+    oracle/Makefile target ref255; the repo's test builder stops at k = 64)."""
+    ref255 = os.path.join(os.path.dirname(oracle.REF_BIN), "sbwt_ref_k255")
+    subprocess.run(["make", "-s", "-C", os.path.dirname(os.path.dirname(oracle.REF_BIN)), "ref255"], check=True)
+    d = os.path.join(HERE, name)
+    os.makedirs(d, exist_ok=True)
+    fa = os.path.join(d, "input.fna")
+    synth.write_fasta(fa, [ref[i] for i in range(ref.shape[0])], line_width=70)
+    idx = os.path.join(d, "index.sbwt")
+    args = [ref255, "build-inmem", "-i", fa, "-o", idx, "-k", str(k), "-p", str(p)]
+    if add_rc:
+        args.append("--add-reverse-complements")
+    subprocess.run(args, check=True, capture_output=True)
+    rng = np.random.default_rng(seed)
+    reads = [r for r in ragged_reads(rng, ref, n_reads, k, add_rc) if len(r) > 0]  # (SeqIO rejects empty FASTA records)
+    synth.write_fasta(os.path.join(d, "reads.fna"), reads)
+    subprocess.run([ref255, "search", "-i", idx, "-q", os.path.join(d, "reads.fna"), "-o", os.path.join(d, "expected.txt")], check=True, capture_output=True)
+    ns = os.path.join(tmp, name + ".ns.sbwt")
+    strip_streaming_support(idx, ns)
+    out = os.path.join(tmp, "o.txt")
+    subprocess.run([ref255, "search", "-i", ns, "-q", os.path.join(d, "reads.fna"), "-o", out], check=True, capture_output=True)
+    assert same(out, os.path.join(d, "expected.txt")), "reference: streaming != per-k-mer search"
+    man[name] = {"index_md5": md5(idx), "k": k, "precalc_k": p, "add_rc": add_rc, "n_reads": len(reads),
+                 "expected_md5": md5(os.path.join(d, "expected.txt")), "built_by": "the reference's in-memory constructor (sbwt_ref_k255)"}
+
+
+LONG_K_CASES = [("long_k80", dict(k=80, p=8, add_rc=False, n_reads=160, seed=41), (3, 2500, 40)),
+                ("long_k255_rc", dict(k=255, p=6, add_rc=True, n_reads=120, seed=43), (2, 2200, 42))]
+
+
 def case_c1(man, tmp):
     """BASELINE config 1: example_data/coli3.fna k=30 (defaults: p=8, streaming support) x example_data/queries.fastq."""
     d = os.path.join(HERE, "c1")
@@ -286,6 +317,17 @@ F4_CASES = [("cli_k6", "queries.fna", 21), ("small_k31", "reads.fna", 22), ("sma
 def main():
     assert os.path.isdir(REF), "run in the build container (needs /root/reference)"
     oracle.build(with_ref=True)
+    if "--only-long-k" in sys.argv:  # add the k > 64 fixtures to an existing set
+        man = json.load(open(os.path.join(HERE, "MANIFEST.json")))
+        tmp = tempfile.mkdtemp(prefix="golden_")
+        try:
+            for name, kw, (nc, L, sd) in LONG_K_CASES:
+                case_long_k(man, tmp, name, synth.random_contigs(nc, L, seed=sd), **kw)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
+            json.dump(man, f, indent=1, sort_keys=True)
+        return
     if "--only-mixed" in sys.argv:  # add the mixed-case fixtures to an existing set
         man = json.load(open(os.path.join(HERE, "MANIFEST.json")))
         for name, q, seed in MIXED_CASES:
@@ -312,6 +354,8 @@ def main():
             case_f4(man, name, q, seed)
         for name, q, seed in MIXED_CASES:
             case_mixed(man, name, q, seed)
+        for name, kw, (nc, L, sd) in LONG_K_CASES:
+            case_long_k(man, tmp, name, synth.random_contigs(nc, L, seed=sd), **kw)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:

@@ -323,12 +323,39 @@ def test_search_table_lengths(tmp_path):
         idx.set_table_length(10)
 
 
-def test_k_above_64_is_refused(tmp_path):
-    d = read_sbwt(golden("small_k63_rc", "index.sbwt"))
-    arrays = dict(bits=[w for _, w in d["bits"]], sgs=d["sgs"][1], C=d["C"], precalc=d["precalc"].reshape(-1), precalc_k=8,
-                  n_nodes=d["n_nodes"], n_kmers=d["n_kmers"], k=65)
-    with pytest.raises(S.SbwtGpuError, match="not supported"):
-        S.Index(arrays=arrays)
+@pytest.mark.parametrize("name", ["long_k80", "long_k255_rc"])
+@pytest.mark.parametrize("wide", [False, True])
+def test_k_above_64(name, wide, tmp_path, monkeypatch):
+    """k > 64 (the reference's search has no limit): indexes built and answered by the reference itself with k = 80 and
+    k = 255 (tests/golden/make_golden.py --only-long-k), through the literal kernels of long_kmer_kernels.cuh: both modes,
+    dense / int32 / hits-only results, the device formatter's text, a chunked session, the forced-wide layout, and the
+    per-k-mer path alone on a file without streaming support."""
+    if wide:
+        monkeypatch.setenv("SBWT_B200_FORCE_WIDE", "3")
+    expected = open(golden(name, "expected.txt"), "rb").read()
+    vals, counts = parse_expected(expected)
+    reads = read_fasta_reads(golden(name, "reads.fna"))
+    a, off = synth.ragged_to_batch(reads)
+    idx = S.Index(golden(name, "index.sbwt"))
+    assert idx.k == MAN[name]["k"] > 64
+    for max_bases, max_reads in ((a.size, len(reads)), (max(len(r) for r in reads) * 2, 5)):
+        ses = S.Session(idx, max_bases, max_reads)
+        for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+            np.testing.assert_array_equal(ses.query_host(a, off, mode), vals)
+        if not wide:
+            np.testing.assert_array_equal(ses.query_host_i32(a, off, S.MODE_STREAMING).astype(np.int64), vals)
+            mask, hits, n = ses.query_host_hits(a, off, S.MODE_SEARCH)
+            bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[: vals.size].astype(bool)
+            assert n == int((vals >= 0).sum()) and np.array_equal(bits, vals >= 0) and np.array_equal(hits, vals[vals >= 0])
+        text, n_lookups = ses.query_host_text(a, off, S.MODE_STREAMING)
+        assert text == expected and n_lookups == vals.size
+        ses.close()
+    idx.close()
+    ns = str(tmp_path / "ns.sbwt")
+    strip_streaming_support(golden(name, "index.sbwt"), ns)
+    np.testing.assert_array_equal(run_both(ns, reads, modes=(S.MODE_SEARCH,))[S.MODE_SEARCH], vals)
+    with pytest.raises(S.SbwtGpuError, match="streaming search support not built"):
+        run_both(ns, reads, modes=(S.MODE_STREAMING,))
 
 
 def test_scale_properties_config2_like(tmp_path):

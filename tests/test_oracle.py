@@ -185,3 +185,19 @@ def test_mixed_case_direct_api_against_the_reference(name):
     np.testing.assert_array_equal(orc.query_batch(a, off, streaming=True), want["streaming"])
     np.testing.assert_array_equal(orc.query_batch(a, off, streaming=False), want["search"])
     assert (want["streaming"] != want["search"]).any()  # the fixture exercises the difference
+
+
+@pytest.mark.parametrize("name", ["long_k80", "long_k255_rc"])
+def test_k_above_64_against_the_reference(name):
+    """k = 80 and k = 255: index built and queries answered by the reference's own classes (driver compiled with
+    MAX_KMER_LENGTH=255); the oracle reproduces the text in both modes."""
+    expected = open(golden(name, "expected.txt"), "rb").read()
+    vals, counts = parse_expected(expected)
+    reads = read_fasta_reads(golden(name, "reads.fna"))
+    a, off = synth.ragged_to_batch(reads)
+    orc = oracle.OracleIndex(golden(name, "index.sbwt"))
+    assert orc.k > 64
+    for streaming in (True, False):
+        got = orc.query_batch(a, off, streaming=streaming)
+        np.testing.assert_array_equal(got, vals)
+    assert oracle.format_lines(vals, counts) == expected
