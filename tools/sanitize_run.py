@@ -45,3 +45,27 @@ for name, q, e in cases:
         assert np.array_equal(idx.forward(f4["forward"]["nodes"], f4["forward"]["chars"].encode()), f4["forward"]["out"])
     idx.close()
     print("ok", name, vals.size, "results", flush=True)
+
+# the direct API's mixed-case mode (case_fixup_kernel, lower_mask_kernel) and k > 64 (long_kmer_kernels.cuh)
+name = "small_k31"
+reads = open(golden(name, "mixed_case.txt"), "rb").read().split(b"\n")[:-1]
+want = np.array([int(x) for row in open(golden(name, "mixed_case.streaming.txt"), "rb").read().split(b"\n")[:-1] for x in row.split()], dtype=np.int64)
+a, off = synth.ragged_to_batch(reads)
+idx = S.Index(golden(name, "index.sbwt"))
+ses = S.Session(idx, max(len(r) for r in reads) * 3, 7)
+assert np.array_equal(ses.query_host(a, off, S.MODE_STREAMING, S.CASE_API), want)
+assert np.array_equal(ses.query_host_i32(a, off, S.MODE_STREAMING, S.CASE_API).astype(np.int64), want)
+ses.close()
+idx.close()
+print("ok mixed case", want.size, "results", flush=True)
+name = "long_k80"
+reads = read_fasta_reads(golden(name, "reads.fna"))
+vals, _ = parse_expected(open(golden(name, "expected.txt"), "rb").read())
+a, off = synth.ragged_to_batch(reads)
+idx = S.Index(golden(name, "index.sbwt"))
+ses = S.Session(idx, max(len(r) for r in reads) * 2, 5)
+for mode in (S.MODE_STREAMING, S.MODE_SEARCH):
+    assert np.array_equal(ses.query_host(a, off, mode), vals), (name, mode)
+ses.close()
+idx.close()
+print("ok", name, vals.size, "results", flush=True)
