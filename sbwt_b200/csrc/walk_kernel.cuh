@@ -416,7 +416,8 @@ struct WalkShared {
 // LAY: the layout rank steps are answered from (device_index.cuh); the compact ones serve narrow, non-LITERAL kernels,
 // and a block flagged there (some column with no edge or several) is answered from the classic sectors.
 template <bool STREAMING, bool WIDE, bool COUNT, bool OUT32, int KW, bool LITERAL, int LAY>
-__global__ void __launch_bounds__(kWalkThreads, WalkBlocks<STREAMING, WIDE, LAY>::value) walk_kernel(const WalkParams P) {
+// (the COUNT instantiations -- one counted launch per bench run, never on the product path -- get 128 registers: no spills)
+__global__ void __launch_bounds__(kWalkThreads, COUNT ? 2 : WalkBlocks<STREAMING, WIDE, LAY>::value) walk_kernel(const WalkParams P) {
     static_assert(STREAMING || !LITERAL, "LITERAL is a streaming-mode variant");
     static_assert(LAY == LAY_CLASSIC || (!WIDE && !LITERAL), "the compact layouts serve narrow indexes that keep the edge invariant");
     typedef typename std::conditional<WIDE, int64_t, uint32_t>::type pos_t;
