@@ -417,6 +417,11 @@ def measure(name: str, args, env: dict, headline: bool) -> dict:
                                    f"(kernel sources sha256 {tr.get('kernel_src_sha256_12')}; this run's {env['kernel_src_sha']}"
                                    + ("" if tr.get("kernel_src_sha256_12") == env["kernel_src_sha"] else ": DIFFERENT KERNEL SOURCES") + ")") if tr else None,
                 "traffic_over_algorithmic": (tr["bytes"] / (stats.index_sectors * 32)) if tr else None}
+    if tr and tr.get("tex_sector_reads") and ceil.get(level) and level == "l2":
+        # every 32-byte sector the kernel requests through L1TEX (index sectors + table rows + code words + work items), from the same capture
+        # as `traffic`: the SM's request-rate ceiling counts them all, the algorithmic figure above only the index sectors
+        roofline["tex_sector_reads"] = int(tr["tex_sector_reads"])
+        roofline["frac_of_level_ceiling_all_requests"] = tr["tex_sector_reads"] / (w_ms * 1e-3) / ceil[level]
     rec = {"workload": f"{name}: {w['desc']}", "value": value, "unit": "lookups/s", "ms_per_step": ms_per_step, "steps": steps,
            "lookups_per_step_per_gpu": int(n_out), "hit_rate": hits_gpu / max(1, n_out), "n_nodes": int(idx.n_nodes), "k": k,
            "index_device_bytes": int(idx.device_bytes), "l2_set_aside_bytes": int(idx.l2_set_aside),
@@ -569,8 +574,41 @@ def cli_e2e(args, env: dict) -> dict | None:
             m = re.search(r"queries: (\d+) in ([\d.]+) s .*?: ([\d.]+) lookups/s", r.stderr)
             out[key] = ({"lookups_per_s": float(m.group(3)), "seconds": float(m.group(2)), "lookups": int(m.group(1))} if (r.returncode == 0 and m)
                         else {"error": r.stderr[-300:]})
+        # compressed INPUT (the reads a sequencer hands over): 2 M reads as one gzip stream (one inflate thread: a plain gzip stream
+        # cannot be entered in the middle) and as a BGZF container (members inflated in parallel), both written with zlib level 1
+        n_gz = min(int(K["reads"].shape[0]), 2_000_000)
+        qs = os.path.join(CACHE, f"cli_reads_gz_{os.getpid()}.fna")
+        write_sample_fasta(qs, K["reads"][:n_gz])
+        raw = open(qs, "rb").read()
+        os.remove(qs)
+        gz, bg = qs + ".gz", qs[:-4] + "_bgzf.fna.gz"  # (the format is read off the name, as in the reference: .fna[.gz])
+        import struct
+        import zlib
+        with open(gz, "wb") as f:
+            c = zlib.compressobj(1, zlib.DEFLATED, 31)
+            f.write(c.compress(raw) + c.flush())
+        with open(bg, "wb") as f:
+            for a0 in list(range(0, len(raw), 0xFF00)) + [None]:
+                chunk = b"" if a0 is None else raw[a0:a0 + 0xFF00]
+                c = zlib.compressobj(1, zlib.DEFLATED, -15)
+                body = c.compress(chunk) + c.flush()
+                f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(body) + 8 - 1))
+                f.write(body + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+        del raw
+        try:
+            for key, path_in in (("gzip_input", gz), ("bgzf_input", bg)):
+                r = subprocess.run([exe, "search", "-i", K["path"], "-q", path_in, "-o", "/dev/null", "--threads", str(out["threads"])],
+                                   capture_output=True, text=True, timeout=600)
+                m = re.search(r"queries: (\d+) in ([\d.]+) s .*?: ([\d.]+) lookups/s", r.stderr)
+                out[key] = ({"lookups_per_s": float(m.group(3)), "seconds": float(m.group(2)), "lookups": int(m.group(1)), "reads": n_gz,
+                             "compressed_bytes": os.path.getsize(path_in)} if (r.returncode == 0 and m) else {"error": r.stderr[-300:]})
+        finally:
+            for f_ in (gz, bg):
+                if os.path.exists(f_):
+                    os.remove(f_)
     finally:
-        os.remove(q)
+        if os.path.exists(q):
+            os.remove(q)
     return out
 
 

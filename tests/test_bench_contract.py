@@ -69,5 +69,6 @@ def test_our_arm_prints_the_contract_line_with_parity_and_legs():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["hits_only"]["value"] > 0 and e["bitmap_only"]["value"] > 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["cpu_model"]
     assert d["cli_e2e"]["plain"]["lookups"] == d["lookups_per_step_per_gpu"]
+    assert d["cli_e2e"]["gzip_input"]["lookups"] == d["cli_e2e"]["bgzf_input"]["lookups"] > 0
     w = d["workloads"]["c2q"]
     assert w["value"] > 0 and w["parity"]["weighted_checksum_match"] and w["roofline"]["kernel_ms"] > 0

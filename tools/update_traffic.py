@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """profiles/traffic.json from the ncu captures of one GPU visit (traffic_<workload>.csv: dram__bytes_read.sum,
-dram__bytes_write.sum, lts__t_sector_hit_rate.pct of one walk_kernel launch), labelled with the sha of the kernel sources.
+dram__bytes_write.sum, lts__t_sector_hit_rate.pct, lts__t_sectors_srcunit_tex_op_read.sum of one walk_kernel launch), labelled with the sha of the kernel sources.
 usage: python tools/update_traffic.py gpurun_out/r02z "profiles/r02z_dram_traffic.txt" """
 import csv, hashlib, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,5 +23,7 @@ for wl in ("c2", "c3", "c4s", "c5s", "c4", "c5"):
     t[wl] = {"bytes": int(m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]),
              "source": f"{source} (ncu; L2 sector hit rate {m.get('lts__t_sector_hit_rate.pct', float('nan')):.1f} %)",
              "kernel_src_sha256_12": sha}
+    if "lts__t_sectors_srcunit_tex_op_read.sum" in m:  # every sector the kernel requested through L1TEX
+        t[wl]["tex_sector_reads"] = int(m["lts__t_sectors_srcunit_tex_op_read.sum"])
     print(wl, t[wl])
 json.dump(t, open(path, "w"), indent=1)
