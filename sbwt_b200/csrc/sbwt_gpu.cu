@@ -498,9 +498,37 @@ extern "C" int sbwt_gpu_index_set_table_length(sbwt_gpu_index* ix, int tp) {
         if (wide) CU(cudaMemcpy(ix->d_table, ix->d_precalc, np * 16, cudaMemcpyDeviceToDevice));
         else { table_compact_kernel<<<grid_for(np, 256), 256>>>((const int64_t*)ix->d_precalc, np, (uint2*)ix->d_table); LAUNCHED(); }
     } else {
-        if (wide) precalc_kernel<true, false><<<grid_for(np, 256), 256>>>(v, tp, ix->d_table);
-        else precalc_kernel<false, true><<<grid_for(np, 256), 256>>>(v, tp, ix->d_table);
-        LAUNCHED();
+        // level by level from a short table walked from scratch (table_extend_kernel); the two previous levels live in scratch
+        // buffers of 1/4 + 1/16 of the table's size -- without room for them every row is walked from scratch as before
+        const int row_bytes = wide ? 16 : 8, p0 = std::min(tp, 8);
+        void* tmp[2] = {nullptr, nullptr};
+        bool levels = tp >= 15; // (shorter tables are quicker from scratch than the scratch buffers take to allocate: profiles/r03j)
+        if (levels) {
+            if (cudaMalloc(&tmp[0], (size_t)(np >> 2) * row_bytes) != cudaSuccess) { cudaGetLastError(); levels = false; }
+            else if (tp - 2 >= p0 && cudaMalloc(&tmp[1], (size_t)(np >> 4) * row_bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(tmp[0]); tmp[0] = nullptr; levels = false; }
+        }
+        if (!levels) {
+            if (wide) precalc_kernel<true, false><<<grid_for(np, 256), 256>>>(v, tp, ix->d_table);
+            else precalc_kernel<false, true><<<grid_for(np, 256), 256>>>(v, tp, ix->d_table);
+            LAUNCHED();
+        } else {
+            // level q lands in: the table itself for q == tp, else the scratch buffer of its parity counted from the top
+            auto buf = [&](int q) -> void* { return q == tp ? ix->d_table : tmp[(tp - 1 - q) & 1]; };
+            const int64_t n0 = 1ll << (2 * p0);
+            if (wide) precalc_kernel<true, false><<<grid_for(n0, 256), 256>>>(v, p0, buf(p0));
+            else precalc_kernel<false, true><<<grid_for(n0, 256), 256>>>(v, p0, buf(p0));
+            LAUNCHED();
+            for (int q = p0 + 1; q <= tp; q++) {
+                const int64_t nq = 1ll << (2 * q);
+                if (wide) table_extend_kernel<true, false><<<grid_for(nq, 256), 256>>>(v, q, buf(q - 1), buf(q));
+                else table_extend_kernel<false, true><<<grid_for(nq, 256), 256>>>(v, q, buf(q - 1), buf(q));
+                LAUNCHED();
+            }
+        }
+        const cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(tmp[0]);
+        cudaFree(tmp[1]);
+        CU(e);
     }
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
