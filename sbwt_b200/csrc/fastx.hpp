@@ -335,7 +335,30 @@ class ParallelFastxReader {
 
     struct Line {
         size_t start, end; // [start, end): without the '\n'
+        bool header() const { return (end >> 63) != 0; } // the line begins with '>' (noted by the scan, while the byte is in cache)
+        size_t stop() const { return end & ~((size_t)1 << 63); }
     };
+    // scratch kept across batches (a 64 MB batch of short reads has millions of lines: allocating, zero-filling and
+    // page-faulting these arrays anew for every batch cost a third of the parser's time)
+    struct LineBuf {
+        std::unique_ptr<Line[]> p;
+        size_t cap = 0, n = 0;
+        void resize(size_t m) { // contents are not kept and not initialised
+            if (m > cap) { cap = m + m / 4 + 1024; p.reset(new Line[cap]); }
+            n = m;
+        }
+        size_t size() const { return n; }
+        Line* data() { return p.get(); }
+        const Line& operator[](size_t i) const { return p[i]; }
+    };
+    struct Rec {
+        size_t first_line, n_lines; // sequence lines
+        int64_t len;
+    };
+    mutable LineBuf lines_buf;
+    std::vector<Rec> recs_buf;
+    mutable std::vector<std::vector<size_t>> nl_buf;
+    double file_bytes_per_base = 1.5; // how much of the file a batch of max_bases covers: learnt from the previous batch
 
     template <typename F>
     void parallel_for(size_t n, F f) const {
@@ -349,9 +372,12 @@ class ParallelFastxReader {
 
     // complete lines of [from, to): every '\n' found ends one. Two parallel passes: collect the newline positions of every
     // slice, then write the lines of every slice at its prefix-summed place.
-    void scan_lines(size_t from, size_t to, std::vector<Line>& lines) const {
+    void scan_lines(size_t from, size_t to, LineBuf& lines) const {
         const size_t T = (size_t)std::max(1, threads);
-        std::vector<std::vector<size_t>> nl(T);
+        std::vector<std::vector<size_t>>& nl = nl_buf;
+        nl.resize(T);
+        for (auto& v : nl) v.clear();
+        const char* dend = data + to;
         parallel_for(to - from, [&](size_t a, size_t b, size_t t) {
             const char* p = data + from + a;
             const char* e = data + from + b;
@@ -359,16 +385,18 @@ class ParallelFastxReader {
             while (p < e) {
                 const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
                 if (!q) break;
-                nl[t].push_back((size_t)(q - data));
+                // bit 63: the line after this newline begins with '>' (its first byte is in the cache line just scanned)
+                nl[t].push_back((size_t)(q - data) | ((q + 1 < dend && q[1] == '>') ? (size_t)1 << 63 : 0));
                 p = q + 1;
             }
         });
-        std::vector<size_t> first(T + 1, 0), start(T, from); // first line index of slice t; start of its first line
-        size_t prev_start = from;
+        constexpr size_t HB = (size_t)1 << 63;
+        std::vector<size_t> first(T + 1, 0), start(T, from); // first line index of slice t; start of its first line (+ its header bit)
+        size_t prev_start = from | ((from < to && data[from] == '>') ? HB : 0);
         for (size_t t = 0; t < T; t++) {
             first[t + 1] = first[t] + nl[t].size();
             start[t] = prev_start;
-            if (!nl[t].empty()) prev_start = nl[t].back() + 1;
+            if (!nl[t].empty()) prev_start = ((nl[t].back() & ~HB) + 1) | (nl[t].back() & HB);
         }
         lines.resize(first[T]);
         Line* out = lines.data();
@@ -377,11 +405,11 @@ class ParallelFastxReader {
         const size_t* startp = start.data();
         parallel_for(T, [=](size_t a, size_t b, size_t) {
             for (size_t t = a; t < b; t++) {
-                size_t st = startp[t];
+                size_t st = startp[t]; // (bit 63: this line is a header)
                 Line* o = out + firstp[t];
                 for (size_t x : nlp[t]) {
-                    *o++ = Line{st, x};
-                    st = x + 1;
+                    *o++ = Line{st & ~HB, (x & ~HB) | (st & HB)};
+                    st = ((x & ~HB) + 1) | (x & HB);
                 }
             }
         });
@@ -458,13 +486,9 @@ public:
         if (max_reads <= 0 || max_bases <= 0) { ascii.clear(); return 0; }
         z_fill(1);
         if (cur >= size) { ascii.clear(); return 0; }
-        struct Rec {
-            size_t first_line, n_lines; // sequence lines
-            int64_t len;
-        };
-        std::vector<Line> lines;
-        std::vector<Rec> recs;
-        size_t window = (size_t)max_bases + (size_t)max_bases / 2 + ((size_t)1 << 20);
+        LineBuf& lines = lines_buf;
+        std::vector<Rec>& recs = recs_buf;
+        size_t window = (size_t)((double)max_bases * file_bytes_per_base) + ((size_t)1 << 20);
         bool anomaly = false;
         size_t next_cur = cur;
         for (;;) {
@@ -481,11 +505,11 @@ public:
             const size_t nl = lines.size();
             if (format == SeqFormat::FASTQ) {
                 while (i + 4 <= nl) {
-                    if (lines[i].end == lines[i].start || lines[i + 1].end == lines[i + 1].start) { anomaly = true; break; }
-                    recs.push_back(Rec{i + 1, 1, (int64_t)(lines[i + 1].end - lines[i + 1].start)});
+                    if (lines[i].stop() == lines[i].start || lines[i + 1].stop() == lines[i + 1].start) { anomaly = true; break; }
+                    recs.push_back(Rec{i + 1, 1, (int64_t)(lines[i + 1].stop() - lines[i + 1].start)});
                     bases += recs.back().len;
                     i += 4;
-                    next_cur = i < nl ? lines[i].start : lines[i - 1].end + 1;
+                    next_cur = i < nl ? lines[i].start : lines[i - 1].stop() + 1;
                     if ((int64_t)recs.size() >= max_reads || bases >= max_bases) { full = true; break; }
                 }
                 // a tail that is not a whole record (or lacks its last '\n') is the serial parser's business
@@ -495,14 +519,14 @@ public:
                     // line i is a header (the first byte of a record is '>' by construction)
                     size_t j = i + 1;
                     int64_t len = 0;
-                    bool bad = lines[i].end == lines[i].start; // cannot happen ('>' is there), kept for symmetry
-                    while (j < nl && data[lines[j].start] != '>') {
-                        if (lines[j].end == lines[j].start) { bad = true; break; }
-                        len += (int64_t)(lines[j].end - lines[j].start);
+                    bool bad = lines[i].stop() == lines[i].start; // cannot happen ('>' is there), kept for symmetry
+                    while (j < nl && !lines[j].header()) {
+                        if (lines[j].stop() == lines[j].start) { bad = true; break; }
+                        len += (int64_t)(lines[j].stop() - lines[j].start);
                         j++;
                     }
                     if (bad || (j < nl && j == i + 1)) { anomaly = true; break; } // empty line / empty sequence
-                    const size_t after = j < nl ? lines[j].start : lines[j - 1].end + 1;
+                    const size_t after = j < nl ? lines[j].start : lines[j - 1].stop() + 1;
                     if (j == nl && !(at_eof && after == size)) {
                         // the record may go on beyond the window; at the end of the file: unterminated last line
                         if (at_eof) anomaly = true;
@@ -538,11 +562,12 @@ public:
             for (size_t r = a; r < b; r++) {
                 char* o = out + off[r];
                 for (size_t l = R[r].first_line; l < R[r].first_line + R[r].n_lines; l++) {
-                    memcpy(o, d + L[l].start, L[l].end - L[l].start);
-                    o += L[l].end - L[l].start;
+                    memcpy(o, d + L[l].start, L[l].stop() - L[l].start);
+                    o += L[l].stop() - L[l].start;
                 }
             }
         });
+        if (offsets[n] > 0) file_bytes_per_base = std::min(8.0, std::max(1.0, 1.03 * (double)(next_cur - cur) / (double)offsets[n]));
         cur = next_cur;
         return (int64_t)n;
     }
