@@ -275,7 +275,7 @@ int sbwt_gpu_query_host_sharded(sbwt_gpu_session *const *sessions, int n_session
 /* Host half of the 32-bit result wire format (no device work): sbwt_gpu_query_host on an index with fewer
  * than 2^31 columns lets the kernel write int32, copies those over PCIe and sign-extends them into the
  * caller's int64 array with `threads` host threads (SBWT_B200_WIDEN_THREADS; default = hardware threads /
- * visible GPUs, at most 8; below 4 the int64 values are copied directly). This entry runs that widening
+ * GPUs of the job, at most 10; below 4 the int64 values are copied directly). This entry runs that widening
  * step alone: out[i] = in[i] for i < n. Values are what SBWT::search returns (SBWT.hh:390-415). */
 int sbwt_gpu_widen_i32(const int32_t *in, int64_t *out, int64_t n, int threads);
 /* Host half of the SPARSE result wire format (the default of sbwt_gpu_query_host / _i32 when host threads are

@@ -1113,7 +1113,7 @@ static void CUDART_CB widen_callback(void* p) { // stream callback: no CUDA call
 // How many host threads sign-extend int32 results into the caller's int64 array (0 = none: int64 values cross
 // PCIe). Default: the host's hardware threads divided by the GPUs THIS JOB drives -- LOCAL_WORLD_SIZE when a launcher
 // set it (one process per GPU), else the sessions alive in this process (one per device in sbwt_gpu_query_host_sharded)
-// -- at most 8; fewer than 4 cannot keep up with a PCIe 5 x16 link, so the plain int64 copy is used instead.
+// -- at most 10; fewer than 4 cannot keep up with a PCIe 5 x16 link, so the plain int64 copy is used instead.
 // (Round 1 divided by the VISIBLE devices: a single-GPU job on an 8-GPU host got 4 threads and lost 20 %.)
 static std::atomic<int> g_live_sessions{0};
 static void session_count(int delta) { g_live_sessions.fetch_add(delta); }
