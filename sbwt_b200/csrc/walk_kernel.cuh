@@ -822,6 +822,13 @@ __global__ void __launch_bounds__(kWalkThreads, COUNT ? 2 : WalkBlocks<STREAMING
                     bool hit = false;
                     typename Stepper<WIDE, LAY>::Load L;
                     ST.issue(L, col, c);
+                    { // the next code word, in place and behind the sector load (see the streaming CHAIN: a plain conditional
+                      // load after the step cost 11 % of the search-mode kernel's stall samples, profiles/r03m)
+                        const uint32_t np = pos + 1u, ph = np & 15u;
+                        if (ph == 0) cw = nx;
+                        asm volatile("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
+                                     : "+r"(nx) : "l"(P.codes + (np >> 4) + 1), "r"(ph));
+                    }
                     if (!ST.eval(L, col, c, ncol, hit)) ST.classic_step(col, c, ncol, hit, cblk);
                     else if (LAY == LAY_CLASSIC) cblk = split_pos<WIDE>((int64_t)col).blk;
                     miss = !hit; // [col, col] -> empty interval (SBWT.hh:433) / l != r (SBWT.hh:574)
@@ -848,8 +855,7 @@ __global__ void __launch_bounds__(kWalkThreads, COUNT ? 2 : WalkBlocks<STREAMING
                     if (!miss) {
                         col = ncol;
                         j++;
-                        pos++;
-                        if ((pos & 15u) == 0) { cw = nx; nx = __ldg(P.codes + (pos >> 4) + 1); }
+                        pos++; // (a step that fails ends the lane's run: cw may be one word ahead)
                     }
                 }
                 const bool ended = act && miss;
