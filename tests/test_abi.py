@@ -33,6 +33,12 @@ def test_count_outputs_host_logic():
     assert L.sbwt_gpu_count_outputs(off.ctypes.data, 5, 31) == 0 + 1 + 0 + 120 + 0
     assert L.sbwt_gpu_count_outputs(off.ctypes.data, 5, 6) == 0 + 26 + 0 + 145 + 25
     assert L.sbwt_gpu_count_outputs(off.ctypes.data, 0, 31) == 0
+    # large batches are counted on four threads (a pass over the offsets is bound by one core's memory bandwidth)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 300, size=2_500_001)
+    big = np.concatenate([[7], 7 + np.cumsum(lens)]).astype(np.int64)
+    for k in (1, 31, 64, 255):
+        assert L.sbwt_gpu_count_outputs(big.ctypes.data, lens.size, k) == int(np.maximum(lens - k + 1, 0).sum())
 
 
 def test_loader_rejects_bad_files(tmp_path):
