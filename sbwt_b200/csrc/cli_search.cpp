@@ -192,15 +192,15 @@ static int queue_sink(void* user, const char* text, int64_t n_bytes) {
     return 0;
 }
 
-static int64_t query_batch_multi(const vector<const sbwt::plain_matrix_sbwt_t*>& replicas, const vector<char>& ascii,
-                                 const vector<int64_t>& offsets, int64_t n, int mode, Writer& writer) {
+static int64_t query_batch_multi(const vector<const sbwt::plain_matrix_sbwt_t*>& replicas, const char* ascii,
+                                 const int64_t* offsets, int64_t n, int mode, Writer& writer) {
     const size_t D = replicas.size();
     vector<int64_t> cuts(D + 1, n);
     cuts[0] = 0;
     const int64_t total = offsets[(size_t)n] - offsets[0];
     for (size_t d = 1; d < D; d++) {
         const int64_t target = offsets[0] + total * (int64_t)d / (int64_t)D;
-        const int64_t c = std::lower_bound(offsets.begin(), offsets.begin() + n + 1, target) - offsets.begin();
+        const int64_t c = std::lower_bound(offsets, offsets + n + 1, target) - offsets;
         cuts[d] = std::min<int64_t>(n, std::max<int64_t>(cuts[d - 1], c));
     }
     vector<PieceQueue> queues(D);
@@ -210,7 +210,7 @@ static int64_t query_batch_multi(const vector<const sbwt::plain_matrix_sbwt_t*>&
         try {
             const int64_t r0 = cuts[d], nr = cuts[d + 1] - r0;
             if (nr > 0)
-                lookups[d] = replicas[d]->query_batch_text(ascii.data(), offsets.data() + r0, nr, mode, SBWT_GPU_CASE_UPPER, queue_sink, &queues[d]);
+                lookups[d] = replicas[d]->query_batch_text(ascii, offsets + r0, nr, mode, SBWT_GPU_CASE_UPPER, queue_sink, &queues[d]);
         } catch (...) { errors[d] = std::current_exception(); }
         std::lock_guard<std::mutex> g(queues[d].mu);
         queues[d].done = true;
@@ -264,18 +264,50 @@ static int64_t run_file(const string& infile, const string& outfile, const vecto
     // two batch buffers: batch i + 1 is parsed by a helper thread while the device answers batch i. A parse error
     // surfaces when its batch is due, after the output of everything before it has been written (as in the reference,
     // which parses and queries read by read)
+    // ... and copies it into page-locked memory there as well (parallel, off the critical path): the device then reads the
+    // batch by DMA straight from these buffers instead of through a staging copy made by the querying thread (6 ms per
+    // 64 MB batch, a third of the batch's turn: profiles/r03q)
     struct Batch {
         vector<char> ascii;
         vector<int64_t> offsets;
         int64_t n = 0;
         std::exception_ptr error;
+        char* p_ascii = nullptr;
+        int64_t* p_off = nullptr;
+        size_t cap_ascii = 0, cap_off = 0;
+        ~Batch() { sbwt_gpu_host_free(p_ascii); sbwt_gpu_host_free(p_off); }
     } batches[2];
+    const int copy_threads = std::max(1, std::min(opt.threads, 8));
+    auto stage = [&](Batch& b) {
+        if (b.n <= 0) return;
+        const size_t na = b.ascii.size(), no = b.offsets.size();
+        if (na > b.cap_ascii) {
+            sbwt_gpu_host_free(b.p_ascii); b.p_ascii = nullptr; b.cap_ascii = 0;
+            void* p = nullptr;
+            if (sbwt_gpu_host_alloc(na + na / 8 + 4096, &p)) throw std::runtime_error(sbwt_gpu_last_error());
+            b.p_ascii = (char*)p; b.cap_ascii = na + na / 8 + 4096;
+        }
+        if (no > b.cap_off) {
+            sbwt_gpu_host_free(b.p_off); b.p_off = nullptr; b.cap_off = 0;
+            void* p = nullptr;
+            if (sbwt_gpu_host_alloc((no + no / 8 + 512) * sizeof(int64_t), &p)) throw std::runtime_error(sbwt_gpu_last_error());
+            b.p_off = (int64_t*)p; b.cap_off = no + no / 8 + 512;
+        }
+        vector<std::thread> th;
+        for (int t = 1; t < copy_threads; t++)
+            th.emplace_back([&, t] { const size_t a = na * (size_t)t / (size_t)copy_threads, e = na * (size_t)(t + 1) / (size_t)copy_threads; memcpy(b.p_ascii + a, b.ascii.data() + a, e - a); });
+        memcpy(b.p_ascii, b.ascii.data(), na / (size_t)copy_threads);
+        memcpy(b.p_off, b.offsets.data(), no * sizeof(int64_t));
+        for (auto& x : th) x.join();
+    };
     auto parse = [&](Batch& b) {
-        try { b.n = reader.next_batch(opt.batch_bases, opt.batch_reads, b.ascii, b.offsets); }
+        try { b.n = reader.next_batch(opt.batch_bases, opt.batch_reads, b.ascii, b.offsets); stage(b); }
         catch (...) { b.error = std::current_exception(); b.n = 0; }
     };
     int64_t n_queries = 0;
+    long long first_parse_micros = cur_time_micros(), join_micros = 0;
     parse(batches[0]);
+    first_parse_micros = cur_time_micros() - first_parse_micros;
     for (int turn = 0;; turn ^= 1) {
         Batch& b = batches[turn];
         if (b.error) std::rethrow_exception(b.error);
@@ -284,8 +316,8 @@ static int64_t run_file(const string& infile, const string& outfile, const vecto
         const long long t0 = cur_time_micros();
         try {
             const int mode = streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH;
-            if (replicas.size() > 1) n_queries += query_batch_multi(replicas, b.ascii, b.offsets, b.n, mode, writer);
-            else n_queries += index.query_batch_text(b.ascii.data(), b.offsets.data(), b.n, mode, SBWT_GPU_CASE_UPPER, text_sink, &sink);
+            if (replicas.size() > 1) n_queries += query_batch_multi(replicas, b.p_ascii, b.p_off, b.n, mode, writer);
+            else n_queries += index.query_batch_text(b.p_ascii, b.p_off, b.n, mode, SBWT_GPU_CASE_UPPER, text_sink, &sink);
         } catch (const std::runtime_error&) {
             ahead.join();
             if (!sink.error.empty()) throw std::runtime_error(sink.error);
@@ -295,9 +327,15 @@ static int64_t run_file(const string& infile, const string& outfile, const vecto
             throw;
         }
         query_micros += cur_time_micros() - t0;
+        const long long tj = cur_time_micros();
         ahead.join();
+        join_micros += cur_time_micros() - tj;
     }
+    const long long tf = cur_time_micros();
     writer.finish();
+    if (getenv("SBWT_B200_CLI_TIMING"))
+        write_log("timing: first batch parsed in " + std::to_string(first_parse_micros / 1e6) + " s, device calls " + std::to_string(query_micros / 1e6) +
+                  " s, waiting for the parser " + std::to_string(join_micros / 1e6) + " s, closing the output " + std::to_string((cur_time_micros() - tf) / 1e6) + " s");
     {
         const double file_s = (double)(cur_time_micros() - file_t0) / 1e6;
         write_log("queries: " + std::to_string(n_queries) + " in " + std::to_string(file_s) + " s of parsing + querying + writing (index load excluded): " +
