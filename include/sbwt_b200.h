@@ -226,6 +226,9 @@ int sbwt_gpu_query_host_text(sbwt_gpu_session *s, const char *ascii, const int64
 /* Page-locked host memory for the buffers handed to sbwt_gpu_query_host: pinned buffers are
  * DMA'd directly, pageable ones are staged through the session's own pinned buffers. */
 int sbwt_gpu_host_alloc(size_t bytes, void **out);
+/* The same with the device whose context does the allocation named (a thread that never selected a device would
+ * otherwise create a context on device 0). The memory is usable with every device. */
+int sbwt_gpu_host_alloc_on(int device, size_t bytes, void **out);
 void sbwt_gpu_host_free(void *p);
 
 /* The packer alone (device buffers): 2-bit codes, 32 bases per u64 word, and one invalid bit

@@ -30,7 +30,7 @@ EXPORTS = [
     "sbwt_gpu_index_device_bytes", "sbwt_gpu_index_edges_only_at_group_starts", "sbwt_gpu_index_compact_layout", "sbwt_gpu_rank",
     "sbwt_gpu_session_create", "sbwt_gpu_session_destroy", "sbwt_gpu_count_outputs",
     "sbwt_gpu_query_host", "sbwt_gpu_query_host_i32", "sbwt_gpu_query_device", "sbwt_gpu_query_device_i32", "sbwt_gpu_search_batch", "sbwt_gpu_streaming_batch",
-    "sbwt_gpu_host_alloc", "sbwt_gpu_host_free", "sbwt_gpu_pack_device",
+    "sbwt_gpu_host_alloc", "sbwt_gpu_host_alloc_on", "sbwt_gpu_host_free", "sbwt_gpu_pack_device",
     "sbwt_gpu_query_device_counted", "sbwt_gpu_launch_count", "sbwt_gpu_sector_probe",
     "sbwt_gpu_session_set_timing", "sbwt_gpu_session_last_timing", "sbwt_gpu_index_get_precalc",
     "sbwt_gpu_index_set_table_length", "sbwt_gpu_index_table_length",

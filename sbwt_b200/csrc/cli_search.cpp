@@ -36,6 +36,28 @@
 #include <zlib.h>
 
 #include "SBWT.hh"
+
+// The readers write a batch's bases straight into page-locked memory (the device then takes them by DMA, without a
+// staging copy): the allocator fastx.hpp gives its batch vector. g_pinned_device is the device whose context allocates.
+static int g_pinned_device = 0;
+template <typename T>
+struct PinnedAllocator {
+    typedef T value_type;
+    PinnedAllocator() = default;
+    template <typename U>
+    PinnedAllocator(const PinnedAllocator<U>&) {}
+    T* allocate(size_t n) {
+        void* p = nullptr;
+        if (sbwt_gpu_host_alloc_on(g_pinned_device, n * sizeof(T), &p)) throw std::bad_alloc();
+        return (T*)p;
+    }
+    void deallocate(T* p, size_t) { sbwt_gpu_host_free(p); }
+    template <typename U>
+    bool operator==(const PinnedAllocator<U>&) const { return true; }
+    template <typename U>
+    bool operator!=(const PinnedAllocator<U>&) const { return false; }
+};
+#define SBWT_B200_ASCII_ALLOCATOR PinnedAllocator
 #include "fastx.hpp"
 
 using std::string;
@@ -264,44 +286,33 @@ static int64_t run_file(const string& infile, const string& outfile, const vecto
     // two batch buffers: batch i + 1 is parsed by a helper thread while the device answers batch i. A parse error
     // surfaces when its batch is due, after the output of everything before it has been written (as in the reference,
     // which parses and queries read by read)
-    // ... and copies it into page-locked memory there as well (parallel, off the critical path): the device then reads the
-    // batch by DMA straight from these buffers instead of through a staging copy made by the querying thread (6 ms per
-    // 64 MB batch, a third of the batch's turn: profiles/r03q)
+    // (the bases land in page-locked memory as they are parsed -- PinnedAllocator above --, the offsets are copied there)
     struct Batch {
-        vector<char> ascii;
+        sbwt_b200::AsciiVec ascii;
         vector<int64_t> offsets;
         int64_t n = 0;
         std::exception_ptr error;
-        char* p_ascii = nullptr;
         int64_t* p_off = nullptr;
-        size_t cap_ascii = 0, cap_off = 0;
-        ~Batch() { sbwt_gpu_host_free(p_ascii); sbwt_gpu_host_free(p_off); }
+        size_t cap_off = 0;
+        ~Batch() { sbwt_gpu_host_free(p_off); }
     } batches[2];
-    const int copy_threads = std::max(1, std::min(opt.threads, 8));
     auto stage = [&](Batch& b) {
         if (b.n <= 0) return;
-        const size_t na = b.ascii.size(), no = b.offsets.size();
-        if (na > b.cap_ascii) {
-            sbwt_gpu_host_free(b.p_ascii); b.p_ascii = nullptr; b.cap_ascii = 0;
-            void* p = nullptr;
-            if (sbwt_gpu_host_alloc(na + na / 8 + 4096, &p)) throw std::runtime_error(sbwt_gpu_last_error());
-            b.p_ascii = (char*)p; b.cap_ascii = na + na / 8 + 4096;
-        }
+        const size_t no = b.offsets.size();
         if (no > b.cap_off) {
             sbwt_gpu_host_free(b.p_off); b.p_off = nullptr; b.cap_off = 0;
             void* p = nullptr;
-            if (sbwt_gpu_host_alloc((no + no / 8 + 512) * sizeof(int64_t), &p)) throw std::runtime_error(sbwt_gpu_last_error());
+            if (sbwt_gpu_host_alloc_on(g_pinned_device, (no + no / 8 + 512) * sizeof(int64_t), &p)) throw std::runtime_error(sbwt_gpu_last_error());
             b.p_off = (int64_t*)p; b.cap_off = no + no / 8 + 512;
         }
-        vector<std::thread> th;
-        for (int t = 1; t < copy_threads; t++)
-            th.emplace_back([&, t] { const size_t a = na * (size_t)t / (size_t)copy_threads, e = na * (size_t)(t + 1) / (size_t)copy_threads; memcpy(b.p_ascii + a, b.ascii.data() + a, e - a); });
-        memcpy(b.p_ascii, b.ascii.data(), na / (size_t)copy_threads);
         memcpy(b.p_off, b.offsets.data(), no * sizeof(int64_t));
-        for (auto& x : th) x.join();
     };
     auto parse = [&](Batch& b) {
-        try { b.n = reader.next_batch(opt.batch_bases, opt.batch_reads, b.ascii, b.offsets); stage(b); }
+        try {
+            if (b.ascii.capacity() == 0) b.ascii.reserve((size_t)opt.batch_bases + ((size_t)1 << 20)); // (one page-locked allocation instead of a doubling sequence)
+            b.n = reader.next_batch(opt.batch_bases, opt.batch_reads, b.ascii, b.offsets);
+            stage(b);
+        }
         catch (...) { b.error = std::current_exception(); b.n = 0; }
     };
     int64_t n_queries = 0;
@@ -316,8 +327,8 @@ static int64_t run_file(const string& infile, const string& outfile, const vecto
         const long long t0 = cur_time_micros();
         try {
             const int mode = streaming ? SBWT_GPU_MODE_STREAMING : SBWT_GPU_MODE_SEARCH;
-            if (replicas.size() > 1) n_queries += query_batch_multi(replicas, b.p_ascii, b.p_off, b.n, mode, writer);
-            else n_queries += index.query_batch_text(b.p_ascii, b.p_off, b.n, mode, SBWT_GPU_CASE_UPPER, text_sink, &sink);
+            if (replicas.size() > 1) n_queries += query_batch_multi(replicas, b.ascii.data(), b.p_off, b.n, mode, writer);
+            else n_queries += index.query_batch_text(b.ascii.data(), b.p_off, b.n, mode, SBWT_GPU_CASE_UPPER, text_sink, &sink);
         } catch (const std::runtime_error&) {
             ahead.join();
             if (!sink.error.empty()) throw std::runtime_error(sink.error);
@@ -447,6 +458,7 @@ static int search_main(int argc, char** argv) {
         return 1;
     }
     if (devices.empty()) devices.push_back(device);
+    g_pinned_device = devices[0];
     vector<std::unique_ptr<sbwt::plain_matrix_sbwt_t>> owned;
     vector<const sbwt::plain_matrix_sbwt_t*> replicas;
     for (size_t d = 0; d < devices.size(); d++) {

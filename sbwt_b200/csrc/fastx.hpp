@@ -30,7 +30,15 @@
 
 #include <zlib.h>
 
+// The bases of a batch are written into a std::vector<char, SBWT_B200_ASCII_ALLOCATOR<char>>: std::allocator unless the
+// including file defines another one first (the command line uses page-locked memory, which the device reads by DMA).
+#ifndef SBWT_B200_ASCII_ALLOCATOR
+#define SBWT_B200_ASCII_ALLOCATOR std::allocator
+#endif
+
 namespace sbwt_b200 {
+
+typedef std::vector<char, SBWT_B200_ASCII_ALLOCATOR<char>> AsciiVec;
 
 enum class SeqFormat { FASTA, FASTQ };
 
@@ -102,7 +110,7 @@ class FastxReader {
         return true;
     }
     // getline into out (appending); returns nothing -- callers test is_eof like the reference does
-    inline void getline_append(std::vector<char>* out) {
+    inline void getline_append(AsciiVec* out) {
         for (;;) {
             char c;
             if (!get(c)) return;
@@ -146,7 +154,7 @@ public:
     }
 
     // Appends the next read's bases to `ascii`; returns its length, 0 at end of file.
-    int64_t next_read(std::vector<char>& ascii) {
+    int64_t next_read(AsciiVec& ascii) {
         if (is_eof) return 0;
         const size_t start = ascii.size();
         if (format == SeqFormat::FASTA) {
@@ -185,7 +193,7 @@ public:
     // A malformed record does not swallow the reads in front of it: they are returned as a (short) batch and the error is
     // raised by the next call -- the reference answers and prints read by read, so everything before the bad record has
     // been written when it throws (sbwt_search.cpp:45-65 over SeqIO.hh:255-360).
-    int64_t next_batch(int64_t max_bases, int64_t max_reads, std::vector<char>& ascii, std::vector<int64_t>& offsets) {
+    int64_t next_batch(int64_t max_bases, int64_t max_reads, AsciiVec& ascii, std::vector<int64_t>& offsets) {
         ascii.clear();
         offsets.clear();
         offsets.push_back(0);
@@ -415,7 +423,7 @@ class ParallelFastxReader {
         });
     }
 
-    int64_t from_serial(int64_t max_bases, int64_t max_reads, std::vector<char>& ascii, std::vector<int64_t>& offsets) {
+    int64_t from_serial(int64_t max_bases, int64_t max_reads, AsciiVec& ascii, std::vector<int64_t>& offsets) {
         return serial->next_batch(max_bases, max_reads, ascii, offsets);
     }
 
@@ -479,7 +487,7 @@ public:
     }
 
     // Same contract as FastxReader::next_batch.
-    int64_t next_batch(int64_t max_bases, int64_t max_reads, std::vector<char>& ascii, std::vector<int64_t>& offsets) {
+    int64_t next_batch(int64_t max_bases, int64_t max_reads, AsciiVec& ascii, std::vector<int64_t>& offsets) {
         if (serial) return from_serial(max_bases, max_reads, ascii, offsets);
         offsets.clear();
         offsets.push_back(0);

@@ -1741,6 +1741,13 @@ extern "C" int sbwt_gpu_host_alloc(size_t bytes, void** out) {
     CU(cudaMallocHost(out, bytes ? bytes : 16));
     return 0;
 }
+extern "C" int sbwt_gpu_host_alloc_on(int device, size_t bytes, void** out) {
+    if (!out) return set_error("null argument");
+    if (device < 0 || device >= sbwt_gpu_device_count()) return set_error("invalid device %d", device);
+    DeviceGuard guard(device); // (no context is created on another device by a thread that never chose one)
+    CU(cudaMallocHost(out, bytes ? bytes : 16));
+    return 0;
+}
 extern "C" void sbwt_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------ probe
