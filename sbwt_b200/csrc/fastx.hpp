@@ -348,23 +348,26 @@ class ParallelFastxReader {
     };
     // scratch kept across batches (a 64 MB batch of short reads has millions of lines: allocating, zero-filling and
     // page-faulting these arrays anew for every batch cost a third of the parser's time)
-    struct LineBuf {
-        std::unique_ptr<Line[]> p;
+    template <typename T>
+    struct RawBuf {
+        std::unique_ptr<T[]> p;
         size_t cap = 0, n = 0;
         void resize(size_t m) { // contents are not kept and not initialised
-            if (m > cap) { cap = m + m / 4 + 1024; p.reset(new Line[cap]); }
+            if (m > cap) { cap = m + m / 4 + 1024; p.reset(new T[cap]); }
             n = m;
         }
         size_t size() const { return n; }
-        Line* data() { return p.get(); }
-        const Line& operator[](size_t i) const { return p[i]; }
+        T* data() { return p.get(); }
+        const T* data() const { return p.get(); }
+        const T& operator[](size_t i) const { return p[i]; }
     };
+    typedef RawBuf<Line> LineBuf;
     struct Rec {
         size_t first_line, n_lines; // sequence lines
         int64_t len;
     };
     mutable LineBuf lines_buf;
-    std::vector<Rec> recs_buf;
+    RawBuf<Rec> recs_buf;
     mutable std::vector<std::vector<size_t>> nl_buf;
     double file_bytes_per_base = 1.5; // how much of the file a batch of max_bases covers: learnt from the previous batch
 
@@ -421,6 +424,62 @@ class ParallelFastxReader {
                 }
             }
         });
+    }
+
+    // Every record the window's lines hold, in parallel over slices of the lines. A FASTA record is a header line and
+    // the lines up to the next header; the last record of the window runs to its end (whether it is whole is the
+    // caller's business). Returns false when the window holds a line the serial parser has to judge -- an empty line,
+    // a header directly behind a header, an empty FASTQ header or sequence line -- wherever it is: the caller then
+    // hands everything from `cur` on to the serial parser, which is always right and only slower.
+    bool form_records(const LineBuf& lines, RawBuf<Rec>& recs) const {
+        const size_t nl = lines.size();
+        const Line* L = lines.data();
+        std::atomic<bool> bad{false};
+        if (format == SeqFormat::FASTQ) {
+            const size_t n = nl / 4;
+            recs.resize(n);
+            Rec* R = recs.data();
+            parallel_for(n, [=, &bad](size_t a, size_t b, size_t) {
+                for (size_t r = a; r < b; r++) {
+                    const Line& h = L[4 * r];
+                    const Line& q = L[4 * r + 1];
+                    if (h.stop() == h.start || q.stop() == q.start) bad = true;
+                    R[r] = Rec{4 * r + 1, 1, (int64_t)(q.stop() - q.start)};
+                }
+            });
+            return !bad;
+        }
+        const size_t T = (size_t)std::max(1, threads);
+        std::vector<size_t> cnt(T + 1, 0);
+        size_t* cntp = cnt.data();
+        if (nl == 0 || !L[0].header()) { recs.resize(0); return nl == 0; }
+        parallel_for(nl, [=, &bad](size_t a, size_t b, size_t t) {
+            size_t c = 0;
+            for (size_t i = a; i < b; i++) {
+                if (L[i].stop() == L[i].start) bad = true; // an empty line
+                if (L[i].header()) {
+                    c++;
+                    if (i + 1 < nl && L[i + 1].header()) bad = true; // an empty sequence
+                }
+            }
+            cntp[t + 1] = c;
+        });
+        if (bad) return false;
+        for (size_t t = 0; t < T; t++) cnt[t + 1] += cnt[t];
+        recs.resize(cnt[T]);
+        Rec* R = recs.data();
+        parallel_for(nl, [=](size_t a, size_t b, size_t t) {
+            size_t r = cntp[t], i = a;
+            while (i < b && !L[i].header()) i++; // (the lines before belong to a record of the slice in front)
+            while (i < b) {
+                size_t j = i + 1;
+                int64_t len = 0;
+                while (j < nl && !L[j].header()) { len += (int64_t)(L[j].stop() - L[j].start); j++; }
+                R[r++] = Rec{i + 1, j - (i + 1), len};
+                i = j;
+            }
+        });
+        return true;
     }
 
     int64_t from_serial(int64_t max_bases, int64_t max_reads, AsciiVec& ascii, std::vector<int64_t>& offsets) {
@@ -495,7 +554,8 @@ public:
         z_fill(1);
         if (cur >= size) { ascii.clear(); return 0; }
         LineBuf& lines = lines_buf;
-        std::vector<Rec>& recs = recs_buf;
+        RawBuf<Rec>& recs = recs_buf;
+        size_t n_take = 0; // records of the window that make the batch
         size_t window = (size_t)((double)max_bases * file_bytes_per_base) + ((size_t)1 << 20);
         bool anomaly = false;
         size_t next_cur = cur;
@@ -504,50 +564,33 @@ public:
             const size_t wend = std::min(size, cur + window);
             const bool at_eof = wend == size && all_here;
             scan_lines(cur, wend, lines);
-            recs.clear();
-            anomaly = false;
-            int64_t bases = 0;
+            anomaly = !form_records(lines, recs);
             bool full = false; // the batch reached max_reads / max_bases
             next_cur = cur;
-            size_t i = 0;
-            const size_t nl = lines.size();
-            if (format == SeqFormat::FASTQ) {
-                while (i + 4 <= nl) {
-                    if (lines[i].stop() == lines[i].start || lines[i + 1].stop() == lines[i + 1].start) { anomaly = true; break; }
-                    recs.push_back(Rec{i + 1, 1, (int64_t)(lines[i + 1].stop() - lines[i + 1].start)});
-                    bases += recs.back().len;
-                    i += 4;
-                    next_cur = i < nl ? lines[i].start : lines[i - 1].stop() + 1;
-                    if ((int64_t)recs.size() >= max_reads || bases >= max_bases) { full = true; break; }
+            n_take = 0;
+            if (!anomaly) {
+                const size_t nl = lines.size(), n_all = recs.size();
+                const Line* L = lines.data();
+                const Rec* R = recs.data();
+                const size_t after_all = nl ? L[nl - 1].stop() + 1 : cur; // first byte behind the window's last complete line
+                // FASTA: the window's last record ends where the lines end -- whole only at the end of the file, when its
+                // last line is terminated and it has a sequence; anything else at the end of the file is the serial parser's
+                size_t n_whole = n_all;
+                bool tail_anomaly = false;
+                if (format == SeqFormat::FASTA && n_all > 0) {
+                    const bool last_whole = at_eof && after_all == size && R[n_all - 1].n_lines > 0;
+                    if (!last_whole) { n_whole = n_all - 1; tail_anomaly = at_eof; }
                 }
+                int64_t bases = 0;
+                for (size_t r = 0; r < n_whole; r++) {
+                    bases += R[r].len;
+                    if ((int64_t)(r + 1) >= max_reads || bases >= max_bases) { full = true; n_take = r + 1; break; }
+                }
+                if (!full) { n_take = n_whole; anomaly = tail_anomaly; }
+                if (format == SeqFormat::FASTQ) next_cur = n_take == 0 ? cur : (4 * n_take < nl ? L[4 * n_take].start : L[4 * n_take - 1].stop() + 1);
+                else next_cur = n_take == 0 ? cur : (n_take < n_all ? L[R[n_take].first_line - 1].start : after_all);
                 // a tail that is not a whole record (or lacks its last '\n') is the serial parser's business
                 if (!full && !anomaly && at_eof && next_cur < size) anomaly = true;
-            } else {
-                while (i < nl) {
-                    // line i is a header (the first byte of a record is '>' by construction)
-                    size_t j = i + 1;
-                    int64_t len = 0;
-                    bool bad = lines[i].stop() == lines[i].start; // cannot happen ('>' is there), kept for symmetry
-                    while (j < nl && !lines[j].header()) {
-                        if (lines[j].stop() == lines[j].start) { bad = true; break; }
-                        len += (int64_t)(lines[j].stop() - lines[j].start);
-                        j++;
-                    }
-                    if (bad || (j < nl && j == i + 1)) { anomaly = true; break; } // empty line / empty sequence
-                    const size_t after = j < nl ? lines[j].start : lines[j - 1].stop() + 1;
-                    if (j == nl && !(at_eof && after == size)) {
-                        // the record may go on beyond the window; at the end of the file: unterminated last line
-                        if (at_eof) anomaly = true;
-                        break;
-                    }
-                    if (j == i + 1) { anomaly = true; break; } // a header at the very end of the file
-                    recs.push_back(Rec{i + 1, j - (i + 1), len});
-                    bases += len;
-                    i = j;
-                    next_cur = after;
-                    if ((int64_t)recs.size() >= max_reads || bases >= max_bases) { full = true; break; }
-                }
-                if (!full && !anomaly && at_eof && next_cur < size) anomaly = true; // bytes after the last '\n'
             }
             if (anomaly || full || at_eof) break;
             window *= 2; // the window ended before the batch was full
@@ -557,7 +600,7 @@ public:
             serial.reset(new FastxReader(filename, format, data + cur, size - cur, gzf)); // (gzip: continues with the rest of the stream)
             return from_serial(max_bases, max_reads, ascii, offsets);
         }
-        const size_t n = recs.size();
+        const size_t n = n_take;
         offsets.resize(n + 1);
         for (size_t r = 0; r < n; r++) offsets[r + 1] = offsets[r] + recs[r].len;
         ascii.resize((size_t)offsets[n]); // (not cleared first: only growth beyond the previous batch is zero-filled)

@@ -93,6 +93,30 @@ def test_wellformed_files_give_identical_batches(exe, tmp_path, kind):
         assert ag == a and bg_ == a, (kind, "bgzf", max_bases, max_reads, threads)
 
 
+def test_random_batch_shapes_and_thread_counts(exe, tmp_path):
+    """The records of a window are formed by slices of its lines in parallel: batch limits, windows and slice boundaries
+    that fall anywhere inside records (multi-line FASTA of uneven line widths, FASTQ), 1 to 16 threads, also with a
+    malformed record late in the file (the reads in front of it are still delivered, then the same error)."""
+    rng = np.random.default_rng(77)
+    recs = []
+    for i in range(4000):
+        s_ = rand_seq(rng, int(rng.integers(1, 900)))
+        w = int(rng.integers(1, 120))
+        recs.append(b">r%d some text\n" % i + b"".join(s_[j:j + w] + b"\n" for j in range(0, len(s_), w)))
+    fa = b"".join(recs)
+    files = {"m.fna": fa, "q.fq": fastq(rng, 4000, max_len=700), "bad_late.fna": fa + b">x\n>y\nACGT\n", "bad_mid.fna": b"".join(recs[:2500]) + b">e\n\nAC\n" + b"".join(recs[2500:])}
+    for name, data in files.items():
+        path = str(tmp_path / name)
+        open(path, "wb").write(data)
+        for _ in range(12):
+            mb = int(rng.choice([1, 50, 997, 20_000, 333_333, 1 << 30]))
+            mr = int(rng.choice([1, 3, 64, 1000, 1 << 30]))
+            th = int(rng.choice([1, 2, 3, 7, 16]))
+            a, b = both(exe, path, mb, mr, th)
+            assert a == b, (name, mb, mr, th, a[:200], b[:200])
+            assert a.startswith("ERROR") == name.startswith("bad"), (name, a[:200])
+
+
 def test_long_reads_exceed_the_scan_window(exe, tmp_path):
     rng = np.random.default_rng(5)
     path = str(tmp_path / "long.fna")
